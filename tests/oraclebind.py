@@ -1,0 +1,102 @@
+"""ctypes bindings for the plain-C oracle (oracle/liblsd_oracle.so) — test infrastructure."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "liblsd_oracle.so")
+LSD_PARAMS = dict(sca=0.3, sig=0.6, angThre=22.5, denThre=0.7, pseBin=1024)
+STAT_FIELDS = ["cells", "live_seeds", "grows", "grown_px", "small", "regrows", "rrr_passes", "nfa_calls",
+               "nfa_px", "rejects", "accepts"]
+
+
+class Stats(C.Structure):
+    _fields_ = [(f, C.c_longlong) for f in STAT_FIELDS]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            build()
+        L = C.CDLL(SO)
+        L.lsdo_lsd.restype = C.c_int
+        L.lsdo_lsd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.lsdo_gauss_taps.restype = C.c_int
+        L.lsdo_gauss_taps.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_int]
+        L.lsdo_map_cache.restype = None
+        L.lsdo_map_cache.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+        L.lsdo_fa_scores.restype = C.c_int
+        L.lsdo_fa_scores.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def lsd(map_u8, want_maps=True, want_line_im=True, max_lines=65536, **kw):
+    p = dict(LSD_PARAMS); p.update(kw)
+    m = np.ascontiguousarray(map_u8, dtype=np.uint8)
+    rows, cols = m.shape
+    W, H = int(np.floor(cols * p["sca"])), int(np.floor(rows * p["sca"]))
+    out = {}
+    if want_maps:
+        out.update(map_out=np.zeros((rows, cols), np.uint8), gauss=np.zeros((H, W)), mag=np.zeros((H, W)),
+                   deg=np.zeros((H, W)), used=np.zeros((H, W), np.uint8), labels=np.zeros((H, W), np.int32),
+                   seeds=np.zeros((H * W, 3), np.int32))
+    if want_line_im:
+        out["line_im"] = np.zeros((rows, cols), np.uint8)
+    rects = np.zeros((max_lines, 13)); lines = np.zeros((max_lines, 10))
+    ns = C.c_int(0); st = Stats()
+    g = out.get
+    n = lib().lsdo_lsd(_p(m), cols, rows, p["sca"], p["sig"], p["angThre"], p["denThre"], p["pseBin"],
+                       _p(g("map_out")), _p(g("gauss")), _p(g("mag")), _p(g("deg")), _p(g("used")), _p(g("labels")),
+                       _p(g("seeds")), H * W if want_maps else 0, C.byref(ns), _p(rects), _p(lines), max_lines,
+                       _p(g("line_im")), C.byref(st))
+    if want_maps:
+        out["seeds"] = out["seeds"][:ns.value].copy()
+    out["n"] = n
+    out["rects"] = rects[:n].copy(); out["lines"] = lines[:n].copy()
+    out["stats"] = {f: getattr(st, f) for f in STAT_FIELDS}
+    return out
+
+
+def gauss_taps(sca=0.3, sig=0.6):
+    buf = np.zeros(3 * 64)
+    h = lib().lsdo_gauss_taps(sca, sig, _p(buf), len(buf))
+    return h, buf[:3 * (2 * h + 1)].reshape(3, 2 * h + 1).copy()
+
+
+def map_cache(map_u8, res):
+    m = np.ascontiguousarray(map_u8, dtype=np.uint8)
+    rows, cols = m.shape
+    out = np.zeros((rows, cols))
+    lib().lsdo_map_cache(_p(m), cols, rows, float(res), _p(out))
+    return out
+
+
+def fa_scores(scan_lines, map_lines, pts, mc, lidar_pose, last_pose):
+    sl = np.ascontiguousarray(scan_lines, np.float64).reshape(-1, 10)
+    ml = np.ascontiguousarray(map_lines, np.float64).reshape(-1, 10)
+    pt = np.ascontiguousarray(pts, np.float64).reshape(-1, 2)
+    mc = np.ascontiguousarray(mc, np.float64)
+    rows, cols = mc.shape
+    lp = np.asarray(lidar_pose, np.float64); la = np.asarray(last_pose, np.float64)
+    cap = max(4 * len(sl) * len(ml), 4)
+    idx = np.zeros((cap, 3), np.int32); val = np.zeros((cap, 4))
+    n = lib().lsdo_fa_scores(_p(sl), len(sl), _p(ml), len(ml), _p(pt), len(pt), _p(mc), cols, rows, _p(lp), _p(la),
+                             _p(idx), _p(val), cap)
+    return idx[:n].copy(), val[:n].copy()
