@@ -1,0 +1,137 @@
+/* lsdb200.h — C ABI of the B200-native LSD / association hot path (liblsdb200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point
+ * names the reference interface it replaces (paths relative to the reference repo):
+ *
+ *   lsdb_lsd / lsdb_batch_*   <- mylsd::myLineSegmentDetector          LSD/myLSD.h:132, LSD/myLSD.cpp:129-376
+ *                                 (stage functions LSD/myLSD.h:133-141 have no external callers)
+ *   lsdb_line                 <- structLinesInfo                        LSD/baseFunc.h:33-44
+ *   lsdb_lsd_params           <- lsd_sca/lsd_sig/lsd_angThre/lsd_denThre/pseBin   LSD/baseFunc.h:64-68
+ *   lsdb_fa_map_* / lsdb_fa_score <- the scoring half of myfa::FeatureAssociation
+ *                                 LSD/myFA.h:83-87, LSD/myFA.cpp:27-63 (dispatch), :186-272
+ *                                 (thread_ScanToMapMatch), :274-305, :307-355, :357-396
+ *   lsdb_hypothesis           <- structScore                            LSD/myFA.h:49-54
+ *
+ * There is no CPU fallback: every compute entry point fails with LSDB_ERR_NO_DEVICE / LSDB_ERR_CUDA
+ * when no sm_100 device is usable.  All functions return LSDB_OK (0) or an error code; the text of
+ * the last error is available from lsdb_last_error().  A context is not thread-safe; use one per
+ * host thread / GPU.
+ */
+#ifndef LSDB200_H
+#define LSDB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSDB_OK 0
+#define LSDB_ERR_CUDA 1       /* a CUDA call or kernel failed */
+#define LSDB_ERR_ARG 2        /* invalid argument */
+#define LSDB_ERR_CAPACITY 3   /* an output/region capacity was exceeded (see message) */
+#define LSDB_ERR_TIMEOUT 4    /* device-side watchdog fired (ordered-commit pipeline stalled) */
+#define LSDB_ERR_NO_DEVICE 5  /* no usable CUDA device */
+
+typedef struct lsdb_ctx lsdb_ctx;
+typedef struct lsdb_batch lsdb_batch;
+typedef struct lsdb_fa_map lsdb_fa_map;
+
+/* arguments 4-8 of myLineSegmentDetector (LSD/myLSD.h:132); defaults LSD/baseFunc.h:64-68 */
+typedef struct {
+    double sca;      /* 0.3  (the 3-phase Gaussian is only defined for 0.3, LSD/baseFunc.h:64) */
+    double sig;      /* 0.6  */
+    double angThre;  /* 22.5 */
+    double denThre;  /* 0.7  */
+    int pseBin;      /* 1024 */
+    int _pad;
+} lsdb_lsd_params;
+
+/* structLinesInfo, field for field (LSD/baseFunc.h:33-44); sizeof == 80 like the reference's */
+typedef struct {
+    double k, b, dx, dy, x1, y1, x2, y2, len;
+    int orient;
+    int _pad;
+} lsdb_line;
+
+/* the fitted rectangle of an accepted region, after the 1/sca rescale (structRec, LSD/myLSD.h:78-92) */
+typedef struct {
+    double x1, y1, x2, y2, wid, cX, cY, deg, dx, dy, p, prec, logNFA;
+} lsdb_rect;
+
+enum { LSDB_STAGE_STENCIL = 0, LSDB_STAGE_ORDER = 1, LSDB_STAGE_GROW = 2, LSDB_NSTAGES = 3 };
+
+typedef struct {
+    long long cells, live_seeds, grows, grown_px, small, regrows, rrr_passes, nfa_calls, nfa_px,
+        rejects, accepts, spec_evals, respec_evals, chunks;
+} lsdb_stats;
+
+/* ---- context ---- */
+/* `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private stream. */
+int lsdb_create(lsdb_ctx** out, int device, void* stream);
+void lsdb_destroy(lsdb_ctx* ctx);
+const char* lsdb_last_error(const lsdb_ctx* ctx);
+const char* lsdb_version(void);
+
+/* ---- LSD: batched, device-resident (the path bench.py times) ---- */
+/* Allocates every device buffer for n_maps maps of the given sizes once; reusable across runs. */
+int lsdb_batch_create(lsdb_ctx* ctx, int n_maps, const int* cols, const int* rows,
+                      const lsdb_lsd_params* params, int max_lines_per_map, lsdb_batch** out);
+void lsdb_batch_destroy(lsdb_batch* b);
+/* host -> device copy of the occupancy grids (maps[i] = rows[i]*cols[i] u8, row-major), async */
+int lsdb_batch_upload(lsdb_batch* b, const uint8_t* const* maps);
+/* enqueue remap+Gaussian+gradient, pseudo-ordering and the region/rectangle/NFA pipeline */
+int lsdb_batch_run(lsdb_batch* b);
+/* wait for the stream and check device-side error flags */
+int lsdb_batch_sync(lsdb_batch* b);
+/* device -> host: counts[n_maps]; lines[n_maps][max_lines_per_map] and rects (same shape) may be NULL.
+ * Implies lsdb_batch_sync.  Lines are produced by the epilogue of LSD/myLSD.cpp:282-368. */
+int lsdb_batch_download(lsdb_batch* b, int* counts, lsdb_line* lines, lsdb_rect* rects);
+/* rasterise map i's segments the way LSD/myLSD.cpp:296-355 fills lineIm (rows*cols u8, 0/255) */
+int lsdb_batch_line_image(lsdb_batch* b, int i, uint8_t* line_im);
+/* intermediate planes of map i for parity tests; every pointer may be NULL.
+ *   mag/deg : H'*W' f64 (magMap/degMap, LSD/myLSD.cpp:146-147); used : H'*W' u8 (usedMap, :145);
+ *   labels : H'*W' int32 (accept index + 1; reference regIdx == labels & 0xFF, :214,261);
+ *   seeds : sorted seed list as linear pixel indices y*W'+x (binCell after qsort, :204) */
+int lsdb_batch_planes(lsdb_batch* b, int i, double* mag, double* deg, uint8_t* used, int32_t* labels,
+                      int32_t* seeds, int max_seeds, int* n_seeds, double* max_grad);
+/* per-stage device time of the last lsdb_batch_run, CUDA events on the context stream */
+int lsdb_batch_stage_ms(lsdb_batch* b, float* ms /* [LSDB_NSTAGES] */);
+int lsdb_batch_stats(lsdb_batch* b, lsdb_stats* total);
+/* number of kernel launches issued by the last lsdb_batch_run */
+int lsdb_batch_launches(const lsdb_batch* b);
+
+/* ---- LSD: one map, host buffers in / host buffers out (what the myLSD.h wrapper calls) ---- */
+/* map is NOT modified; map_remapped (nullable) receives the in-place remap the reference applies to
+ * its caller's Mat (LSD/myLSD.cpp:135-142); line_im (nullable) = rows*cols u8. */
+int lsdb_lsd(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, const lsdb_lsd_params* params,
+             lsdb_line* lines, int max_lines, int* n_lines, uint8_t* line_im, uint8_t* map_remapped);
+
+/* ---- association scoring ---- */
+/* structScore (LSD/myFA.h:49-54) plus the indices that identify the hypothesis */
+typedef struct {
+    int frame, i_scan, i_map, i_pair; /* i_pair = 1..4, the endpoint pairing of LSD/myFA.cpp:194-235 */
+    double x, y, ang, score;          /* score = +inf when gated out / < 70 % of points in the map */
+} lsdb_hypothesis;
+
+/* uploads mapCache (rows*cols f64 metres, output of createMapCache) and the map's LSD lines once */
+int lsdb_fa_map_create(lsdb_ctx* ctx, const double* map_cache, int cols, int rows,
+                       const lsdb_line* map_lines, int n_map_lines, lsdb_fa_map** out);
+void lsdb_fa_map_destroy(lsdb_fa_map* m);
+/* Scores every (scan line, map line, pairing) triple that passes the reference's length filter
+ * (LSD/myFA.cpp:29-41) for n_frames scan frames in one launch.
+ *   scan_lines : concatenated per frame, scan_line_off[n_frames+1] offsets
+ *   scan_pts   : concatenated (x,y) pairs (FS.scanImPoint), scan_pt_off[n_frames+1] offsets (in points)
+ *   lidar_pose : [n_frames][2]   (already rounded as LSD/main_on_windows.cpp:229-230 does)
+ *   last_pose  : [n_frames][3]   (x == -1 disables the 60 px gate, LSD/myFA.cpp:330)
+ * Output: up to max_hyp records in (frame, i_scan, i_map, i_pair) order; *n_hyp = number produced. */
+int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int n_frames, const lsdb_line* scan_lines,
+                  const int* scan_line_off, const double* scan_pts, const int* scan_pt_off,
+                  const double* lidar_pose, const double* last_pose, lsdb_hypothesis* out, int max_hyp,
+                  int* n_hyp);
+/* device time of the last lsdb_fa_score kernel (ms) */
+float lsdb_fa_last_ms(const lsdb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

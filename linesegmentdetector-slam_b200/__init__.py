@@ -1,0 +1,266 @@
+"""Python (ctypes) face of liblsdb200.so — the B200-native LSD / association hot path.
+
+The product is the C-ABI library declared in include/lsdb200.h; this module only marshals numpy
+buffers into it for tests, bench.py and smoke().  There is no CPU fallback: importing works
+anywhere, but creating a Context without the built library or without an sm_100 GPU raises.
+
+Load it by path (the directory name is not a Python identifier):
+    from __graft_entry__ import load_package; lsdb = load_package()
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "liblsdb200.so")
+LSD_DEFAULTS = dict(sca=0.3, sig=0.6, angThre=22.5, denThre=0.7, pseBin=1024)  # LSD/baseFunc.h:64-68
+ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "CAPACITY", 4: "TIMEOUT", 5: "NO_DEVICE"}
+STAGES = ("stencil", "order", "grow")
+STAT_FIELDS = ["cells", "live_seeds", "grows", "grown_px", "small", "regrows", "rrr_passes", "nfa_calls", "nfa_px",
+               "rejects", "accepts", "spec_evals", "respec_evals", "chunks"]
+
+LINE_DTYPE = np.dtype([("k", "f8"), ("b", "f8"), ("dx", "f8"), ("dy", "f8"), ("x1", "f8"), ("y1", "f8"), ("x2", "f8"),
+                       ("y2", "f8"), ("len", "f8"), ("orient", "i4"), ("_pad", "i4")])
+RECT_FIELDS = ["x1", "y1", "x2", "y2", "wid", "cX", "cY", "deg", "dx", "dy", "p", "prec", "logNFA"]
+HYP_DTYPE = np.dtype([("frame", "i4"), ("i_scan", "i4"), ("i_map", "i4"), ("i_pair", "i4"), ("x", "f8"), ("y", "f8"),
+                      ("ang", "f8"), ("score", "f8")])
+
+
+class LsdbError(RuntimeError):
+    pass
+
+
+class _Params(C.Structure):
+    _fields_ = [("sca", C.c_double), ("sig", C.c_double), ("angThre", C.c_double), ("denThre", C.c_double),
+                ("pseBin", C.c_int), ("_pad", C.c_int)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [(f, C.c_longlong) for f in STAT_FIELDS]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise LsdbError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        L.lsdb_version.restype = C.c_char_p
+        L.lsdb_last_error.restype = C.c_char_p
+        L.lsdb_last_error.argtypes = [vp]
+        L.lsdb_create.argtypes = [C.POINTER(vp), ci, vp]
+        L.lsdb_destroy.argtypes = [vp]; L.lsdb_destroy.restype = None
+        L.lsdb_batch_create.argtypes = [vp, ci, vp, vp, C.POINTER(_Params), ci, C.POINTER(vp)]
+        L.lsdb_batch_destroy.argtypes = [vp]; L.lsdb_batch_destroy.restype = None
+        L.lsdb_batch_upload.argtypes = [vp, vp]
+        L.lsdb_batch_run.argtypes = [vp]
+        L.lsdb_batch_sync.argtypes = [vp]
+        L.lsdb_batch_download.argtypes = [vp, vp, vp, vp]
+        L.lsdb_batch_line_image.argtypes = [vp, ci, vp]
+        L.lsdb_batch_planes.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci, vp, vp]
+        L.lsdb_batch_stage_ms.argtypes = [vp, vp]
+        L.lsdb_batch_stats.argtypes = [vp, C.POINTER(_Stats)]
+        L.lsdb_batch_launches.argtypes = [vp]
+        L.lsdb_lsd.argtypes = [vp, vp, ci, ci, C.POINTER(_Params), vp, ci, vp, vp, vp]
+        L.lsdb_fa_map_create.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(vp)]
+        L.lsdb_fa_map_destroy.argtypes = [vp]; L.lsdb_fa_map_destroy.restype = None
+        L.lsdb_fa_score.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+        L.lsdb_fa_last_ms.argtypes = [vp]; L.lsdb_fa_last_ms.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _params(kw):
+    d = dict(LSD_DEFAULTS); d.update(kw or {})
+    return _Params(d["sca"], d["sig"], d["angThre"], d["denThre"], int(d["pseBin"]), 0)
+
+
+class Context:
+    """lsdb_ctx: one per process/GPU.  `stream` = a cudaStream_t handle (int) or None."""
+
+    def __init__(self, device=0, stream=None):
+        self.h = C.c_void_p()
+        rc = lib().lsdb_create(C.byref(self.h), int(device), C.c_void_p(stream) if stream else None)
+        if rc:
+            raise LsdbError(f"lsdb_create(device={device}) failed: {ERR_NAMES.get(rc, rc)} — an sm_100 (B200) GPU is "
+                            "required; there is no CPU fallback")
+
+    def check(self, rc, what):
+        if rc:
+            raise LsdbError(f"{what}: {ERR_NAMES.get(rc, rc)}: {lib().lsdb_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            lib().lsdb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def lsd(self, map_u8, want_line_im=True, want_remap=False, max_lines=4096, **params):
+        """mylsd::myLineSegmentDetector on one host map (LSD/myLSD.h:132) through lsdb_lsd."""
+        m = np.ascontiguousarray(map_u8, np.uint8)
+        rows, cols = m.shape
+        lines = np.zeros(max_lines, LINE_DTYPE)
+        n = C.c_int(0)
+        im = np.zeros((rows, cols), np.uint8) if want_line_im else None
+        rm = np.zeros((rows, cols), np.uint8) if want_remap else None
+        prm = _params(params)
+        self.check(lib().lsdb_lsd(self.h, _p(m), cols, rows, C.byref(prm), _p(lines), max_lines, C.byref(n), _p(im), _p(rm)),
+                   "lsdb_lsd")
+        return dict(n=n.value, lines=lines[:n.value].copy(), line_im=im, map_out=rm)
+
+
+class Batch:
+    """lsdb_batch: device-resident buffers for a fixed list of map sizes."""
+
+    def __init__(self, ctx, sizes, max_lines=4096, **params):
+        self.ctx = ctx
+        self.sizes = [(int(c), int(r)) for c, r in sizes]
+        self.n = len(self.sizes)
+        self.max_lines = max_lines
+        self.sca = dict(LSD_DEFAULTS, **params)["sca"]
+        cols = np.array([s[0] for s in self.sizes], np.int32); rows = np.array([s[1] for s in self.sizes], np.int32)
+        self.h = C.c_void_p()
+        prm = _params(params)
+        ctx.check(lib().lsdb_batch_create(ctx.h, self.n, _p(cols), _p(rows), C.byref(prm), max_lines, C.byref(self.h)),
+                  "lsdb_batch_create")
+
+    def scaled(self, i):
+        c, r = self.sizes[i]
+        return int(np.floor(c * self.sca)), int(np.floor(r * self.sca))
+
+    def upload(self, maps):
+        """maps: list of C-contiguous uint8 arrays (rows x cols) or raw host pointers (ints)."""
+        ptrs = (C.c_void_p * self.n)()
+        keep = []
+        for i, m in enumerate(maps):
+            if isinstance(m, (int, np.integer)):
+                ptrs[i] = int(m)
+            else:
+                a = np.ascontiguousarray(m, np.uint8); keep.append(a)
+                assert a.shape == (self.sizes[i][1], self.sizes[i][0]), (a.shape, self.sizes[i])
+                ptrs[i] = a.ctypes.data
+        self._keep = keep
+        self.ctx.check(lib().lsdb_batch_upload(self.h, C.cast(ptrs, C.c_void_p)), "lsdb_batch_upload")
+
+    def run(self):
+        self.ctx.check(lib().lsdb_batch_run(self.h), "lsdb_batch_run")
+
+    def sync(self):
+        self.ctx.check(lib().lsdb_batch_sync(self.h), "lsdb_batch_sync")
+
+    def download(self, want_lines=True, want_rects=False):
+        counts = np.zeros(self.n, np.int32)
+        lines = np.zeros((self.n, self.max_lines), LINE_DTYPE) if want_lines else None
+        rects = np.zeros((self.n, self.max_lines, 13)) if want_rects else None
+        self.ctx.check(lib().lsdb_batch_download(self.h, _p(counts), _p(lines), _p(rects)), "lsdb_batch_download")
+        out = dict(counts=counts)
+        if want_lines:
+            out["lines"] = [lines[i, :counts[i]].copy() for i in range(self.n)]
+        if want_rects:
+            out["rects"] = [rects[i, :counts[i]].copy() for i in range(self.n)]
+        return out
+
+    def counts(self):
+        counts = np.zeros(self.n, np.int32)
+        self.ctx.check(lib().lsdb_batch_download(self.h, _p(counts), None, None), "lsdb_batch_download")
+        return counts
+
+    def line_image(self, i):
+        c, r = self.sizes[i]
+        im = np.zeros((r, c), np.uint8)
+        self.ctx.check(lib().lsdb_batch_line_image(self.h, i, _p(im)), "lsdb_batch_line_image")
+        return im
+
+    def planes(self, i):
+        W, H = self.scaled(i)
+        mag = np.zeros((H, W)); deg = np.zeros((H, W)); used = np.zeros((H, W), np.uint8)
+        labels = np.zeros((H, W), np.int32); seeds = np.zeros(H * W, np.int32); ns = C.c_int(0); mg = C.c_double(0)
+        self.ctx.check(lib().lsdb_batch_planes(self.h, i, _p(mag), _p(deg), _p(used), _p(labels), _p(seeds), H * W,
+                                               C.byref(ns), C.byref(mg)), "lsdb_batch_planes")
+        return dict(mag=mag, deg=deg, used=used, labels=labels, seeds=seeds[:ns.value].copy(), max_grad=mg.value)
+
+    def stage_ms(self):
+        ms = np.zeros(len(STAGES), np.float32)
+        self.ctx.check(lib().lsdb_batch_stage_ms(self.h, _p(ms)), "lsdb_batch_stage_ms")
+        return dict(zip(STAGES, (float(v) for v in ms)))
+
+    def stats(self):
+        st = _Stats()
+        self.ctx.check(lib().lsdb_batch_stats(self.h, C.byref(st)), "lsdb_batch_stats")
+        return {f: getattr(st, f) for f in STAT_FIELDS}
+
+    def launches(self):
+        return lib().lsdb_batch_launches(self.h)
+
+    def close(self):
+        if self.h:
+            lib().lsdb_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def lines_to_array(lines):
+    """structured lsdb_line records -> (n,10) float array in oracle column order"""
+    out = np.zeros((len(lines), 10))
+    for j, f in enumerate(["k", "b", "dx", "dy", "x1", "y1", "x2", "y2", "len"]):
+        out[:, j] = lines[f]
+    out[:, 9] = lines["orient"]
+    return out
+
+
+def array_to_lines(arr):
+    arr = np.asarray(arr, np.float64).reshape(-1, 10)
+    out = np.zeros(len(arr), LINE_DTYPE)
+    for j, f in enumerate(["k", "b", "dx", "dy", "x1", "y1", "x2", "y2", "len"]):
+        out[f] = arr[:, j]
+    out["orient"] = arr[:, 9].astype(np.int32)
+    return out
+
+
+class FaMap:
+    """lsdb_fa_map: mapCache + the map's LSD lines resident on the device."""
+
+    def __init__(self, ctx, map_cache, map_lines):
+        self.ctx = ctx
+        mc = np.ascontiguousarray(map_cache, np.float64)
+        ml = map_lines if getattr(map_lines, "dtype", None) == LINE_DTYPE else array_to_lines(map_lines)
+        ml = np.ascontiguousarray(ml)
+        self.h = C.c_void_p()
+        rows, cols = mc.shape
+        ctx.check(lib().lsdb_fa_map_create(ctx.h, _p(mc), cols, rows, _p(ml), len(ml), C.byref(self.h)), "lsdb_fa_map_create")
+        self.n_lines = len(ml)
+
+    def score(self, frames, max_hyp=None):
+        """frames: list of dicts(scan_lines=(n,10) or LINE_DTYPE, pts=(P,2), lidar_pose=(2,), last_pose=(3,))."""
+        nf = len(frames)
+        sl = [f["scan_lines"] if getattr(f["scan_lines"], "dtype", None) == LINE_DTYPE else array_to_lines(f["scan_lines"])
+              for f in frames]
+        loff = np.zeros(nf + 1, np.int32); poff = np.zeros(nf + 1, np.int32)
+        for i, f in enumerate(frames):
+            loff[i + 1] = loff[i] + len(sl[i]); poff[i + 1] = poff[i] + len(f["pts"])
+        lines = np.ascontiguousarray(np.concatenate(sl)) if nf else np.zeros(0, LINE_DTYPE)
+        pts = np.ascontiguousarray(np.concatenate([np.asarray(f["pts"], np.float64).reshape(-1, 2) for f in frames])) if nf else np.zeros((0, 2))
+        lid = np.ascontiguousarray(np.array([f["lidar_pose"] for f in frames], np.float64).reshape(nf, 2))
+        last = np.ascontiguousarray(np.array([f["last_pose"] for f in frames], np.float64).reshape(nf, 3))
+        if max_hyp is None:
+            max_hyp = max(4 * int(loff[-1]) * max(self.n_lines, 1), 4)
+        out = np.zeros(max_hyp, HYP_DTYPE); n = C.c_int(0)
+        self.ctx.check(lib().lsdb_fa_score(self.ctx.h, self.h, nf, _p(lines), _p(loff), _p(pts), _p(poff), _p(lid), _p(last),
+                                           _p(out), max_hyp, C.byref(n)), "lsdb_fa_score")
+        return out[:n.value].copy()
+
+    def last_ms(self):
+        return float(lib().lsdb_fa_last_ms(self.ctx.h))
+
+    def close(self):
+        if self.h:
+            lib().lsdb_fa_map_destroy(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,518 @@
+// C ABI of liblsdb200.so (include/lsdb200.h): contexts, device-resident batches, the host epilogue
+// that turns accepted rectangles into structLinesInfo / lineIm (LSD/myLSD.cpp:274-368 — O(segments),
+// kept on the host), and the association-scoring entry point.  No CPU fallback anywhere: without a
+// usable CUDA device every compute call fails.
+#include "../../include/lsdb200.h"
+#include "lsdb_common.cuh"
+
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+struct lsdb_ctx {
+    int device;
+    cudaStream_t stream;
+    bool ownStream;
+    std::string err;
+    double* lgammaTab;
+    int lgammaN;
+    int maxGrowCtas;
+    lsdb_batch* cached;  // single-map batch reused by lsdb_lsd
+    cudaEvent_t faEv[2];
+    float faMs;
+    // FA staging buffers (grown on demand)
+    void* faDev; size_t faDevCap;
+    void* faHost; size_t faHostCap;
+};
+
+struct lsdb_batch {
+    lsdb_ctx* ctx;
+    int n;
+    lsdb_lsd_params params;
+    int maxSeg, listCap, nTiles, nCtas;
+    size_t totalN, totalSrc;
+    std::vector<LsdbImg> imgs;
+    LsdbLsdConst kc;
+    // device
+    uint8_t* src; double* mag; double* deg; unsigned int* state; unsigned short* bins; unsigned int* cells;
+    int* labels; LsdbRect* rects; LsdbImgDyn* dyn; LsdbImg* imgsD; int* tileImg; unsigned int* lists;
+    int* imgCounter; LsdbLsdConst* kcD; double* gaussDbg;
+    // host (pinned)
+    LsdbImgDyn* dynH; LsdbRect* rectsH;
+    cudaEvent_t ev[4];
+    bool ran, downloaded;
+    int launches;
+};
+
+static int fail(lsdb_ctx* c, int code, const char* fmt, const char* a = "", long long v = 0) {
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a, v);
+    if (c) c->err = buf;
+    return code;
+}
+#define CK(ctx, call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return fail(ctx, LSDB_ERR_CUDA, "%s (line %lld)", cudaGetErrorString(e_), __LINE__); \
+    } while (0)
+
+static int x86_d2i(double v) {
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+    return (int)v;
+}
+
+extern "C" const char* lsdb_version(void) { return "lsdb200 0.1 (sm_100a)"; }
+
+extern "C" const char* lsdb_last_error(const lsdb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
+    if (!out) return LSDB_ERR_ARG;
+    *out = 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LSDB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LSDB_ERR_NO_DEVICE;
+    if (prop.major != 10) return LSDB_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+    lsdb_ctx* c = new lsdb_ctx();
+    c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0;
+    c->lgammaTab = 0; c->lgammaN = 0;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return LSDB_ERR_NO_DEVICE; }
+    if (stream) { c->stream = (cudaStream_t)stream; c->ownStream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LSDB_ERR_CUDA; }
+        c->ownStream = true;
+    }
+    c->lgammaN = 1 << 16;
+    if (cudaMalloc(&c->lgammaTab, sizeof(double) * c->lgammaN) != cudaSuccess) { delete c; return LSDB_ERR_CUDA; }
+    lsdb_launch_lgamma_table(c->stream, c->lgammaTab, c->lgammaN);
+    cudaEventCreate(&c->faEv[0]); cudaEventCreate(&c->faEv[1]);
+    c->maxGrowCtas = lsdb_grow_max_ctas(device);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFree(c->lgammaTab); delete c; return LSDB_ERR_CUDA; }
+    *out = c;
+    return LSDB_OK;
+}
+
+extern "C" void lsdb_destroy(lsdb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->cached) lsdb_batch_destroy(c->cached);
+    cudaFree(c->lgammaTab);
+    if (c->faDev) cudaFree(c->faDev);
+    if (c->faHost) cudaFreeHost(c->faHost);
+    cudaEventDestroy(c->faEv[0]); cudaEventDestroy(c->faEv[1]);
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// the three 17-tap phase kernels, LSD/myLSD.cpp:384-417 (host side, same lsd_math.h as the device)
+static int gauss_taps(double sca, double sig, double* out) {
+    const int prec = 3;
+    if (sca < 1) sig = sig / sca;
+    const int h = x86_d2i(ceil(sig * sqrt(2 * prec * lsdm_log(10))));
+    if (h != 8) return h;
+    const int hSize = 17;
+    double s1 = 0, s2 = 0, s3 = 0;
+    double *k1 = out, *k2 = out + hSize, *k3 = out + 2 * hSize;
+    for (int k = 0; k < hSize; k++) {
+        const double a = (k - h) / sig, b = (k - h - 1.0 / 3) / sig, c = (k - h + 1.0 / 3) / sig;
+        k1[k] = lsdm_exp(-0.5 * (a * a));
+        k2[k] = lsdm_exp(-0.5 * (b * b));
+        k3[k] = lsdm_exp(-0.5 * (c * c));
+        s1 += k1[k]; s2 += k2[k]; s3 += k3[k];
+    }
+    for (int k = 0; k < hSize; k++) { k1[k] /= s1; k2[k] /= s2; k3[k] /= s3; }
+    return h;
+}
+
+extern "C" void lsdb_batch_destroy(lsdb_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaFree(b->src); cudaFree(b->mag); cudaFree(b->deg); cudaFree(b->state); cudaFree(b->bins); cudaFree(b->cells);
+    cudaFree(b->labels); cudaFree(b->rects); cudaFree(b->dyn); cudaFree(b->imgsD); cudaFree(b->tileImg); cudaFree(b->lists);
+    cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg);
+    cudaFreeHost(b->dynH); cudaFreeHost(b->rectsH);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(b->ev[i]);
+    if (b->ctx->cached == b) b->ctx->cached = 0;
+    delete b;
+}
+
+extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const int* rows, const lsdb_lsd_params* prm,
+                                 int maxLines, lsdb_batch** out) {
+    if (!ctx || !out || n <= 0 || !cols || !rows || !prm) return fail(ctx, LSDB_ERR_ARG, "lsdb_batch_create: bad argument%s");
+    *out = 0;
+    if (prm->pseBin < 1 || prm->pseBin > 1024) return fail(ctx, LSDB_ERR_ARG, "pseBin must be in [1,1024]%s");
+    if (!(prm->sca > 0 && prm->sca <= 1)) return fail(ctx, LSDB_ERR_ARG, "sca must be in (0,1]%s");
+    CK(ctx, cudaSetDevice(ctx->device));
+    lsdb_batch* b = new lsdb_batch();
+    memset(&b->kc, 0, sizeof b->kc);
+    b->ctx = ctx; b->n = n; b->params = *prm; b->ran = false; b->downloaded = false; b->launches = 0;
+    b->src = 0; b->mag = 0; b->deg = 0; b->state = 0; b->bins = 0; b->cells = 0; b->labels = 0; b->rects = 0; b->dyn = 0;
+    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->dynH = 0; b->rectsH = 0;
+    for (int i = 0; i < 4; i++) cudaEventCreate(&b->ev[i]);
+    b->maxSeg = maxLines > 0 ? maxLines : 4096;
+
+    const int h = gauss_taps(prm->sca, prm->sig, b->kc.taps);
+    if (h != 8) { lsdb_batch_destroy(b); return fail(ctx, LSDB_ERR_ARG, "Gaussian half-width %s%lld != 8: only sig/sca = 2 (0.6/0.3) is supported", "", h); }
+    const double pi = 4.0 * lsdm_atan(1.0);
+    b->kc.sca = prm->sca; b->kc.pi = pi; b->kc.h = h; b->kc.pseBin = prm->pseBin;
+    b->kc.degThre = prm->angThre / 180.0 * pi;              // :148
+    b->kc.gradThre = 2.0 / lsdm_sin(b->kc.degThre);        // :149
+    b->kc.aliPro = prm->angThre / 180.0;                   // :209
+    b->kc.denThre = prm->denThre;
+
+    b->imgs.resize(n);
+    size_t srcOff = 0, nOff = 0;
+    int tile0 = 0, maxN = 0;
+    std::vector<int> tileImgH;
+    for (int i = 0; i < n; i++) {
+        LsdbImg& im = b->imgs[i];
+        memset(&im, 0, sizeof im);
+        if (cols[i] <= 0 || rows[i] <= 0 || cols[i] > 200000 || rows[i] > 200000) { lsdb_batch_destroy(b); return fail(ctx, LSDB_ERR_ARG, "bad map size%s"); }
+        im.cols = cols[i]; im.rows = rows[i];
+        im.W = x86_d2i(floor(cols[i] * prm->sca)); im.H = x86_d2i(floor(rows[i] * prm->sca));  // :132-133
+        if (im.W < 1 || im.H < 1 || im.W > 65535 || im.H > 65535) { lsdb_batch_destroy(b); return fail(ctx, LSDB_ERR_ARG, "scaled map size out of range%s"); }
+        im.n = im.W * im.H;
+        im.srcPitch = (cols[i] + 15) & ~15;
+        im.srcOff = srcOff; im.nOff = nOff; im.segOff = (size_t)i * b->maxSeg;
+        im.tilesX = (im.W + LSDB_TILE - 1) / LSDB_TILE; im.tilesY = (im.H + LSDB_TILE - 1) / LSDB_TILE;
+        im.tile0 = tile0;
+        im.logNT = 5 * (lsdm_log10(im.H) + lsdm_log10(im.W)) / 2.0;         // :207
+        im.regThre = -im.logNT / lsdm_log10(prm->angThre / 180.0);           // :208
+        for (int t = 0; t < im.tilesX * im.tilesY; t++) tileImgH.push_back(i);
+        tile0 += im.tilesX * im.tilesY;
+        srcOff += (size_t)im.srcPitch * rows[i];
+        nOff += ((size_t)im.n + 31) & ~(size_t)31;
+        if (im.n > maxN) maxN = im.n;
+    }
+    b->nTiles = tile0; b->totalN = nOff; b->totalSrc = srcOff;
+    b->listCap = maxN + 2 < (1 << 16) ? maxN + 2 : (1 << 16);
+    b->nCtas = n < ctx->maxGrowCtas ? n : ctx->maxGrowCtas;
+
+    cudaError_t e = cudaSuccess;
+#define AL(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
+    AL(b->src, b->totalSrc + 64); AL(b->mag, b->totalN * 8); AL(b->deg, b->totalN * 8); AL(b->state, b->totalN * 4);
+    AL(b->bins, b->totalN * 2); AL(b->cells, b->totalN * 4); AL(b->labels, b->totalN * 4);
+    AL(b->rects, (size_t)n * b->maxSeg * sizeof(LsdbRect)); AL(b->dyn, (size_t)n * sizeof(LsdbImgDyn));
+    AL(b->imgsD, (size_t)n * sizeof(LsdbImg)); AL(b->tileImg, (size_t)b->nTiles * sizeof(int));
+    AL(b->lists, (size_t)b->nCtas * LSDB_GROW_WARPS * 2 * (size_t)b->listCap * 4);
+    AL(b->imgCounter, 64); AL(b->kcD, sizeof(LsdbLsdConst));
+#undef AL
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&b->dynH, (size_t)n * sizeof(LsdbImgDyn));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&b->rectsH, (size_t)n * b->maxSeg * sizeof(LsdbRect));
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->src, 0, b->totalSrc + 64, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->imgsD, b->imgs.data(), (size_t)n * sizeof(LsdbImg), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->tileImg, tileImgH.data(), tileImgH.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->kcD, &b->kc, sizeof(LsdbLsdConst), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        lsdb_batch_destroy(b);
+        return fail(ctx, LSDB_ERR_CUDA, "lsdb_batch_create: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_upload(lsdb_batch* b, const uint8_t* const* maps) {
+    if (!b || !maps) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < b->n; i++) {
+        const LsdbImg& im = b->imgs[i];
+        CK(ctx, cudaMemcpy2DAsync(b->src + im.srcOff, im.srcPitch, maps[i], im.cols, im.cols, im.rows, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_run(lsdb_batch* b) {
+    if (!b) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    cudaStream_t s = ctx->stream;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemsetAsync(b->dyn, 0, (size_t)b->n * sizeof(LsdbImgDyn), s));
+    CK(ctx, cudaMemsetAsync(b->labels, 0, b->totalN * 4, s));
+    CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
+    CK(ctx, cudaEventRecord(b->ev[0], s));
+    lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->state, b->gaussDbg);
+    CK(ctx, cudaEventRecord(b->ev[1], s));
+    lsdb_launch_order(s, b->n, b->imgsD, b->dyn, b->kcD, b->mag, b->bins, b->cells);
+    CK(ctx, cudaEventRecord(b->ev[2], s));
+    lsdb_launch_grow(s, b->n, b->nCtas, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->state, b->cells, b->labels, b->rects,
+                     b->maxSeg, b->lists, b->listCap, ctx->lgammaTab, ctx->lgammaN, b->imgCounter);
+    CK(ctx, cudaEventRecord(b->ev[3], s));
+    CK(ctx, cudaGetLastError());
+    b->ran = true; b->downloaded = false; b->launches = 3;
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_launches(const lsdb_batch* b) { return b ? b->launches : 0; }
+
+static int fetch_dyn(lsdb_batch* b) {
+    lsdb_ctx* ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(b->dynH, b->dyn, (size_t)b->n * sizeof(LsdbImgDyn), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < b->n; i++) {
+        if (b->dynH[i].err == LSDB_ERR_TIMEOUT) return fail(ctx, LSDB_ERR_TIMEOUT, "map %s%lld: ordered-commit watchdog fired", "", i);
+        if (b->dynH[i].err) return fail(ctx, LSDB_ERR_CAPACITY, "map %s%lld: region list or segment capacity exceeded", "", i);
+    }
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_sync(lsdb_batch* b) {
+    if (!b) return LSDB_ERR_ARG;
+    if (!b->ran) return fail(b->ctx, LSDB_ERR_ARG, "lsdb_batch_sync before lsdb_batch_run%s");
+    return fetch_dyn(b);
+}
+
+// epilogue of one segment, LSD/myLSD.cpp:282-368 (host; identical operation order to the reference)
+static void line_from_rect(const LsdbRect& R, double pi, lsdb_line* L) {
+    const double x1 = R.v[0], y1 = R.v[1], x2 = R.v[2], y2 = R.v[3];
+    const double k = (y2 - y1) / (x2 - x1);
+    double ang = lsdm_atan(k) * 180.0 / pi;  // atand
+    int orient = 1;
+    if (ang < 0) { ang += 180; orient = -1; }
+    L->k = k;
+    L->b = (y1 + y2) / 2.0 - k * (x1 + x2) / 2.0;
+    L->dx = lsdm_cos(ang / 180.0 * pi);      // cosd
+    L->dy = lsdm_sin(ang / 180.0 * pi);      // sind
+    L->x1 = x1; L->y1 = y1; L->x2 = x2; L->y2 = y2;
+    const double ddy = y2 - y1, ddx = x2 - x1;
+    L->len = sqrt(ddy * ddy + ddx * ddx);
+    L->orient = orient; L->_pad = 0;
+}
+
+static void raster_line(const LsdbRect& R, int oriMapCol, int oriMapRow, uint8_t* lineIm) {  // :296-355
+    const double x1 = R.v[0], y1 = R.v[1], x2 = R.v[2], y2 = R.v[3];
+    const double k = (y2 - y1) / (x2 - x1);
+    int xLow, xHigh, yLow, yHigh;
+    if (x1 > x2) { xLow = x86_d2i(floor(x2)); xHigh = x86_d2i(ceil(x1)); } else { xLow = x86_d2i(floor(x1)); xHigh = x86_d2i(ceil(x2)); }
+    if (y1 > y2) { yLow = x86_d2i(floor(y2)); yHigh = x86_d2i(ceil(y1)); } else { yLow = x86_d2i(floor(y1)); yHigh = x86_d2i(ceil(y2)); }
+    const double xRang = fabs(x2 - x1), yRang = fabs(y2 - y1);
+    const int xx_len = xHigh - xLow + 1, yy_len = yHigh - yLow + 1;
+    const int n = xx_len > yy_len ? xx_len : yy_len;  // marking loop length (:344)
+    for (int j = 0; j < n; j++) {
+        int xx = 0, yy = 0;  // slots the sampling loop did not fill read as 0 (reference: heap garbage)
+        if (xRang > yRang) {
+            if (j < xx_len) { xx = j + xLow; yy = x86_d2i(round((xx - x1) * k + y1)); }
+        } else {
+            if (j < yy_len) { yy = j + yLow; xx = x86_d2i(round((yy - y1) / k + x1)); }
+        }
+        if (xx < 0 || xx >= oriMapCol || yy < 0 || yy >= oriMapRow) { xx = 0; yy = 0; }
+        if (xx != 0 && yy != 0) lineIm[(size_t)yy * oriMapCol + xx] = 255;
+    }
+}
+
+extern "C" int lsdb_batch_download(lsdb_batch* b, int* counts, lsdb_line* lines, lsdb_rect* rects) {
+    if (!b) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    if (!b->ran) return fail(ctx, LSDB_ERR_ARG, "lsdb_batch_download before lsdb_batch_run%s");
+    int rc = fetch_dyn(b);
+    if (rc) return rc;
+    for (int i = 0; i < b->n; i++) {
+        const int ns = b->dynH[i].nSeg;
+        if (ns > 0)
+            CK(ctx, cudaMemcpyAsync(b->rectsH + (size_t)i * b->maxSeg, b->rects + (size_t)i * b->maxSeg, (size_t)ns * sizeof(LsdbRect),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    b->downloaded = true;
+    const double pi = b->kc.pi;
+    for (int i = 0; i < b->n; i++) {
+        const int ns = b->dynH[i].nSeg;
+        if (counts) counts[i] = ns;
+        for (int j = 0; j < ns; j++) {
+            const LsdbRect& R = b->rectsH[(size_t)i * b->maxSeg + j];
+            if (lines) line_from_rect(R, pi, &lines[(size_t)i * b->maxSeg + j]);
+            if (rects) memcpy(&rects[(size_t)i * b->maxSeg + j], R.v, sizeof(lsdb_rect));
+        }
+    }
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_line_image(lsdb_batch* b, int i, uint8_t* lineIm) {
+    if (!b || !lineIm || i < 0 || i >= b->n) return LSDB_ERR_ARG;
+    if (!b->downloaded) { int rc = lsdb_batch_download(b, 0, 0, 0); if (rc) return rc; }
+    const LsdbImg& im = b->imgs[i];
+    memset(lineIm, 0, (size_t)im.cols * im.rows);
+    for (int j = 0; j < b->dynH[i].nSeg; j++) raster_line(b->rectsH[(size_t)i * b->maxSeg + j], im.cols, im.rows, lineIm);
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_planes(lsdb_batch* b, int i, double* mag, double* deg, uint8_t* used, int32_t* labels,
+                                 int32_t* seeds, int maxSeeds, int* nSeeds, double* maxGrad) {
+    if (!b || i < 0 || i >= b->n) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    int rc = fetch_dyn(b);
+    if (rc) return rc;
+    const LsdbImg& im = b->imgs[i];
+    cudaStream_t s = ctx->stream;
+    if (mag) CK(ctx, cudaMemcpyAsync(mag, b->mag + im.nOff, (size_t)im.n * 8, cudaMemcpyDeviceToHost, s));
+    if (deg) CK(ctx, cudaMemcpyAsync(deg, b->deg + im.nOff, (size_t)im.n * 8, cudaMemcpyDeviceToHost, s));
+    if (labels) CK(ctx, cudaMemcpyAsync(labels, b->labels + im.nOff, (size_t)im.n * 4, cudaMemcpyDeviceToHost, s));
+    if (used) {
+        uint8_t* tmp = (uint8_t*)b->bins;  // the bin plane is dead after the ordering stage
+        lsdb_launch_used_plane(s, b->state + im.nOff, tmp, im.n);
+        CK(ctx, cudaMemcpyAsync(used, tmp, (size_t)im.n, cudaMemcpyDeviceToHost, s));
+    }
+    const int nc = b->dynH[i].nCells;
+    if (nSeeds) *nSeeds = nc;
+    if (seeds && nc > 0) CK(ctx, cudaMemcpyAsync(seeds, b->cells + im.nOff, (size_t)(nc < maxSeeds ? nc : maxSeeds) * 4, cudaMemcpyDeviceToHost, s));
+    if (maxGrad) { long long bits = (long long)b->dynH[i].maxGradBits; memcpy(maxGrad, &bits, 8); }
+    CK(ctx, cudaStreamSynchronize(s));
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_stage_ms(lsdb_batch* b, float* ms) {
+    if (!b || !ms || !b->ran) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    CK(ctx, cudaEventSynchronize(b->ev[3]));
+    for (int k = 0; k < LSDB_NSTAGES; k++) CK(ctx, cudaEventElapsedTime(&ms[k], b->ev[k], b->ev[k + 1]));
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_stats(lsdb_batch* b, lsdb_stats* total) {
+    if (!b || !total) return LSDB_ERR_ARG;
+    int rc = fetch_dyn(b);
+    if (rc) return rc;
+    long long* t = (long long*)total;
+    for (int k = 0; k < 14; k++) t[k] = 0;
+    for (int i = 0; i < b->n; i++)
+        for (int k = 0; k < 14; k++) t[k] += b->dynH[i].stat[k];
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_lsd(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, const lsdb_lsd_params* prm, lsdb_line* lines,
+                        int maxLines, int* nLines, uint8_t* lineIm, uint8_t* mapRemapped) {
+    if (!ctx || !map || !prm || !nLines) return fail(ctx, LSDB_ERR_ARG, "lsdb_lsd: bad argument%s");
+    lsdb_batch* b = ctx->cached;
+    if (b && (b->imgs[0].cols != cols || b->imgs[0].rows != rows || memcmp(&b->params, prm, sizeof(double) * 4) != 0 ||
+              b->params.pseBin != prm->pseBin)) {
+        lsdb_batch_destroy(b);
+        b = 0;
+    }
+    int rc;
+    if (!b) {
+        rc = lsdb_batch_create(ctx, 1, &cols, &rows, prm, 0, &b);
+        if (rc) return rc;
+        ctx->cached = b;
+    }
+    if ((rc = lsdb_batch_upload(b, &map))) return rc;
+    if ((rc = lsdb_batch_run(b))) return rc;
+    int count = 0;
+    std::vector<lsdb_line> tmp(b->maxSeg);
+    if ((rc = lsdb_batch_download(b, &count, tmp.data(), 0))) return rc;
+    *nLines = count;
+    if (lines) memcpy(lines, tmp.data(), sizeof(lsdb_line) * (size_t)(count < maxLines ? count : maxLines));
+    if (lineIm && (rc = lsdb_batch_line_image(b, 0, lineIm))) return rc;
+    if (mapRemapped) {  // the side effect on the caller's Mat, LSD/myLSD.cpp:135-142 (host memory, host loop)
+        memcpy(mapRemapped, map, (size_t)cols * rows);
+        for (int y = 1; y < rows; y++)
+            for (int x = 1; x < cols; x++) {
+                uint8_t* p = mapRemapped + (size_t)y * cols + x;
+                if (*p == 1) *p = 255; else if (*p == 255) *p = 0;
+            }
+    }
+    return LSDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ association
+struct lsdb_fa_map {
+    lsdb_ctx* ctx;
+    int cols, rows, nLines;
+    double* cacheD;
+    LsdbFaLine* linesD;
+    std::vector<lsdb_line> lines;
+};
+
+extern "C" int lsdb_fa_map_create(lsdb_ctx* ctx, const double* mapCache, int cols, int rows, const lsdb_line* mapLines,
+                                  int nLines, lsdb_fa_map** out) {
+    if (!ctx || !mapCache || !out || cols <= 0 || rows <= 0 || nLines < 0 || (nLines > 0 && !mapLines)) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_map_create: bad argument%s");
+    CK(ctx, cudaSetDevice(ctx->device));
+    lsdb_fa_map* m = new lsdb_fa_map();
+    m->ctx = ctx; m->cols = cols; m->rows = rows; m->nLines = nLines; m->cacheD = 0; m->linesD = 0;
+    m->lines.assign(mapLines, mapLines + nLines);
+    cudaError_t e = cudaMalloc((void**)&m->cacheD, (size_t)cols * rows * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->linesD, sizeof(LsdbFaLine) * (size_t)(nLines > 0 ? nLines : 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->cacheD, mapCache, (size_t)cols * rows * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nLines) e = cudaMemcpyAsync(m->linesD, mapLines, sizeof(LsdbFaLine) * (size_t)nLines, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(m->cacheD); cudaFree(m->linesD); delete m; return fail(ctx, LSDB_ERR_CUDA, "lsdb_fa_map_create: %s", cudaGetErrorString(e)); }
+    *out = m;
+    return LSDB_OK;
+}
+
+extern "C" void lsdb_fa_map_destroy(lsdb_fa_map* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaFree(m->cacheD); cudaFree(m->linesD);
+    delete m;
+}
+
+extern "C" float lsdb_fa_last_ms(const lsdb_ctx* ctx) { return ctx ? ctx->faMs : 0.f; }
+
+static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_line* scanLines, const int* lineOff,
+                             const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
+                             lsdb_hypothesis* out, int maxHyp, int* nHyp) {
+    if (!ctx || !m || nFrames < 0 || !lineOff || !ptOff || !nHyp || (nFrames > 0 && (!lidarPose || !lastPose)))
+        return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score: bad argument%s");
+    static_assert(sizeof(lsdb_hypothesis) == sizeof(LsdbFaHyp), "layout");
+    static_assert(sizeof(lsdb_line) == sizeof(LsdbFaLine), "layout");
+    CK(ctx, cudaSetDevice(ctx->device));
+    // pair filter, LSD/myFA.cpp:29-41 (ignoreScanLength = 40, scanToMapDiff = 0.35; LSD/baseFunc.h:80-82)
+    std::vector<LsdbFaTask> tasks;
+    for (int f = 0; f < nFrames; f++)
+        for (int is = 0; is < lineOff[f + 1] - lineOff[f]; is++) {
+            const double lenS = scanLines[lineOff[f] + is].len;
+            if (lenS < 40) continue;
+            const double lenDiff = lenS * 0.35;
+            for (int im = 0; im < m->nLines; im++) {
+                const double lenM = m->lines[im].len;
+                if (lenM < lenS - lenDiff || lenM > lenS + lenDiff) continue;
+                LsdbFaTask t = {f, is, im, 0};
+                tasks.push_back(t);
+            }
+        }
+    const int nTasks = (int)tasks.size();
+    *nHyp = nTasks * 4;
+    if (nTasks == 0) return LSDB_OK;
+    if (nTasks * 4 > maxHyp) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_fa_score: %s%lld hypotheses exceed max_hyp", "", (long long)nTasks * 4);
+    const int nL = lineOff[nFrames], nP = ptOff[nFrames];
+    const size_t oTasks = 0, oLines = oTasks + al256(sizeof(LsdbFaTask) * nTasks), oLoff = oLines + al256(sizeof(LsdbFaLine) * nL),
+                 oPts = oLoff + al256(sizeof(int) * (nFrames + 1)), oPoff = oPts + al256(16 * (size_t)nP),
+                 oLid = oPoff + al256(sizeof(int) * (nFrames + 1)), oLast = oLid + al256(16 * (size_t)nFrames),
+                 oOut = oLast + al256(24 * (size_t)nFrames), total = oOut + al256(sizeof(LsdbFaHyp) * (size_t)nTasks * 4);
+    if (total > ctx->faDevCap) {
+        if (ctx->faDev) cudaFree(ctx->faDev);
+        if (ctx->faHost) cudaFreeHost(ctx->faHost);
+        ctx->faDev = 0; ctx->faHost = 0; ctx->faDevCap = 0;
+        CK(ctx, cudaMalloc(&ctx->faDev, total + total / 4));
+        CK(ctx, cudaMallocHost(&ctx->faHost, total + total / 4));
+        ctx->faDevCap = ctx->faHostCap = total + total / 4;
+    }
+    char* H = (char*)ctx->faHost; char* D = (char*)ctx->faDev;
+    memcpy(H + oTasks, tasks.data(), sizeof(LsdbFaTask) * nTasks);
+    memcpy(H + oLines, scanLines, sizeof(LsdbFaLine) * nL);
+    memcpy(H + oLoff, lineOff, sizeof(int) * (nFrames + 1));
+    memcpy(H + oPts, pts, 16 * (size_t)nP);
+    memcpy(H + oPoff, ptOff, sizeof(int) * (nFrames + 1));
+    memcpy(H + oLid, lidarPose, 16 * (size_t)nFrames);
+    memcpy(H + oLast, lastPose, 24 * (size_t)nFrames);
+    cudaStream_t s = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(D, H, oOut, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaEventRecord(ctx->faEv[0], s));
+    lsdb_launch_fa(s, nTasks, (LsdbFaTask*)(D + oTasks), (LsdbFaLine*)(D + oLines), (int*)(D + oLoff), (double*)(D + oPts),
+                   (int*)(D + oPoff), (double*)(D + oLid), (double*)(D + oLast), m->linesD, m->cacheD, m->cols, m->rows,
+                   4.0 * lsdm_atan(1.0), (LsdbFaHyp*)(D + oOut));
+    CK(ctx, cudaEventRecord(ctx->faEv[1], s));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(H + oOut, D + oOut, sizeof(LsdbFaHyp) * (size_t)nTasks * 4, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    CK(ctx, cudaEventElapsedTime(&ctx->faMs, ctx->faEv[0], ctx->faEv[1]));
+    memcpy(out, H + oOut, sizeof(LsdbFaHyp) * (size_t)nTasks * 4);
+    return LSDB_OK;
+}

@@ -1,0 +1,86 @@
+// Shared declarations of the sm_100a LSD pipeline (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lsd_math.h"
+
+// Per-map geometry, built once on the host (lsdb_batch_create) and read by every kernel.
+struct LsdbImg {
+    int cols, rows;       // source occupancy grid
+    int W, H;             // scaled image: floor(cols*sca), floor(rows*sca)  (LSD/myLSD.cpp:132-133)
+    int n;                // W*H
+    int srcPitch;         // bytes per source row in the device copy
+    int tile0;            // first stencil tile of this map
+    int tilesX, tilesY;
+    int pad_;
+    unsigned long long srcOff;   // byte offset of the map in the source buffer
+    unsigned long long nOff;     // element offset of the map in every per-pixel plane
+    unsigned long long segOff;   // element offset into the rect output
+    double logNT;                // 5*(log10(H)+log10(W))/2          (LSD/myLSD.cpp:207)
+    double regThre;              // -logNT/log10(angThre/180)        (:208)
+};
+
+// Per-map results produced on the device.
+struct LsdbImgDyn {
+    unsigned long long maxGradBits;  // bits of maxGrad (non-negative doubles order like integers)
+    int nCells;                      // length of the sorted seed list
+    int nSeg;                        // accepted segments
+    int err;                         // LSDB_ERR_* raised by a kernel for this map
+    int pad_;
+    long long stat[14];              // lsdb_stats fields
+};
+
+struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec logNFA
+
+// state word per scaled pixel (u32):
+//   bit 0   : usedMap == 1 (below gradient threshold, or member of an accepted region)
+//   bit 1   : usedMap == 2 (member of an NFA-rejected region)  [bit 0 wins]
+//   bit 8+w : pixel is in the region warp w of the owning CTA is currently growing (curMap)
+#define LSDB_ST_BAN 1u
+#define LSDB_ST_REJ 2u
+#define LSDB_ST_WARP_SHIFT 8
+
+#define LSDB_TILE 32            // stencil output tile (scaled pixels)
+#define LSDB_SRC_MAX 136        // max source-window edge of one tile
+#define LSDB_GROW_WARPS 16
+#define LSDB_CHUNK 32           // seed-list cells per ordered-commit chunk
+
+struct LsdbLsdConst {
+    double sca, degThre, gradThre, pi, aliPro, denThre;
+    int pseBin, h;
+    double taps[3 * 17];
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned int lsdb_ld_state(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// x86-64 cvttsd2si semantics for (int)double: NaN / out of range -> INT_MIN
+__device__ __forceinline__ int lsdb_x86_d2i(double v) {
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return (int)0x80000000;
+    return __double2int_rz(v);
+}
+#endif
+
+// launchers (defined in the .cu files, called from api.cu)
+void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
+                         const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg,
+                         unsigned int* state, double* gaussOut);
+void lsdb_launch_order(cudaStream_t s, int nImgs, const LsdbImg* imgs, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
+                       const double* mag, unsigned short* bins, unsigned int* cells);
+void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, const LsdbImg* imgs, LsdbImgDyn* dyn,
+                      const LsdbLsdConst* kc, const double* mag, const double* deg, unsigned int* state,
+                      const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
+                      unsigned int* lists, int listCap, const double* lgammaTab, int lgammaN, int* imgCounter);
+void lsdb_launch_lgamma_table(cudaStream_t s, double* tab, int n);
+void lsdb_launch_used_plane(cudaStream_t s, const unsigned int* state, uint8_t* used, int n);
+int lsdb_grow_max_ctas(int device);
+
+struct LsdbFaTask { int frame, iScan, iMap, pad; };
+struct LsdbFaHyp { int frame, iScan, iMap, iPair; double x, y, ang, score; };  // == lsdb_hypothesis
+struct LsdbFaLine { double k, b, dx, dy, x1, y1, x2, y2, len; int orient, pad; };  // == lsdb_line
+void lsdb_launch_fa(cudaStream_t s, int nTasks, const LsdbFaTask* tasks, const LsdbFaLine* scanLines, const int* scanLineOff,
+                    const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
+                    const LsdbFaLine* mapLines, const double* mapCache, int cols, int rows, double pi, LsdbFaHyp* out);

@@ -1,0 +1,54 @@
+"""The C-ABI boundary: liblsdb200.so loads, exports every symbol include/lsdb200.h declares, and fails loudly
+(no CPU fallback) when no B200 is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "lsdb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lsdb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lsdb):
+    L = lsdb.lib()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), n
+    assert b"sm_100a" in L.lsdb_version()
+
+
+def test_struct_layouts_match_reference(lsdb):
+    assert lsdb.LINE_DTYPE.itemsize == 80      # sizeof(structLinesInfo), LSD/baseFunc.h:33-44 (9 doubles + int + pad)
+    assert lsdb.HYP_DTYPE.itemsize == 48
+    assert [lsdb.LINE_DTYPE.fields[f][1] for f in ("k", "b", "dx", "dy", "x1", "y1", "x2", "y2", "len", "orient")] == \
+        [0, 8, 16, 24, 32, 40, 48, 56, 64, 72]
+
+
+def test_no_cpu_fallback(lsdb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lsdb.LsdbError):
+        lsdb.Context(0)
+    h = C.c_void_p()
+    assert lsdb.lib().lsdb_create(C.byref(h), 0, None) == 5 and not h     # LSDB_ERR_NO_DEVICE
+    assert lsdb.lib().lsdb_batch_run(None) != 0
+
+
+def test_product_does_not_touch_the_oracle():
+    """nothing under the package or include/ may reference oracle/ (the oracle is test infrastructure)"""
+    for base in ("linesegmentdetector-slam_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            if os.path.basename(dp) == "build":
+                continue
+            for f in fs:
+                if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py", "Makefile")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    assert "lsd_oracle" not in txt and "oraclebind" not in txt and "oracle/" not in txt, os.path.join(dp, f)

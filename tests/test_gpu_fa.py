@@ -1,0 +1,68 @@
+"""Parity of the CUDA association scoring (lsdb_fa_score) with the reference's golden scores and the oracle:
+poses bit-exact against the oracle, scores within the 1e-6 contract."""
+import os
+
+import numpy as np
+import pytest
+
+import oraclebind
+import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_fa_golden_frames_batched(lsdb, ctx):
+    g = np.load(os.path.join(GOLD, "fa_frames.npz"))
+    gm = np.load(os.path.join(GOLD, "bundled_maps.npz"))
+    mc = oraclebind.map_cache(gm["mapValue/map"], float(gm["mapValue/param"][2]))
+    nf = int(g["n_frames"])
+    frames = [dict(scan_lines=g[f"f{f}/scan_lines"], pts=g[f"f{f}/pts"], lidar_pose=g[f"f{f}/lidar_pose"],
+                   last_pose=g[f"f{f}/last_pose"]) for f in range(nf)]
+    fm = lsdb.FaMap(ctx, mc, g["map_lines"])
+    hyp = fm.score(frames)                     # all frames in ONE launch
+    pos = 0
+    for f in range(nf):
+        idx, want = g[f"f{f}/idx"], g[f"f{f}/val"]
+        h = hyp[pos:pos + len(idx)]; pos += len(idx)
+        assert np.all(h["frame"] == f)
+        assert np.array_equal(np.stack([h["i_scan"], h["i_map"], h["i_pair"]], 1), idx)
+        fin = np.isfinite(want[:, 3])
+        assert np.array_equal(np.isfinite(h["score"]), fin)
+        assert np.allclose(h["score"][fin], want[fin, 3], rtol=1e-6, atol=0)          # vs unmodified reference
+        for j, k in enumerate(("x", "y", "ang")):
+            assert np.allclose(h[k], want[:, j], rtol=1e-9, atol=1e-9)
+        oi, ov = oraclebind.fa_scores(frames[f]["scan_lines"], g["map_lines"], frames[f]["pts"], mc,
+                                      frames[f]["lidar_pose"], frames[f]["last_pose"])
+        assert np.array_equal(oi, idx)
+        for j, k in enumerate(("x", "y", "ang")):
+            assert np.array_equal(h[k], ov[:, j])                                      # poses: same bits as the oracle
+        assert np.allclose(h["score"][fin], ov[fin, 3], rtol=1e-12, atol=0)            # sums differ only by reassociation
+    assert pos == len(hyp)
+    assert fm.last_ms() > 0
+    fm.close()
+
+
+def test_fa_edge_cases(lsdb, ctx):
+    m = synth.occupancy_grid(500, 400, seed=31)
+    o = oraclebind.lsd(m)
+    mc = oraclebind.map_cache(m, 0.05)
+    fm = lsdb.FaMap(ctx, mc, o["lines"])
+    fr = synth.fake_scan_frame(m, o["lines"], seed=4)
+    empty = dict(scan_lines=np.zeros((0, 10)), pts=np.zeros((0, 2)), lidar_pose=[0, 0], last_pose=[-1, -1, 0])
+    short = dict(fr); short["scan_lines"] = fr["scan_lines"].copy(); short["scan_lines"][:, 8] = 10.0  # all < ignoreScanLength
+    nopts = dict(fr); nopts["pts"] = np.zeros((0, 2))
+    gated = dict(fr); gated["last_pose"] = np.array([1e6, 1e6, 0.0])
+    hyp = fm.score([empty, short, fr, nopts, gated])
+    assert not np.any(hyp["frame"] <= 1)
+    for f, frame in [(2, fr), (3, nopts), (4, gated)]:
+        h = hyp[hyp["frame"] == f]
+        oi, ov = oraclebind.fa_scores(frame["scan_lines"], o["lines"], frame["pts"], mc, frame["lidar_pose"], frame["last_pose"])
+        assert len(h) == len(oi) and len(h) > 0
+        fin = np.isfinite(ov[:, 3])
+        assert np.array_equal(np.isfinite(h["score"]), fin)
+        assert np.allclose(h["score"][fin], ov[fin, 3], rtol=1e-9)
+        if f != 2:
+            assert not fin.any()
+    assert fm.score([]).shape == (0,)
+    fm.close()

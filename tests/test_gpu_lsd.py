@@ -1,0 +1,131 @@
+"""Parity of the CUDA LSD path (through the C ABI) with the oracle and with the reference's golden outputs.
+Bit-exact: mag, deg (vs the oracle on the same arithmetic), seed order, used-map, labels, segment table, lineIm."""
+import os
+
+import numpy as np
+import pytest
+
+import oraclebind
+import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = ["mapValue", "mapValue_aisle1", "mapValue_aisle2", "mapValue_aisle3", "mapValue_map1", "mapValue_map2"]
+
+
+def _compare_with_oracle(lsdb, b, i, m, got, check_planes=True):
+    o = oraclebind.lsd(m)
+    W = o["used"].shape[1]
+    assert got["counts"][i] == o["n"]
+    pl = b.planes(i)
+    if check_planes:
+        assert np.array_equal(pl["mag"], o["mag"])
+        assert np.array_equal(pl["deg"], o["deg"])
+    assert np.array_equal(pl["seeds"], o["seeds"][:, 2] * W + o["seeds"][:, 1])
+    assert np.array_equal(pl["used"], o["used"])
+    assert np.array_equal(pl["labels"], o["labels"])
+    assert np.array_equal(lsdb.lines_to_array(got["lines"][i]), o["lines"], equal_nan=True)
+    assert np.array_equal(got["rects"][i], o["rects"], equal_nan=True)      # rectangles and log-NFA, bit for bit
+    assert np.array_equal(b.line_image(i), o["line_im"])
+    return o
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "bundled_maps.npz"))
+
+
+def test_bundled_maps_batched_bit_exact(lsdb, ctx, gold):
+    """BASELINE config 2: all bundled maps in one batch; golden = unmodified reference (stock glibc)."""
+    maps = [gold[n + "/map"] for n in NAMES]
+    b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for m in maps])
+    b.upload(maps); b.run()
+    got = b.download(want_rects=True)
+    for i, n in enumerate(NAMES):
+        o = _compare_with_oracle(lsdb, b, i, maps[i], got)
+        pl = b.planes(i)
+        assert got["counts"][i] == len(gold[n + "/lines"])
+        assert np.array_equal(lsdb.lines_to_array(got["lines"][i]), gold[n + "/lines"], equal_nan=True)
+        assert np.array_equal(pl["used"], gold[n + "/used"])
+        assert np.array_equal((pl["labels"] & 0xFF).astype(np.uint8), gold[n + "/reg_idx"])
+        assert np.array_equal(pl["seeds"], gold[n + "/seeds"])
+        assert np.array_equal(np.packbits(b.line_image(i) > 0), gold[n + "/line_im_bits"])
+    st = b.stats()
+    assert st["accepts"] == sum(len(gold[n + "/lines"]) for n in NAMES)
+    b.close()
+
+
+def test_single_map_call_matches_reference_entry_point(lsdb, ctx, gold):
+    """lsdb_lsd = the body behind mylsd::myLineSegmentDetector (config 1)."""
+    m = gold["mapValue/map"]
+    r = ctx.lsd(m, want_remap=True)
+    o = oraclebind.lsd(m)
+    assert r["n"] == 41
+    assert np.array_equal(lsdb.lines_to_array(r["lines"]), gold["mapValue/lines"], equal_nan=True)
+    assert np.array_equal(r["line_im"], o["line_im"]) and np.array_equal(r["map_out"], o["map_out"])
+    r2 = ctx.lsd(m)   # cached batch, second call identical
+    assert np.array_equal(lsdb.lines_to_array(r2["lines"]), lsdb.lines_to_array(r["lines"]), equal_nan=True)
+
+
+@pytest.mark.parametrize("shape,seed", [((600, 400), 7), ((333, 901), 22), ((64, 50), 23), ((1377, 428), 11),
+                                         ((40, 34), 3), ((2048, 2048), 1000)])
+def test_synthetic_maps_vs_oracle(lsdb, ctx, shape, seed):
+    m = synth.occupancy_grid(shape[0], shape[1], seed=seed)
+    b = lsdb.Batch(ctx, [shape])
+    b.upload([m]); b.run()
+    got = b.download(want_rects=True)
+    _compare_with_oracle(lsdb, b, 0, m, got)
+    b.close()
+
+
+def test_ragged_batch_and_determinism(lsdb, ctx):
+    shapes = [(500, 300), (34, 40), (777, 555), (128, 128), (1000, 90), (90, 1000), (600, 400)]
+    maps = [synth.occupancy_grid(c, r, seed=100 + i) for i, (c, r) in enumerate(shapes)]
+    b = lsdb.Batch(ctx, shapes)
+    b.upload(maps); b.run()
+    got = b.download(want_rects=True)
+    for i, m in enumerate(maps):
+        _compare_with_oracle(lsdb, b, i, m, got)
+    b.run()   # same resident inputs again: identical output (the commit order is deterministic)
+    got2 = b.download(want_rects=True)
+    assert np.array_equal(got["counts"], got2["counts"])
+    for i in range(len(maps)):
+        assert np.array_equal(got["rects"][i], got2["rects"][i], equal_nan=True)
+    b.close()
+
+
+def test_edge_cases(lsdb, ctx):
+    blank = np.zeros((120, 160), np.uint8)                      # maxGrad == 0: no seeds, no segments
+    full = np.ones((120, 160), np.uint8)                        # everything occupied: flat interior
+    unknown = np.full((100, 100), 255, np.uint8)
+    one = np.zeros((90, 90), np.uint8); one[45, 10:80] = 1      # a single 1-px wall
+    border = np.zeros((90, 120), np.uint8); border[0, :] = 1; border[:, 0] = 1; border[30, :] = 1
+    tiny = np.zeros((7, 9), np.uint8); tiny[3, :] = 1           # scaled image 2x2
+    maps = [blank, full, unknown, one, border, tiny]
+    b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for m in maps])
+    b.upload(maps); b.run()
+    got = b.download(want_rects=True)
+    assert got["counts"][0] == 0 and got["counts"][2] == 0
+    for i, m in enumerate(maps):
+        _compare_with_oracle(lsdb, b, i, m, got)
+    b.close()
+
+
+def test_full_size_map_vs_oracle(lsdb, ctx):
+    """BASELINE config 3 shape (4096x4096): one map compared in full with the oracle, plus size-independent
+    properties: every accepted pixel is banned, labels are 1..n, seed list sorted by (bin desc, raster asc)."""
+    m = synth.occupancy_grid(4096, 4096, seed=1000)
+    b = lsdb.Batch(ctx, [(4096, 4096)])
+    b.upload([m]); b.run()
+    got = b.download(want_rects=True)
+    _compare_with_oracle(lsdb, b, 0, m, got)
+    pl = b.planes(0)
+    n = got["counts"][0]
+    assert n > 100
+    assert set(np.unique(pl["labels"])) == set(range(0, n + 1))
+    assert np.all(pl["used"][pl["labels"] > 0] == 1)
+    zoom = 1024.0 / pl["max_grad"]
+    bins = np.minimum(np.floor(pl["mag"].ravel()[pl["seeds"]] * zoom), 1024)
+    key = bins * 2.0 ** 32 - pl["seeds"]
+    assert np.all(np.diff(key) < 0)
+    b.close()
