@@ -1,0 +1,282 @@
+#!/usr/bin/env python3
+"""bench.py — LSD throughput on synthetic 4096x4096 occupancy grids (BASELINE.json configs[2]).
+
+A "step" = one pass of the LSD hot path (remap + Gaussian + gradient, pseudo-ordering, region grow /
+rectangle / NFA) over one batch of `--maps-per-gpu` (256) synthetic maps per GPU.  Weak scaling: every
+rank owns its own 256 maps (seed 1000 + global index), no data-path collective.
+  value : whole-job source Mpixel/s with the maps already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the C ABI with HOST buffers — H2D of the maps + run + D2H of the segments
+          inside the timed region
+  roofline : the HBM-bound stencil kernel, algorithmic bytes N + 17n per map over its measured time
+  cpu_baseline : the unmodified reference (oracle/_ref, stock glibc) on a bounded sample of the same maps
+`--impl reference` times that CPU reference alone (rank 0 only), one map per host thread.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "lsd_source_mpixel_per_s"
+UNIT = "Mpixel/s"
+
+
+def make_map(size, gidx):
+    import synth
+    return synth.occupancy_grid(size, size, seed=1000 + gidx)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_throughput(size, n_maps, threads, first_gidx=0):
+    """The unmodified reference myLineSegmentDetector (oracle/_ref, stock glibc) on n_maps of the workload,
+    one map per host thread (the reference is single-threaded per map; ctypes releases the GIL)."""
+    import refbind
+    if not refbind.available("glibc"):
+        return None
+    maps = [make_map(size, first_gidx + i) for i in range(n_maps)]
+    counts = [0] * n_maps
+
+    def work(tid):
+        for i in range(tid, n_maps, threads):
+            counts[i] = refbind.ref_lsd(maps[i], want_maps=False)["n"]
+
+    t0 = time.time()
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    dt = time.time() - t0
+    return dict(seconds=dt, mpix_per_s=n_maps * size * size / dt / 1e6, segments=int(sum(counts)), n_maps=n_maps)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(cores, args.ref_threads or cores)
+    k_run, w_run = min(args.steps, 3), min(args.warmup, 1)   # every step is >= one 4096^2 map per thread (~30 s)
+    sample = f"{threads} maps of {args.size}x{args.size} per step, one per host thread (of the {args.maps_per_gpu}-map batch)"
+    for s in range(w_run):
+        r = cpu_reference_throughput(args.size, threads, threads)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_glibc.so not built"}))
+            return
+    t_all, px = 0.0, 0
+    for s in range(k_run):
+        r = cpu_reference_throughput(args.size, threads, threads, first_gidx=s * threads)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_glibc.so not built"}))
+            return
+        t_all += r["seconds"]; px += r["n_maps"] * args.size * args.size
+    v = px / t_all / 1e6
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": k_run, "warmup": w_run,
+        "ms_per_step": t_all / k_run * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"synthetic {args.size}x{args.size} occupancy grids (BASELINE configs[2])",
+                                        "maps_per_step": threads, "note": "steps/warmup capped at 3/1: one step is ~30 s of CPU per thread"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--maps-per-gpu", type=int, default=256)
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--cpu-sample-maps", type=int, default=0, help="maps for the cpu_baseline leg (0 = one per core, max 8)")
+    ap.add_argument("--ref-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from __graft_entry__ import load_package
+    lsdb = load_package()
+    stream = torch.cuda.Stream()          # an explicit stream: its handle is what the library launches on
+    torch.cuda.set_stream(stream)
+    ctx = lsdb.Context(local, stream.cuda_stream)
+
+    n, size = args.maps_per_gpu, args.size
+    host = torch.empty((n, size, size), dtype=torch.uint8).pin_memory()
+    hnp = host.numpy()
+    for i in range(n):
+        hnp[i] = make_map(size, rank * n + i)
+    ptrs = [int(hnp[i].ctypes.data) for i in range(n)]
+    batch = lsdb.Batch(ctx, [(size, size)] * n)
+    W = batch.scaled(0)[0]; npx = W * batch.scaled(0)[1]
+    src_px = n * size * size
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident: inputs already in HBM
+    batch.upload(ptrs)
+    for _ in range(args.warmup):
+        batch.run()
+    batch.sync()
+    stage_acc = {k: 0.0 for k in lsdb.STAGES}
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        batch.run()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    # per-stage times of the last step (events on the same stream, recorded by the library)
+    batch.run(); batch.sync()
+    last = batch.stage_ms()
+    stats = batch.stats()
+    counts = batch.counts()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * src_px / (ms_step * 1e-3) / 1e6
+
+    # ---------------- end to end through the C ABI with host buffers
+    for _ in range(1):
+        batch.upload(ptrs); batch.run(); batch.download()
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        batch.upload(ptrs); batch.run(); out = batch.download()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * src_px / (float(dt.item()) / args.steps) / 1e6
+    nseg = int(out["counts"].sum())
+    d2h = n * 4 * 32 + nseg * 13 * 8   # per-map result records + one rectangle record per segment
+
+    segs = torch.tensor([float(counts.sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(segs)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s"
+        alg_bytes = n * (size * size + 17 * npx)          # read N source bytes, write mag(8)+deg(8)+used(1) per scaled pixel
+        achieved = alg_bytes / (last["stencil"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic {size}x{size} occupancy grids, batch {n} per GPU (BASELINE configs[2])",
+                       "maps_per_gpu": n, "global_batch": n * world, "parallelism": f"map-sharded x{world}, no collective",
+                       "l2": f"inputs {n * size * size / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed"},
+            "segments_per_s": float(segs.item()) / (ms_step * 1e-3), "segments_per_step": float(segs.item()),
+            "p50_ms_per_map": ms_step / n,
+            "stage_ms": last,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * size * size, "d2h_bytes_per_step": d2h},
+            "gpu_launches": batch.launches() * args.steps,
+            "clocks": clocks,
+            "roofline": {"kernel": "lsdb_stencil_kernel (remap+Gaussian+gradient)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": last["stencil"],
+                         "share_of_step": last["stencil"] / sum(last.values())},
+            "grow_stage": {"bound": "latency", "ms": last["grow"], "share_of_step": last["grow"] / sum(last.values()),
+                           "seeds_per_s": stats["live_seeds"] / (last["grow"] * 1e-3),
+                           "committed_regions_per_s": (stats["accepts"] + stats["rejects"]) / (last["grow"] * 1e-3),
+                           "respeculated_frac": stats["respec_evals"] / max(1, stats["live_seeds"])},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            import refbind
+            cores = os.cpu_count() or 1
+            if refbind.available("glibc"):
+                nm = args.cpu_sample_maps or min(cores, 8)
+                th = min(cores, nm)
+                r = cpu_reference_throughput(size, nm, th)
+                line["cpu_baseline"] = {"value": r["mpix_per_s"], "unit": UNIT, "cores": th, "kind": "reference",
+                                        "sample": f"{nm} of the {n} maps ({size}x{size}), one per host thread, {r['seconds']:.1f} s",
+                                        "segments": r["segments"]}
+            else:
+                import oraclebind
+                t0 = time.time(); o = oraclebind.lsd(hnp[0], want_maps=False, want_line_im=False); dt1 = time.time() - t0
+                line["cpu_baseline"] = {"value": size * size / dt1 / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": f"1 of the {n} maps, oracle C port, {dt1:.2f} s"}
+        print(json.dumps(line))
+    batch.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,10 @@ enum { LSDB_STAGE_STENCIL = 0, LSDB_STAGE_ORDER = 1, LSDB_STAGE_GROW = 2, LSDB_N
 typedef struct {
     long long cells, live_seeds, grows, grown_px, small, regrows, rrr_passes, nfa_calls, nfa_px,
         rejects, accepts, spec_evals, respec_evals, chunks;
+    /* SM cycles summed over the warps of the region pipeline (lane-0 clock64 deltas): time inside
+     * RegionGrower / RectangleConverter / RectangleNFACalculator, waiting for the commit frontier,
+     * in the retire phase and in the speculative phase */
+    long long cyc_grow, cyc_rect, cyc_nfa, cyc_wait, cyc_retire, cyc_spec;
 } lsdb_stats;
 
 /* ---- context ---- */

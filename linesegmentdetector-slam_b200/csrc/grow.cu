@@ -34,7 +34,9 @@
 
 enum { OC_NONE = 0, OC_NOCHANGE = 1, OC_REJECT = 2, OC_ACCEPT = 3, OC_DEFER = 4 };
 enum { ST_CELLS = 0, ST_LIVE, ST_GROWS, ST_GROWNPX, ST_SMALL, ST_REGROWS, ST_RRR, ST_NFACALLS, ST_NFAPX, ST_REJECTS,
-       ST_ACCEPTS, ST_SPEC, ST_RESPEC, ST_CHUNKS, ST_N };
+       ST_ACCEPTS, ST_SPEC, ST_RESPEC, ST_CHUNKS, ST_N,
+       // cycle counters (lane 0 of every warp, summed): only kept in LSDB_TIMING builds, reported through stat[] slots 14..19
+       TM_GROW = ST_N, TM_RECT, TM_NFA, TM_WAIT, TM_RETIRE, TM_SPEC, TM_N };
 
 struct GrowShared {
     volatile int frontier;
@@ -46,13 +48,20 @@ struct GrowShared {
     int nChunks;
     int nCells;
     unsigned int logBox[LOG_CAP][2];
-    unsigned long long stats[ST_N];
+    unsigned long long stats[TM_N];
 };
 
 struct Rect { double x1, y1, x2, y2, wid, cX, cY, deg, dx, dy, p, prec; };
 
 struct BBox { int x0, y0, x1, y1; };
 
+#if 1  /* cycle counters are cheap (one clock64 + one smem atomic per measured call) and feed bench.py */
+#define TIC long long t0_ = clock64()
+#define TOC(c, idx) do { if ((c).lane == 0) atomicAdd(&(c).sh->stats[idx], (unsigned long long)(clock64() - t0_)); } while (0)
+#else
+#define TIC
+#define TOC(c, idx)
+#endif
 #define STAT(c, idx, v) do { if ((c).lane == 0) atomicAdd(&(c).sh->stats[idx], (unsigned long long)(v)); } while (0)
 
 struct WarpCtx {
@@ -103,6 +112,7 @@ __device__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double de
     const int W = c.W, H = c.H;
     const double pi = c.kc->pi;
     const double pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
+    TIC;
     double sinDeg = d_sin(regDeg), cosDeg = d_cos(regDeg);
     if (c.lane == 0) {
         c.list[0] = pack_xy(sx, sy);
@@ -154,6 +164,7 @@ __device__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double de
         }
     }
     STAT(c, ST_GROWS, 1); STAT(c, ST_GROWNPX, num);
+    TOC(c, TM_GROW);
     return num;
 }
 
@@ -162,6 +173,7 @@ __device__ Rect rect_from_region(const WarpCtx& c, const unsigned int* lst, int 
                                  double degThre) {
     const int W = c.W;
     const double pi = c.kc->pi;
+    TIC;
     double cenX = 0, cenY = 0, weiSum = 0;
     for (int base = 0; base < num; base += 32) {  // CenterGetter :608-613, sums in list order
         const int k = base + c.lane;
@@ -233,6 +245,7 @@ __device__ Rect rect_from_region(const WarpCtx& c, const unsigned int* lst, int 
     r.cX = cenX; r.cY = cenY; r.deg = inertiaDeg; r.dx = dx; r.dy = dy;
     r.p = aliPro; r.prec = degThre;
     if (r.wid < 1) r.wid = 1;
+    TOC(c, TM_RECT);
     return r;
 }
 
@@ -276,7 +289,7 @@ __global__ void lsdb_lgamma_table_kernel(double* tab, int n) {
 }
 
 // ------------------------------------------------------------------ RectangleNFACalculator (:926-1059)
-__device__ double rect_nfa(WarpCtx& c, const Rect& rec, double logNT) {
+__device__ double rect_nfa_impl(WarpCtx& c, const Rect& rec, double logNT) {
     const int xLim = c.W, yLim = c.H;
     const double pi = c.kc->pi;
     const double pi32 = pi * 3 / 2.0, pi2 = 2 * pi;
@@ -357,6 +370,13 @@ __device__ double rect_nfa(WarpCtx& c, const Rect& rec, double logNT) {
         }
     }
     return -d_log10(binTail) - logNT;
+}
+
+__device__ double rect_nfa(WarpCtx& c, const Rect& rec, double logNT) {
+    TIC;
+    const double v = rect_nfa_impl(c, rec, logNT);
+    TOC(c, TM_NFA);
+    return v;
 }
 
 // ------------------------------------------------------------------ RectangleImprover (:1061-1158)
@@ -627,7 +647,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lsdb_grow_kernel(int nImgs, const 
                 sh.nChunks = (sh.nCells + LSDB_CHUNK - 1) / LSDB_CHUNK;
             }
         }
-        if (tid < ST_N) sh.stats[tid] = 0;
+        if (tid < TM_N) sh.stats[tid] = 0;
         __syncthreads();
         const int img = sh.img;
         if (img >= nImgs) break;
@@ -658,6 +678,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lsdb_grow_kernel(int nImgs, const 
 
             // ---------------- speculative phase
             unsigned int rem = liveMask;
+            long long tSpec = clock64();
             while (rem && sh.frontier != chunk && !sh.abortFlag) {
                 const int k = __ffs(rem) - 1;
                 rem &= rem - 1;
@@ -673,6 +694,8 @@ __global__ void __launch_bounds__(NW * 32, 1) lsdb_grow_kernel(int nImgs, const 
             }
 
             // ---------------- wait for every earlier chunk to retire
+            long long tWait = clock64();
+            if (lane == 0) atomicAdd(&sh.stats[TM_SPEC], (unsigned long long)(tWait - tSpec));
             if (lane == 0) {
                 unsigned int spins = 0;
                 while (sh.frontier != chunk && !sh.abortFlag) {
@@ -685,6 +708,8 @@ __global__ void __launch_bounds__(NW * 32, 1) lsdb_grow_kernel(int nImgs, const 
             if (sh.abortFlag) break;
 
             // ---------------- retire phase: in seed order, validate or re-evaluate, commit
+            long long tRet = clock64();
+            if (lane == 0) atomicAdd(&sh.stats[TM_WAIT], (unsigned long long)(tRet - tWait));
             rem = liveMask;
             while (rem) {
                 const int k = __ffs(rem) - 1;
@@ -713,6 +738,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lsdb_grow_kernel(int nImgs, const 
             __syncwarp();
             __threadfence_block();
             if (lane == 0) { atomicAdd(&sh.stats[ST_CHUNKS], 1ull); sh.frontier = chunk + 1; }
+            if (lane == 0) atomicAdd(&sh.stats[TM_RETIRE], (unsigned long long)(clock64() - tRet));
         }
         __syncthreads();
         if (tid == 0) {
@@ -721,7 +747,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lsdb_grow_kernel(int nImgs, const 
             sh.stats[ST_CELLS] = nCells;
         }
         __syncthreads();
-        if (tid < ST_N) dyn[img].stat[tid] = (long long)sh.stats[tid];
+        if (tid < TM_N) dyn[img].stat[tid] = (long long)sh.stats[tid];
     }
 }
 

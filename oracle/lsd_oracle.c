@@ -26,6 +26,12 @@ static int x86_d2i(double v) {
     return (int)v;
 }
 
+/* optional debug tap: sizes of every region grown (set by lsdo_set_grow_size_log) */
+static int* lsdo_grow_size_log = 0;
+static int lsdo_grow_size_cap = 0, lsdo_grow_size_n = 0;
+void lsdo_set_grow_size_log(int* buf, int cap) { lsdo_grow_size_log = buf; lsdo_grow_size_cap = cap; lsdo_grow_size_n = 0; }
+int lsdo_grow_size_count(void) { return lsdo_grow_size_n; }
+
 typedef struct {
     int W, H;
     const double* deg;
@@ -155,6 +161,7 @@ static void region_grower(ctx_t* c, int x, int y, double regDeg, double degThre,
     memcpy(c->tpy, reg->py, sizeof(int) * (size_t)growNum);
     c->tnum = growNum;
     if (c->st) { c->st->grows++; c->st->grown_px += growNum; }
+    if (lsdo_grow_size_log && lsdo_grow_size_n < lsdo_grow_size_cap) lsdo_grow_size_log[lsdo_grow_size_n++] = growNum;
 }
 
 /* CenterGetter :592-619, OrientationGetter :621-667, RectangleConverter :669-734 */

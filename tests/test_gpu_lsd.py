@@ -97,7 +97,7 @@ def test_ragged_batch_and_determinism(lsdb, ctx):
 def test_edge_cases(lsdb, ctx):
     blank = np.zeros((120, 160), np.uint8)                      # maxGrad == 0: no seeds, no segments
     full = np.ones((120, 160), np.uint8)                        # everything occupied: flat interior
-    unknown = np.full((100, 100), 255, np.uint8)
+    unknown = np.full((100, 100), 255, np.uint8)               # row 0 / col 0 keep 255 (not remapped): a border edge
     one = np.zeros((90, 90), np.uint8); one[45, 10:80] = 1      # a single 1-px wall
     border = np.zeros((90, 120), np.uint8); border[0, :] = 1; border[:, 0] = 1; border[30, :] = 1
     tiny = np.zeros((7, 9), np.uint8); tiny[3, :] = 1           # scaled image 2x2
@@ -105,7 +105,7 @@ def test_edge_cases(lsdb, ctx):
     b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for m in maps])
     b.upload(maps); b.run()
     got = b.download(want_rects=True)
-    assert got["counts"][0] == 0 and got["counts"][2] == 0
+    assert got["counts"][0] == 0
     for i, m in enumerate(maps):
         _compare_with_oracle(lsdb, b, i, m, got)
     b.close()
