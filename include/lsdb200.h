@@ -65,8 +65,8 @@ typedef struct {
         rejects, accepts, spec_evals, respec_evals, chunks;
     /* SM cycles summed over the warps of the region pipeline (lane-0 clock64 deltas): time inside
      * RegionGrower / RectangleConverter / RectangleNFACalculator, waiting for the commit frontier,
-     * in the retire phase and in the speculative phase */
-    long long cyc_grow, cyc_rect, cyc_nfa, cyc_wait, cyc_retire, cyc_spec;
+     * in the retire phase, in the speculative phase, and in frontier re-evaluations */
+    long long cyc_grow, cyc_rect, cyc_nfa, cyc_wait, cyc_retire, cyc_spec, cyc_respec;
 } lsdb_stats;
 
 /* ---- context ---- */

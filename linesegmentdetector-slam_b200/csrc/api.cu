@@ -32,14 +32,14 @@ struct lsdb_batch {
     lsdb_ctx* ctx;
     int n;
     lsdb_lsd_params params;
-    int maxSeg, listCap, nTiles, nCtas;
+    int maxSeg, listCap, arenaCap, nTiles, nCtas, nWarps, runAhead;
     size_t totalN, totalSrc;
     std::vector<LsdbImg> imgs;
     LsdbLsdConst kc;
     // device
-    uint8_t* src; double* mag; double* deg; unsigned int* state; unsigned short* bins; unsigned int* cells;
+    uint8_t* src; double* mag; double* deg; double* cosm; double* sinm; unsigned int* state; unsigned short* bins; unsigned int* cells;
     int* labels; LsdbRect* rects; LsdbImgDyn* dyn; LsdbImg* imgsD; int* tileImg; unsigned int* lists;
-    int* imgCounter; LsdbLsdConst* kcD; double* gaussDbg;
+    int* imgCounter; LsdbLsdConst* kcD; double* gaussDbg; unsigned char* recBuf;
     // host (pinned)
     LsdbImgDyn* dynH; LsdbRect* rectsH;
     cudaEvent_t ev[4];
@@ -89,7 +89,7 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
     if (cudaMalloc(&c->lgammaTab, sizeof(double) * c->lgammaN) != cudaSuccess) { delete c; return LSDB_ERR_CUDA; }
     lsdb_launch_lgamma_table(c->stream, c->lgammaTab, c->lgammaN);
     cudaEventCreate(&c->faEv[0]); cudaEventCreate(&c->faEv[1]);
-    c->maxGrowCtas = lsdb_grow_max_ctas(device);
+    c->maxGrowCtas = 0;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFree(c->lgammaTab); delete c; return LSDB_ERR_CUDA; }
     *out = c;
     return LSDB_OK;
@@ -130,9 +130,9 @@ static int gauss_taps(double sca, double sig, double* out) {
 extern "C" void lsdb_batch_destroy(lsdb_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    cudaFree(b->src); cudaFree(b->mag); cudaFree(b->deg); cudaFree(b->state); cudaFree(b->bins); cudaFree(b->cells);
+    cudaFree(b->src); cudaFree(b->mag); cudaFree(b->deg); cudaFree(b->cosm); cudaFree(b->sinm); cudaFree(b->state); cudaFree(b->bins); cudaFree(b->cells);
     cudaFree(b->labels); cudaFree(b->rects); cudaFree(b->dyn); cudaFree(b->imgsD); cudaFree(b->tileImg); cudaFree(b->lists);
-    cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg);
+    cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg); cudaFree(b->recBuf);
     cudaFreeHost(b->dynH); cudaFreeHost(b->rectsH);
     for (int i = 0; i < 4; i++) cudaEventDestroy(b->ev[i]);
     if (b->ctx->cached == b) b->ctx->cached = 0;
@@ -149,8 +149,8 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     lsdb_batch* b = new lsdb_batch();
     memset(&b->kc, 0, sizeof b->kc);
     b->ctx = ctx; b->n = n; b->params = *prm; b->ran = false; b->downloaded = false; b->launches = 0;
-    b->src = 0; b->mag = 0; b->deg = 0; b->state = 0; b->bins = 0; b->cells = 0; b->labels = 0; b->rects = 0; b->dyn = 0;
-    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->dynH = 0; b->rectsH = 0;
+    b->src = 0; b->mag = 0; b->deg = 0; b->cosm = 0; b->sinm = 0; b->state = 0; b->bins = 0; b->cells = 0; b->labels = 0; b->rects = 0; b->dyn = 0;
+    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->dynH = 0; b->rectsH = 0;
     for (int i = 0; i < 4; i++) cudaEventCreate(&b->ev[i]);
     b->maxSeg = maxLines > 0 ? maxLines : 4096;
 
@@ -162,6 +162,13 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     b->kc.gradThre = 2.0 / lsdm_sin(b->kc.degThre);        // :149
     b->kc.aliPro = prm->angThre / 180.0;                   // :209
     b->kc.denThre = prm->denThre;
+    b->kc.cosDegThre = lsdm_cos(b->kc.degThre);
+    {
+        double p = b->kc.aliPro;
+        for (int k = 0; k < LSDB_NP; k++, p /= 2.0) {
+            b->kc.pTab[k] = p; b->kc.logP[k] = lsdm_log(p); b->kc.log1mP[k] = lsdm_log(1 - p); b->kc.log10P[k] = lsdm_log10(p);
+        }
+    }
 
     b->imgs.resize(n);
     size_t srcOff = 0, nOff = 0;
@@ -188,16 +195,30 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         if (im.n > maxN) maxN = im.n;
     }
     b->nTiles = tile0; b->totalN = nOff; b->totalSrc = srcOff;
-    b->listCap = maxN + 2 < (1 << 16) ? maxN + 2 : (1 << 16);
-    b->nCtas = n < ctx->maxGrowCtas ? n : ctx->maxGrowCtas;
+    b->listCap = maxN + 2 < (1 << 16) ? ((maxN + 2 + 1) & ~1) : (1 << 16);  // even: the arena behind it holds doubles
+    {   // team size: spread the device's warp slots over the maps of the batch (16 warps for a lone map,
+        // 8 when ~2 maps share an SM, ...); every CTA grows one map at a time
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        int nw = LSDB_GROW_WARPS;
+        while (nw > 4 && (long long)n * nw > (long long)sms * LSDB_GROW_WARPS) nw >>= 1;
+        if (getenv("LSDB_GROW_WARPS")) { int v = atoi(getenv("LSDB_GROW_WARPS")); if (v >= 1 && v <= LSDB_GROW_WARPS) nw = v; }
+        b->nWarps = nw;
+        b->runAhead = 8 * nw;   // chunks a map's team may speculate ahead of its commit frontier
+        if (getenv("LSDB_RUNAHEAD")) b->runAhead = atoi(getenv("LSDB_RUNAHEAD"));
+        const int maxCtas = lsdb_grow_max_ctas(ctx->device, nw);
+        b->nCtas = n < maxCtas ? n : maxCtas;
+    }
 
     cudaError_t e = cudaSuccess;
 #define AL(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
-    AL(b->src, b->totalSrc + 64); AL(b->mag, b->totalN * 8); AL(b->deg, b->totalN * 8); AL(b->state, b->totalN * 4);
+    AL(b->src, b->totalSrc + 64); AL(b->mag, b->totalN * 8); AL(b->deg, b->totalN * 8); AL(b->cosm, b->totalN * 8); AL(b->sinm, b->totalN * 8); AL(b->state, b->totalN * 4);
     AL(b->bins, b->totalN * 2); AL(b->cells, b->totalN * 4); AL(b->labels, b->totalN * 4);
     AL(b->rects, (size_t)n * b->maxSeg * sizeof(LsdbRect)); AL(b->dyn, (size_t)n * sizeof(LsdbImgDyn));
     AL(b->imgsD, (size_t)n * sizeof(LsdbImg)); AL(b->tileImg, (size_t)b->nTiles * sizeof(int));
-    AL(b->lists, (size_t)b->nCtas * LSDB_GROW_WARPS * 2 * (size_t)b->listCap * 4);
+    b->arenaCap = 2 * b->listCap < (1 << 15) ? (1 << 15) : 2 * b->listCap;
+    AL(b->lists, (size_t)b->nCtas * b->nWarps * lsdb_grow_list_words_per_warp(b->listCap, b->arenaCap) * 4);
+    AL(b->recBuf, (size_t)b->nCtas * lsdb_grow_rec_bytes_per_cta());
     AL(b->imgCounter, 64); AL(b->kcD, sizeof(LsdbLsdConst));
 #undef AL
     if (e == cudaSuccess) e = cudaMallocHost((void**)&b->dynH, (size_t)n * sizeof(LsdbImgDyn));
@@ -235,12 +256,12 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaMemsetAsync(b->labels, 0, b->totalN * 4, s));
     CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
     CK(ctx, cudaEventRecord(b->ev[0], s));
-    lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->state, b->gaussDbg);
+    lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->gaussDbg);
     CK(ctx, cudaEventRecord(b->ev[1], s));
     lsdb_launch_order(s, b->n, b->imgsD, b->dyn, b->kcD, b->mag, b->bins, b->cells);
     CK(ctx, cudaEventRecord(b->ev[2], s));
-    lsdb_launch_grow(s, b->n, b->nCtas, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->state, b->cells, b->labels, b->rects,
-                     b->maxSeg, b->lists, b->listCap, ctx->lgammaTab, ctx->lgammaN, b->imgCounter);
+    lsdb_launch_grow(s, b->n, b->nCtas, b->nWarps, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->cosm, b->sinm, b->state, b->cells, b->labels, b->rects,
+                     b->maxSeg, b->lists, b->listCap, b->arenaCap, b->runAhead, b->recBuf, ctx->lgammaTab, ctx->lgammaN, b->imgCounter);
     CK(ctx, cudaEventRecord(b->ev[3], s));
     CK(ctx, cudaGetLastError());
     b->ran = true; b->downloaded = false; b->launches = 3;
@@ -378,9 +399,9 @@ extern "C" int lsdb_batch_stats(lsdb_batch* b, lsdb_stats* total) {
     int rc = fetch_dyn(b);
     if (rc) return rc;
     long long* t = (long long*)total;
-    for (int k = 0; k < 20; k++) t[k] = 0;
+    for (int k = 0; k < 21; k++) t[k] = 0;
     for (int i = 0; i < b->n; i++)
-        for (int k = 0; k < 20; k++) t[k] += b->dynH[i].stat[k];
+        for (int k = 0; k < 21; k++) t[k] += b->dynH[i].stat[k];
     return LSDB_OK;
 }
 

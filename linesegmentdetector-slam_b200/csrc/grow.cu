@@ -11,24 +11,29 @@
 // kept: a warp replays one region in the reference's exact candidate order (lanes only evaluate
 // the 32 next neighbour candidates in parallel; accepts are applied one at a time), and regions
 // are RETIRED strictly in seed order:
-//   * the sorted seed list is cut into chunks of 32 cells; warps take chunks by ticket;
-//   * a warp evaluates the live seeds of its chunk speculatively against the current state;
-//   * it then waits until every earlier chunk has retired (frontier == its ticket) and validates
-//     each evaluation: it stands iff no region ACCEPTED since the evaluation started overlaps the
-//     bounding box of the pixels the evaluation examined (regions that are too small, fail
-//     refinement or are NFA-rejected never change what growth sees — SURVEY.md §0 fact 4);
-//     otherwise the seed is simply re-evaluated at the frontier, where the state is final;
+//   * the sorted seed list is cut into chunks of 32 cells; warps claim chunks by ticket and may run
+//     up to RING chunks ahead of the commit frontier;
+//   * a warp evaluates the live seeds of its chunk speculatively against the current state and
+//     parks, per seed, the outcome, the accepted-pixel lists and (for NFA-accepted / rejected
+//     regions) the rectangle in its arena, then flags the chunk READY;
+//   * whichever warp finds the frontier chunk READY takes the retire lock and drains the ready
+//     prefix in order.  A parked evaluation stands iff every pixel it accepted is still un-banned
+//     (bans only grow, and a candidate rejected by angle stays out whether or not it is banned
+//     later, so the evaluation then replays identically); a cheap bounding-box + coarse-grid filter
+//     against the log of regions accepted since the evaluation started short-cuts the pixel check.
+//     Otherwise the seed is simply re-evaluated at the frontier, where the state is final;
 //   * commits (usedMap 1 / 2, labels, rectangle record) happen only at the frontier.
 // So usedMap, labels and the segment list are exactly the sequential result.
 //
-// One CTA (16 warps) per map, CTAs pull maps from a counter.  All floating-point sums the
-// reference accumulates sequentially are accumulated sequentially here too (lane-parallel loads,
-// serial adds); counts and min/max are order-free and reduced in parallel.  Stage is
-// latency-bound (dependent gathers + double-double trig chains), not bandwidth-bound.
+// One CTA (4-16 warps, chosen from the batch size) per map, CTAs pull maps from a counter.  All
+// floating-point sums the reference accumulates sequentially are accumulated sequentially here too
+// (lane-parallel loads, serial adds); counts and min/max are order-free and reduced in parallel.
+// The stage is latency-bound (dependent gathers, serial accept chains), not bandwidth-bound.
 #include "lsdb_common.cuh"
 #include "../../include/lsdb200.h"
 
-#define NW LSDB_GROW_WARPS
+#define NW_MAX LSDB_GROW_WARPS
+#define ARENA_HDR 32  // words: 13 doubles (rect + logNFA), nCommit, outcome
 #define LOG_CAP 1024
 #define FULL 0xffffffffu
 
@@ -36,24 +41,31 @@ enum { OC_NONE = 0, OC_NOCHANGE = 1, OC_REJECT = 2, OC_ACCEPT = 3, OC_DEFER = 4 
 enum { ST_CELLS = 0, ST_LIVE, ST_GROWS, ST_GROWNPX, ST_SMALL, ST_REGROWS, ST_RRR, ST_NFACALLS, ST_NFAPX, ST_REJECTS,
        ST_ACCEPTS, ST_SPEC, ST_RESPEC, ST_CHUNKS, ST_N,
        // cycle counters (lane 0 of every warp, summed): only kept in LSDB_TIMING builds, reported through stat[] slots 14..19
-       TM_GROW = ST_N, TM_RECT, TM_NFA, TM_WAIT, TM_RETIRE, TM_SPEC, TM_N };
+       TM_GROW = ST_N, TM_RECT, TM_NFA, TM_WAIT, TM_RETIRE, TM_SPEC, TM_RESPEC, TM_N };
 
+#define RING 1024          // chunks a CTA may run ahead of the commit frontier
 struct GrowShared {
-    volatile int frontier;
-    int nextChunk;
+    volatile int frontier;     // first chunk not yet retired
+    int nextChunk;             // ticket counter
+    int retireLock;
     volatile int logCount;
     volatile int nSeg;
     volatile int abortFlag;
     int img;
     int nChunks;
     int nCells;
+    volatile int chunkFlag[RING];            // 1 = evaluated, records parked
+    unsigned char chunkWarp[RING];           // which warp's arena holds the records
+    unsigned int chunkEnd[RING];             // that warp's virtual arena offset after the chunk
+    volatile unsigned int arenaTail[NW_MAX]; // virtual offset up to which warp w's arena is free again
     unsigned int logBox[LOG_CAP][2];
+    unsigned long long logMask[LOG_CAP];
     unsigned long long stats[TM_N];
 };
 
 struct Rect { double x1, y1, x2, y2, wid, cX, cY, deg, dx, dy, p, prec; };
 
-struct BBox { int x0, y0, x1, y1; };
+struct BBox { int x0, y0, x1, y1; unsigned long long mask; };  // mask: 8x8 coarse grid cells holding accepted pixels
 
 #if 1  /* cycle counters are cheap (one clock64 + one smem atomic per measured call) and feed bench.py */
 #define TIC long long t0_ = clock64()
@@ -70,15 +82,28 @@ struct WarpCtx {
     unsigned int* state;
     const double* deg;
     const double* mag;
-    unsigned int* list;   // working point list (packed y<<16|x)
-    unsigned int* tlist;  // second list: RRR backup / commit stash
-    int listCap;
+    const double* cosm;   // lsdm_cos(deg), lsdm_sin(deg) of every non-banned pixel (stencil stage)
+    const double* sinm;
+    unsigned int* list;     // working point list (packed y<<16|x), listCap words
+    unsigned int* scratch;  // 2*listCap+64 words: result of a frontier (non-speculative) evaluation
+    unsigned int* arena;    // arenaCap words, ring: parked speculative results of this warp
+    unsigned int* listsBase;  // this CTA's first warp buffer (to reach other warps' arenas)
+    size_t warpStride;
+    int listCap, arenaCap;
     const LsdbLsdConst* kc;
     const double* lgammaTab;
     int lgammaN;
     GrowShared* sh;
     double logNT, regThre;
+    int cellShift;        // coarse-grid cell = 2^cellShift pixels, grid <= 8x8
 };
+
+__device__ __forceinline__ unsigned long long cell_bit(int x, int y, int sh) { return 1ull << (((y >> sh) << 3) | (x >> sh)); }
+// add an accepted pixel (x,y) of a growing region: bounding box + coarse-grid cell
+__device__ __forceinline__ void bbox_add(const WarpCtx& c, BBox& b, int x, int y) {
+    b.x0 = min(b.x0, x); b.y0 = min(b.y0, y); b.x1 = max(b.x1, x); b.y1 = max(b.y1, y);
+    b.mask |= cell_bit(x, y, c.cellShift);
+}
 
 // noinline wrappers keep one copy of each math routine in the kernel
 __device__ __noinline__ double d_sin(double x) { return lsdm_sin(x); }
@@ -93,9 +118,6 @@ __device__ __forceinline__ unsigned int pack_xy(int x, int y) { return ((unsigne
 __device__ __forceinline__ int px_of(unsigned int v) { return (int)(v & 0xffffu); }
 __device__ __forceinline__ int py_of(unsigned int v) { return (int)(v >> 16); }
 
-__device__ __forceinline__ void bbox_add(BBox& b, int x, int y) {
-    b.x0 = min(b.x0, x); b.y0 = min(b.y0, y); b.x1 = max(b.x1, x); b.y1 = max(b.y1, y);
-}
 
 // clear this warp's curMap bit on list[0..num)
 __device__ void clear_bits(const WarpCtx& c, const unsigned int* lst, int num) {
@@ -107,20 +129,45 @@ __device__ void clear_bits(const WarpCtx& c, const unsigned int* lst, int num) {
 }
 
 // ------------------------------------------------------------------ RegionGrower (:491-590)
-// Returns the region size (points in c.list), -1 on list overflow.  regDeg in/out.
+// Returns the region size (points in c.list), -1 on list overflow.  regDeg in (= deg[seed] at both
+// call sites :225,:857) / out (atan2 of the final sums, :547).
+//
+// The reference re-estimates regDeg = atan2(sinDeg, cosDeg) after EVERY accepted pixel and tests the
+// next neighbour with |regDeg - deg| < tol (:540-543).  Evaluating that literally puts ~300 dependent
+// double-double flops on the accept chain.  Here the test is decided from the running sums directly:
+//     cos(angle between (cosDeg,sinDeg) and the candidate) = (cosDeg*cos d + sinDeg*sin d)/|(cosDeg,sinDeg)|
+// compared with cos(tol), using the per-pixel cos/sin planes written by the stencil stage (the same
+// lsdm_cos/lsdm_sin values the reference adds to its sums).  The comparison is accepted only when it
+// clears the threshold by 1e-13 (the reference's own rounding moves the decision by < 2e-15); the rare
+// knife-edge candidate, tolerances above pi/2 near the reference's un-wrapped band (pi, 3pi/2], and
+// degenerate sums fall back to the literal atan2 test.  Decisions — and therefore the pixel order,
+// the sums and the final regDeg — are identical to the literal evaluation.
 __device__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double degThre, BBox& bb) {
     const int W = c.W, H = c.H;
     const double pi = c.kc->pi;
     const double pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
     TIC;
-    double sinDeg = d_sin(regDeg), cosDeg = d_cos(regDeg);
+    const size_t sp = (size_t)sy * W + sx;
+    const double regDeg0 = regDeg;
+    double sinDeg = c.sinm[sp], cosDeg = c.cosm[sp];  // sin(regDeg), cos(regDeg)  (:515-516)
+    const bool tauSmall = degThre <= pi / 2.0;
+    const bool tauGtPi = degThre > pi;
+    const double cTau = degThre == c.kc->degThre ? c.kc->cosDegThre : (tauGtPi ? -1.0 : d_cos(degThre));
+    const float tauF = (float)degThre;
     if (c.lane == 0) {
         c.list[0] = pack_xy(sx, sy);
-        atomicOr(&c.state[(size_t)sy * W + sx], c.mybit);
+        atomicOr(&c.state[sp], c.mybit);
     }
     __syncwarp();
-    bbox_add(bb, sx, sy);
+    bbox_add(c, bb, sx, sy);
     int num = 1, exNum = 0;
+    // uniform quantities derived from the running sums
+    double nrm = sqrt(cosDeg * cosDeg + sinDeg * sinDeg);
+    double thr = cTau * nrm, margin = 1e-13 * nrm;
+    float regA = tauSmall ? 0.f : atan2f((float)sinDeg, (float)cosDeg);
+    bool nrmOK = nrm > 1e-9;
+    bool haveExact = true;
+    double regExact = regDeg0;
     while (exNum != num) {
         exNum = num;
         int cur = 0;
@@ -134,28 +181,53 @@ __device__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double de
             const bool inb = valid && m >= 0 && n >= 0 && m < H && n < W;
             const size_t p = inb ? (size_t)m * W + n : 0;
             const unsigned int st = inb ? lsdb_ld_state(&c.state[p]) : LSDB_ST_BAN;
-            const double dg = inb ? c.deg[p] : 0.0;
+            double dg = 0.0, cd = 0.0, sd = 0.0;
+            if (inb) { dg = c.deg[p]; cd = c.cosm[p]; sd = c.sinm[p]; }  // issued with the state load, not after it
             bool cand = inb && !(st & (LSDB_ST_BAN | c.mybit));
             int start = 0;
             while (true) {
-                double degDif = fabs(regDeg - dg);
-                if (degDif > pi32) degDif = fabs(degDif - pi2);
-                const bool pass = cand && c.lane >= start && degDif < degThre;
+                const bool active = cand && c.lane >= start;
+                bool pass = false, unc = false;
+                if (active) {
+                    const double diff = (cosDeg * cd + sinDeg * sd) - thr;
+                    const bool cosCertain = fabs(diff) > margin;
+                    if (tauSmall) {
+                        pass = diff > 0; unc = !cosCertain;
+                    } else {
+                        const float aA = fabsf(regA - (float)dg);
+                        if (fabsf(aA - 3.14159265f) < 1e-3f || fabsf(aA - 4.71238898f) < 1e-3f) unc = true;
+                        else if (aA > 3.14159265f && aA < 4.71238898f) {  // the reference keeps a in (pi,3pi/2] un-wrapped
+                            if (fabsf(aA - tauF) < 1e-3f) unc = true; else pass = aA < tauF;
+                        } else if (tauGtPi) pass = true;
+                        else { pass = diff > 0; unc = !cosCertain; }
+                    }
+                    if (!nrmOK) unc = true;
+                }
+                if (__any_sync(FULL, unc)) {
+                    if (!haveExact) { regExact = d_atan2(sinDeg, cosDeg); haveExact = true; }
+                    if (unc) {  // the literal test, :540-543
+                        double degDif = fabs(regExact - dg);
+                        if (degDif > pi32) degDif = fabs(degDif - pi2);
+                        pass = degDif < degThre;
+                    }
+                }
                 const unsigned int b = __ballot_sync(FULL, pass);
                 if (!b) break;
                 const int f = __ffs(b) - 1;
-                const double curDeg = __shfl_sync(FULL, dg, f);
                 const int fn = __shfl_sync(FULL, n, f), fm = __shfl_sync(FULL, m, f);
-                cosDeg += d_cos(curDeg);
-                sinDeg += d_sin(curDeg);
-                regDeg = d_atan2(sinDeg, cosDeg);
+                cosDeg += __shfl_sync(FULL, cd, f);  // :545-546
+                sinDeg += __shfl_sync(FULL, sd, f);
+                nrm = sqrt(cosDeg * cosDeg + sinDeg * sinDeg);
+                thr = cTau * nrm; margin = 1e-13 * nrm; nrmOK = nrm > 1e-9;
+                if (!tauSmall) regA = atan2f((float)sinDeg, (float)cosDeg);
+                haveExact = false;
                 if (num >= c.listCap - 1) return -1;
                 if (c.lane == f) {
                     atomicOr(&c.state[p], c.mybit);
                     c.list[num] = pack_xy(n, m);
                 }
                 if (inb && n == fn && m == fm) cand = false;
-                bbox_add(bb, fn, fm);
+                bbox_add(c, bb, fn, fm);
                 num++;
                 start = f + 1;
             }
@@ -163,6 +235,7 @@ __device__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double de
             cur = min(cur + 32, lim);
         }
     }
+    if (num > 1) regDeg = haveExact ? regExact : d_atan2(sinDeg, cosDeg);  // :547 after the last accept
     STAT(c, ST_GROWS, 1); STAT(c, ST_GROWNPX, num);
     TOC(c, TM_GROW);
     return num;
@@ -174,18 +247,19 @@ __device__ Rect rect_from_region(const WarpCtx& c, const unsigned int* lst, int 
     const int W = c.W;
     const double pi = c.kc->pi;
     TIC;
+    // Sums are accumulated in list order like the reference (:608-613, :637-643): lanes form the addends of 32
+    // points in parallel (same operations on the same inputs, so the same bits), the adds run serially.
     double cenX = 0, cenY = 0, weiSum = 0;
-    for (int base = 0; base < num; base += 32) {  // CenterGetter :608-613, sums in list order
+    for (int base = 0; base < num; base += 32) {  // CenterGetter :608-613
         const int k = base + c.lane;
         const unsigned int v = k < num ? lst[k] : 0u;
         const double wv = k < num ? c.mag[(size_t)py_of(v) * W + px_of(v)] : 0.0;
+        const double tx = wv * px_of(v), ty = wv * py_of(v);
         const int cnt = min(32, num - base);
-        for (int j = 0; j < cnt; j++) {
-            const double wj = __shfl_sync(FULL, wv, j);
-            const unsigned int vj = __shfl_sync(FULL, v, j);
-            cenX += wj * px_of(vj);
-            cenY += wj * py_of(vj);
-            weiSum += wj;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const double wj = __shfl_sync(FULL, wv, j), xj = __shfl_sync(FULL, tx, j), yj = __shfl_sync(FULL, ty, j);
+            if (j < cnt) { cenX += xj; cenY += yj; weiSum += wj; }
         }
     }
     cenX = cenX / weiSum;
@@ -196,15 +270,14 @@ __device__ Rect rect_from_region(const WarpCtx& c, const unsigned int* lst, int 
         const int k = base + c.lane;
         const unsigned int v = k < num ? lst[k] : 0u;
         const double wv = k < num ? c.mag[(size_t)py_of(v) * W + px_of(v)] : 0.0;
+        const double ey = py_of(v) - cenY, ex = px_of(v) - cenX;
+        const double t1 = wv * (ey * ey), t2 = wv * (ex * ex), t3 = wv * ex * ey;
         const int cnt = min(32, num - base);
-        for (int j = 0; j < cnt; j++) {
-            const double wj = __shfl_sync(FULL, wv, j);
-            const unsigned int vj = __shfl_sync(FULL, v, j);
-            const double ey = py_of(vj) - cenY, ex = px_of(vj) - cenX;
-            Ixx += wj * (ey * ey);
-            Iyy += wj * (ex * ex);
-            Ixy -= wj * ex * ey;
-            weiSum += wj;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const double wj = __shfl_sync(FULL, wv, j), a1 = __shfl_sync(FULL, t1, j), a2 = __shfl_sync(FULL, t2, j),
+                         a3 = __shfl_sync(FULL, t3, j);
+            if (j < cnt) { Ixx += a1; Iyy += a2; Ixy -= a3; weiSum += wj; }
         }
     }
     Ixx /= weiSum; Iyy /= weiSum; Ixy /= weiSum;
@@ -347,10 +420,19 @@ __device__ double rect_nfa_impl(WarpCtx& c, const Rect& rec, double logNT) {
     STAT(c, ST_NFACALLS, 1); STAT(c, ST_NFAPX, allPixNum);
 
     if (allPixNum == 0 || aliPixNum == 0) return -logNT;
-    if (allPixNum == aliPixNum) return -logNT - allPixNum * d_log10(rec.p);
+    // log(p), log(1-p), log10(p): p only takes the values aliPro/2^k (:1085,:1149) — host-made table
+    double logP, log1mP, log10P;
+    {
+        int k = -1;
+#pragma unroll
+        for (int i = 0; i < LSDB_NP; i++) if (rec.p == c.kc->pTab[i]) k = i;
+        if (k >= 0) { logP = c.kc->logP[k]; log1mP = c.kc->log1mP[k]; log10P = c.kc->log10P[k]; }
+        else { logP = d_log(rec.p); log1mP = d_log(1 - rec.p); log10P = d_log10(rec.p); }
+    }
+    if (allPixNum == aliPixNum) return -logNT - allPixNum * log10P;
     const double proTerm = rec.p / (1.0 - rec.p);
     const double log1Coef = log_gamma(c, allPixNum + 1) - log_gamma(c, aliPixNum + 1) - log_gamma(c, allPixNum - aliPixNum + 1);
-    const double log1Term = log1Coef + aliPixNum * d_log(rec.p) + (allPixNum - aliPixNum) * d_log(1 - rec.p);
+    const double log1Term = log1Coef + aliPixNum * logP + (allPixNum - aliPixNum) * log1mP;
     double term = d_exp(log1Term);
     const double eps = 2.2204e-16;
     if (fabs(term) < 100 * eps) {
@@ -365,8 +447,22 @@ __device__ double rect_nfa_impl(WarpCtx& c, const Rect& rec, double logNT) {
         term *= multTerm;
         binTail += term;
         if (binTerm < 1) {
-            const double err = term * ((1 - d_pow(multTerm, allPixNum - i + 1)) / (1.0 - multTerm) - 1);
-            if (err < tole * fabs(-d_log10(binTail) - logNT) * binTail) break;
+            // break test of :1052-1054.  It is a comparison, so it is first decided with the hardware
+            // pow/log10 (<= 2 ulp) and a 1e-9 safety margin; only a knife-edge falls back to the
+            // correctly-rounded pow/log10 the reference's arithmetic is defined by.
+            const double nn = (double)(allPixNum - i + 1);
+            const double X = (1 - pow(multTerm, nn)) / (1.0 - multTerm);
+            const double errA = term * (X - 1);
+            const double l10 = log10(binTail);
+            const double rhsA = tole * fabs(-l10 - logNT) * binTail;
+            const double scale = fabs(term) * (fabs(X) + 1) + tole * fabs(binTail) * (fabs(l10) + fabs(logNT));
+            bool brk;
+            if (fabs(errA - rhsA) > 1e-9 * scale) brk = errA < rhsA;
+            else {
+                const double err = term * ((1 - d_pow(multTerm, nn)) / (1.0 - multTerm) - 1);
+                brk = err < tole * fabs(-d_log10(binTail) - logNT) * binTail;
+            }
+            if (brk) break;
         }
     }
     return -d_log10(binTail) - logNT;
@@ -418,29 +514,41 @@ __device__ double rectangle_improver(WarpCtx& c, Rect& rec, double logNT) {
 }
 
 // ------------------------------------------------------------------ one seed: grow -> rect -> refine -> NFA
-// On OC_REJECT / OC_ACCEPT the pixels with curMap==1 are compacted into c.tlist[0..*nCommit) and the
-// warp's curMap bits are cleared.  allowTlist=false forbids touching c.tlist (it holds a stash):
-// the evaluation returns OC_DEFER as soon as it would need it.
-__device__ int eval_seed(WarpCtx& c, int p0, bool allowTlist, Rect& rec, double& logNFA, BBox& bb, int& nCommit,
-                         bool& touchedT) {
+// Result record written at `out` (cap words available):
+//   [0..25] 13 doubles: rectangle + logNFA   [26] nCommit  [27] outcome  [28] offset of the commit list
+//   [ARENA_HDR ..]  pixel lists.  With wantChk every pixel the evaluation accepted is kept: the first
+//   grow G1, the Refiner re-grow G2, and the commit list (pixels whose curMap bit is still set, what
+//   :242-248/:259-265 visit); chk = number of words after the header to re-validate.  Without wantChk
+//   (frontier evaluation) only the re-grow backup and the commit list are written.
+// The warp's curMap bits are cleared on return.  OC_DEFER = `cap` too small (nothing was changed).
+__device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wantChk, BBox& bb, int& used, int& chk) {
     const LsdbLsdConst* kc = c.kc;
     const int W = c.W;
     const int sx = p0 % W, sy = p0 / W;
-    bb.x0 = bb.y0 = 0x7fffffff; bb.x1 = bb.y1 = -1;
-    touchedT = false;
+    bb.x0 = bb.y0 = 0x7fffffff; bb.x1 = bb.y1 = -1; bb.mask = 0ull;
+    used = 0;
+    chk = -1;
     double regDeg = c.deg[p0];
     int num = grow_region(c, sx, sy, regDeg, kc->degThre, bb);
     if (num < 0) { c.sh->abortFlag = LSDB_ERR_CAPACITY; return OC_NOCHANGE; }
+    unsigned int* body = out + ARENA_HDR;
+    int aw = 0;  // words written after the header
     if (num < c.regThre) {  // :228
+        if (wantChk) {
+            if (ARENA_HDR + num + 2 > cap) { clear_bits(c, c.list, num); return OC_DEFER; }
+            for (int k = c.lane; k < num; k += 32) body[k] = c.list[k];
+            chk = num;
+            used = (ARENA_HDR + num + 1) & ~1;
+        }
         clear_bits(c, c.list, num);
         STAT(c, ST_SMALL, 1);
         return OC_NOCHANGE;
     }
-    if (!allowTlist) { clear_bits(c, c.list, num); return OC_DEFER; }  // would need the stash buffer
-    touchedT = true;
-    rec = rect_from_region(c, c.list, num, regDeg, kc->aliPro, kc->degThre);
+    if (ARENA_HDR + 3 * num + 8 > cap && wantChk) { clear_bits(c, c.list, num); return OC_DEFER; }
+    Rect rec = rect_from_region(c, c.list, num, regDeg, kc->aliPro, kc->degThre);
     bool usedT = false;
     int tnum = 0;
+    unsigned int* backup = body;
     // Refiner :804-880
     double den = rect_density(num, rec);
     if (!(den >= kc->denThre)) {
@@ -471,62 +579,77 @@ __device__ int eval_seed(WarpCtx& c, int p0, bool allowTlist, Rect& rec, double&
         }
         const double meanDif = difSum / (ptNum * 1.0);
         const double degThre2 = 2.0 * sqrt((squSum - 2 * meanDif * difSum) / (ptNum * 1.0) + meanDif * meanDif);
+        if (wantChk) {  // keep G1 for re-validation
+            for (int k = c.lane; k < num; k += 32) body[aw + k] = c.list[k];
+            aw += num;
+        }
         clear_bits(c, c.list, num);
         regDeg = cenDeg;
         num = grow_region(c, sx, sy, regDeg, degThre2, bb);
         STAT(c, ST_REGROWS, 1);
         if (num < 0) { c.sh->abortFlag = LSDB_ERR_CAPACITY; return OC_NOCHANGE; }
-        if (num < 2) { clear_bits(c, c.list, num); return OC_NOCHANGE; }
+        if (ARENA_HDR + aw + 2 * num + 8 > cap) { clear_bits(c, c.list, num); return OC_DEFER; }
+        backup = body + aw;  // G2 in full: re-validation list and RegionRadiusReducer's "every pixel the bit was set on"
+        for (int k = c.lane; k < num; k += 32) backup[k] = c.list[k];
+        __syncwarp();
+        usedT = true; tnum = num;
+        aw += num;
+        if (num < 2) {
+            clear_bits(c, c.list, num);
+            if (wantChk) { chk = aw; used = (ARENA_HDR + aw + 1) & ~1; }
+            return OC_NOCHANGE;
+        }
         rec = rect_from_region(c, c.list, num, regDeg, rec.p, rec.prec);
         den = rect_density(num, rec);
         if (den < kc->denThre) {
-            for (int k = c.lane; k < num; k += 32) c.tlist[k] = c.list[k];  // every pixel the bit was set on
-            __syncwarp();
-            usedT = true; tnum = num;
-            // RegionRadiusReducer :736-802 (rect_from_region inside needs reg.deg = regDeg)
+            // RegionRadiusReducer :736-802, serial on lane 0, in place, with the `i <= num` quirk
             bool ok = true;
-            {
-                double d2 = rect_density(num, rec);
-                if (!(d2 > kc->denThre)) {
-                    const double rad1 = dist_xy(sx, sy, rec.x1, rec.y1), rad2 = dist_xy(sx, sy, rec.x2, rec.y2);
-                    double rad = rad1 > rad2 ? rad1 : rad2;
-                    while (d2 < kc->denThre) {
-                        rad *= 0.75;
-                        if (c.lane == 0) {
-                            int i = 0, nn = num;
-                            c.list[nn] = 0u;  // slot [num] reads as (0,0)  
-                            while (i <= nn) {
-                                const unsigned int v = c.list[i];
-                                if (dist_xy(sx, sy, (double)px_of(v), (double)py_of(v)) > rad) {
-                                    atomicAnd(&c.state[(size_t)py_of(v) * W + px_of(v)], ~c.mybit);
-                                    c.list[i] = c.list[nn - 1];
-                                    c.list[nn - 1] = 0u;
-                                    i--;
-                                    nn--;
-                                }
-                                i++;
+            double d2 = den;
+            if (!(d2 > kc->denThre)) {
+                const double rad1 = dist_xy(sx, sy, rec.x1, rec.y1), rad2 = dist_xy(sx, sy, rec.x2, rec.y2);
+                double rad = rad1 > rad2 ? rad1 : rad2;
+                while (d2 < kc->denThre) {
+                    rad *= 0.75;
+                    if (c.lane == 0) {
+                        int i = 0, nn = num;
+                        c.list[nn] = 0u;  // slot [num] reads as (0,0)
+                        while (i <= nn) {
+                            if (nn <= 0) break;  // the reference would index [-1] here (heap underflow, UB)
+                            const unsigned int v = c.list[i];
+                            if (dist_xy(sx, sy, (double)px_of(v), (double)py_of(v)) > rad) {
+                                atomicAnd(&c.state[(size_t)py_of(v) * W + px_of(v)], ~c.mybit);
+                                c.list[i] = c.list[nn - 1];
+                                c.list[nn - 1] = 0u;
+                                i--;
+                                nn--;
                             }
-                            num = nn;
-                            atomicAdd(&c.sh->stats[ST_RRR], 1ull);
+                            i++;
                         }
-                        __syncwarp();
-                        num = __shfl_sync(FULL, num, 0);
-                        if (num < 2) { ok = false; break; }
-                        rec = rect_from_region(c, c.list, num, regDeg, rec.p, rec.prec);
-                        d2 = rect_density(num, rec);
+                        num = nn;
+                        atomicAdd(&c.sh->stats[ST_RRR], 1ull);
                     }
+                    __syncwarp();
+                    num = __shfl_sync(FULL, num, 0);
+                    if (num < 2) { ok = false; break; }
+                    rec = rect_from_region(c, c.list, num, regDeg, rec.p, rec.prec);
+                    d2 = rect_density(num, rec);
                 }
             }
-            if (!ok) { clear_bits(c, c.tlist, tnum); return OC_NOCHANGE; }
+            if (!ok) {
+                clear_bits(c, backup, tnum);
+                if (wantChk) { chk = aw; used = (ARENA_HDR + aw + 1) & ~1; }
+                return OC_NOCHANGE;
+            }
         }
     }
-    logNFA = rectangle_improver(c, rec, c.logNT);
-    // finalize: commit list = pixels whose curMap bit is still set
+    const double logNFA = rectangle_improver(c, rec, c.logNT);
+    // finalize: commit list = pixels whose curMap bit is still set; clear the bits
+    unsigned int* commit = body + aw;
     int outN = 0;
     if (!usedT) {
         for (int k = c.lane; k < num; k += 32) {
             const unsigned int v = c.list[k];
-            c.tlist[k] = v;
+            commit[k] = v;
             atomicAnd(&c.state[(size_t)py_of(v) * W + px_of(v)], ~c.mybit);
         }
         outN = num;
@@ -536,44 +659,73 @@ __device__ int eval_seed(WarpCtx& c, int p0, bool allowTlist, Rect& rec, double&
             unsigned int v = 0;
             bool keep = false;
             if (k < tnum) {
-                v = c.tlist[k];
+                v = backup[k];
                 const unsigned int old = atomicAnd(&c.state[(size_t)py_of(v) * W + px_of(v)], ~c.mybit);
                 keep = (old & c.mybit) != 0;
             }
             const unsigned int mk = __ballot_sync(FULL, keep);
-            __syncwarp();
-            if (keep) c.tlist[outN + __popc(mk & ((1u << c.lane) - 1u))] = v;
+            if (keep) commit[outN + __popc(mk & ((1u << c.lane) - 1u))] = v;
             outN += __popc(mk);
-            __syncwarp();
         }
     }
+    const int oc = logNFA <= 0 ? OC_REJECT : OC_ACCEPT;
+    if (c.lane == 0) {
+        double* hd = reinterpret_cast<double*>(out);
+        hd[0] = rec.x1; hd[1] = rec.y1; hd[2] = rec.x2; hd[3] = rec.y2; hd[4] = rec.wid; hd[5] = rec.cX; hd[6] = rec.cY;
+        hd[7] = rec.deg; hd[8] = rec.dx; hd[9] = rec.dy; hd[10] = rec.p; hd[11] = rec.prec; hd[12] = logNFA;
+        out[26] = (unsigned int)outN;
+        out[27] = (unsigned int)oc;
+        out[28] = (unsigned int)(ARENA_HDR + aw);
+    }
     __syncwarp();
-    nCommit = outN;
-    return logNFA <= 0 ? OC_REJECT : OC_ACCEPT;
+    if (wantChk) {
+        // speculative result parked: tell other warps that these pixels are about to leave the seed pool
+        // (usedMap 1 or 2 once this record retires), so evaluating them as seeds now would be wasted work.
+        // A hint only steers speculation; stale hints merely move an evaluation to the frontier.
+        for (int k = c.lane; k < outN; k += 32) {
+            const unsigned int v = commit[k];
+            atomicOr(&c.state[(size_t)py_of(v) * W + px_of(v)], LSDB_ST_HINT);
+        }
+    }
+    aw += outN;
+    used = (ARENA_HDR + aw + 1) & ~1;
+    if (wantChk) chk = aw;
+    return oc;
 }
 
-// any ACCEPT logged in [L0, logCount) overlapping the examined box (region bbox dilated by 1)?
-__device__ bool has_conflict(const WarpCtx& c, int L0, unsigned int bb0, unsigned int bb1) {
-    const int L1 = c.sh->logCount;
-    if (L1 - L0 > LOG_CAP) return true;
-    const int ax0 = (int)(bb0 & 0xffff) - 1, ay0 = (int)(bb0 >> 16) - 1, ax1 = (int)(bb1 & 0xffff) + 1, ay1 = (int)(bb1 >> 16) + 1;
+__device__ bool any_banned(const WarpCtx& c, const unsigned int* px, int n) {
     bool hit = false;
-    for (int e = L0 + c.lane; e < L1; e += 32) {
-        const unsigned int b0 = c.sh->logBox[e & (LOG_CAP - 1)][0], b1 = c.sh->logBox[e & (LOG_CAP - 1)][1];
-        const int bx0 = b0 & 0xffff, by0 = b0 >> 16, bx1 = b1 & 0xffff, by1 = b1 >> 16;
-        if (bx0 <= ax1 && bx1 >= ax0 && by0 <= ay1 && by1 >= ay0) hit = true;
+    for (int k = c.lane; k < n; k += 32) {
+        const unsigned int v = px[k];
+        if (lsdb_ld_state(&c.state[(size_t)py_of(v) * c.W + px_of(v)]) & LSDB_ST_BAN) hit = true;
     }
     return __any_sync(FULL, hit);
 }
 
-// commit c.tlist[0..nCommit) at the frontier (:242-271)
-__device__ void commit_region(WarpCtx& c, int outcome, int nCommit, const Rect& rec, double logNFA, int* labels,
-                              LsdbRect* rects, int maxSeg) {
+// coarse filter: any ACCEPT logged in [L0, logCount) whose bounding box AND coarse-cell mask overlap
+// those of the pixels this evaluation accepted?  (conservative: never misses an overlap)
+__device__ bool has_conflict(const WarpCtx& c, int L0, unsigned int bb0, unsigned int bb1, unsigned long long mask) {
+    const int L1 = c.sh->logCount;
+    if (L1 - L0 > LOG_CAP) return true;
+    const int ax0 = (int)(bb0 & 0xffff), ay0 = (int)(bb0 >> 16), ax1 = (int)(bb1 & 0xffff), ay1 = (int)(bb1 >> 16);
+    bool hit = false;
+    for (int e = L0 + c.lane; e < L1; e += 32) {
+        const unsigned int b0 = c.sh->logBox[e & (LOG_CAP - 1)][0], b1 = c.sh->logBox[e & (LOG_CAP - 1)][1];
+        const int bx0 = b0 & 0xffff, by0 = b0 >> 16, bx1 = b1 & 0xffff, by1 = b1 >> 16;
+        if (bx0 <= ax1 && bx1 >= ax0 && by0 <= ay1 && by1 >= ay0 && (c.sh->logMask[e & (LOG_CAP - 1)] & mask)) hit = true;
+    }
+    return __any_sync(FULL, hit);
+}
+
+// commit the result record at `recp`, at the frontier (:242-271)
+__device__ void commit_region(WarpCtx& c, const unsigned int* recp, int* labels, LsdbRect* rects, int maxSeg) {
     GrowShared* sh = c.sh;
     const int W = c.W;
+    const int nCommit = (int)recp[26], outcome = (int)recp[27];
+    const unsigned int* px = recp + recp[28];
     if (outcome == OC_REJECT) {
         for (int k = c.lane; k < nCommit; k += 32) {
-            const unsigned int v = c.tlist[k];
+            const unsigned int v = px[k];
             atomicOr(&c.state[(size_t)py_of(v) * W + px_of(v)], LSDB_ST_REJ);
         }
         STAT(c, ST_REJECTS, 1);
@@ -582,36 +734,41 @@ __device__ void commit_region(WarpCtx& c, int outcome, int nCommit, const Rect& 
     }
     const int idx = sh->nSeg;
     int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
+    unsigned long long mask = 0ull;
     for (int k = c.lane; k < nCommit; k += 32) {
-        const unsigned int v = c.tlist[k];
+        const unsigned int v = px[k];
         const size_t p = (size_t)py_of(v) * W + px_of(v);
         atomicOr(&c.state[p], LSDB_ST_BAN);
         labels[p] += idx + 1;  // regIdx += curMap*(regCnt+1), :261 (int32 here, u8 there)
         x0 = min(x0, px_of(v)); y0 = min(y0, py_of(v)); x1 = max(x1, px_of(v)); y1 = max(y1, py_of(v));
+        mask |= cell_bit(px_of(v), py_of(v), c.cellShift);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         x0 = min(x0, __shfl_xor_sync(FULL, x0, o)); y0 = min(y0, __shfl_xor_sync(FULL, y0, o));
         x1 = max(x1, __shfl_xor_sync(FULL, x1, o)); y1 = max(y1, __shfl_xor_sync(FULL, y1, o));
+        mask |= __shfl_xor_sync(FULL, mask, o);
     }
     if (c.lane == 0) {
         if (idx < maxSeg) {
+            const double* hd = reinterpret_cast<const double*>(recp);
             const double sca = c.kc->sca;
             LsdbRect& R = rects[idx];
-            double rx1 = rec.x1, ry1 = rec.y1, rx2 = rec.x2, ry2 = rec.y2, rw = rec.wid;
+            double rx1 = hd[0], ry1 = hd[1], rx2 = hd[2], ry2 = hd[3], rw = hd[4];
             if (sca != 1) {  // :252-258
                 rx1 = (rx1 - 1.0) / sca + 1; ry1 = (ry1 - 1.0) / sca + 1;
                 rx2 = (rx2 - 1.0) / sca + 1; ry2 = (ry2 - 1.0) / sca + 1;
                 rw = (rw - 1.0) / sca + 1;
             }
-            R.v[0] = rx1; R.v[1] = ry1; R.v[2] = rx2; R.v[3] = ry2; R.v[4] = rw; R.v[5] = rec.cX; R.v[6] = rec.cY;
-            R.v[7] = rec.deg; R.v[8] = rec.dx; R.v[9] = rec.dy; R.v[10] = rec.p; R.v[11] = rec.prec; R.v[12] = logNFA;
+            R.v[0] = rx1; R.v[1] = ry1; R.v[2] = rx2; R.v[3] = ry2; R.v[4] = rw;
+            for (int k = 5; k < 13; k++) R.v[k] = hd[k];
         } else {
             sh->abortFlag = LSDB_ERR_CAPACITY;
         }
         const int L = sh->logCount;
         sh->logBox[L & (LOG_CAP - 1)][0] = pack_xy(x0, y0);
         sh->logBox[L & (LOG_CAP - 1)][1] = pack_xy(x1, y1);
+        sh->logMask[L & (LOG_CAP - 1)] = mask;
         __threadfence_block();
         sh->logCount = L + 1;
         sh->nSeg = idx + 1;
@@ -620,21 +777,202 @@ __device__ void commit_region(WarpCtx& c, int outcome, int nCommit, const Rect& 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(NW * 32, 1) lsdb_grow_kernel(int nImgs, const LsdbImg* __restrict__ imgs, LsdbImgDyn* __restrict__ dyn,
-                                                               const LsdbLsdConst* __restrict__ kc, const double* __restrict__ mag,
-                                                               const double* __restrict__ deg, unsigned int* __restrict__ state,
-                                                               const unsigned int* __restrict__ cells, int* __restrict__ labels,
-                                                               LsdbRect* __restrict__ rects, int maxSeg, unsigned int* __restrict__ lists,
-                                                               int listCap, const double* __restrict__ lgammaTab, int lgammaN,
-                                                               int* __restrict__ imgCounter) {
+// per-seed record of a parked evaluation (one per lane of a chunk), SoA in global memory: [RING][32]
+struct ChunkRecs {
+    int* oc; int* L0; unsigned int* b0; unsigned int* b1; unsigned long long* mask; unsigned int* off; int* chk;
+};
+
+// speculative evaluation of every live seed of `chunk`; parks the results and flags the chunk READY
+__device__ void speculate_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int nCells, const ChunkRecs& R, unsigned int& head) {
+    GrowShared& sh = *c.sh;
+    const int lane = c.lane;
+    const int slot = chunk & (RING - 1);
+    const int ci = chunk * LSDB_CHUNK + lane;
+    const int myp = ci < nCells ? (int)cl[ci] : -1;
+    const bool live = myp >= 0 && (lsdb_ld_state(&c.state[myp]) & 3u) == 0;
+    unsigned int rem = __ballot_sync(FULL, live);
+    int recOc = OC_NONE, recL0 = 0, recChk = -1;
+    unsigned int recB0 = 0, recB1 = 0, recOff = 0;
+    unsigned long long recMask = 0ull;
+    BBox bb; int used = 0, chk = -1;
+    const unsigned int cap = (unsigned int)c.arenaCap;
+    long long tSpec = clock64();
+    while (rem && !sh.abortFlag) {
+        const int k = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int p = __shfl_sync(FULL, myp, k);
+        if (lsdb_ld_state(&c.state[p]) & (3u | LSDB_ST_HINT)) continue;   // used, or inside a parked region: leave to the frontier
+        // contiguous room in the ring: skip the tail of the buffer if the record could straddle it
+        const unsigned int tail = sh.arenaTail[c.w];
+        unsigned int phys = head % cap;
+        unsigned int room = cap - phys;                   // contiguous words at phys
+        unsigned int h2 = head;
+        if (room < 4096u && cap - (head + room - tail) >= 4096u) { h2 = head + room; phys = 0; room = cap; }
+        const unsigned int freeW = cap - (h2 - tail);     // words not holding parked records
+        const int avail = (int)min(room, freeW);
+        if (avail < ARENA_HDR + 64) continue;             // arena full: this seed is decided at the frontier
+        const int L0 = sh.logCount;
+        __threadfence_block();
+        const int oc = eval_seed(c, p, c.arena + phys, avail, true, bb, used, chk);
+        STAT(c, ST_SPEC, 1);
+        if (oc == OC_DEFER) continue;
+        if (lane == k) {
+            recOc = oc; recL0 = L0; recB0 = pack_xy(bb.x0, bb.y0); recB1 = pack_xy(bb.x1, bb.y1); recMask = bb.mask;
+            recOff = phys; recChk = chk;
+        }
+        head = h2 + (unsigned int)used;
+    }
+    const size_t ri = (size_t)slot * 32 + lane;
+    R.oc[ri] = recOc; R.L0[ri] = recL0; R.b0[ri] = recB0; R.b1[ri] = recB1; R.mask[ri] = recMask; R.off[ri] = recOff; R.chk[ri] = recChk;
+    if (lane == 0) {
+        sh.chunkWarp[slot] = (unsigned char)c.w;
+        sh.chunkEnd[slot] = head;
+        atomicAdd(&sh.stats[TM_SPEC], (unsigned long long)(clock64() - tSpec));
+    }
+    __threadfence();   // records + arena contents visible before the flag
+    __syncwarp();
+    if (lane == 0) sh.chunkFlag[slot] = 1;
+}
+
+// does log entry e overlap the accepted-pixel bbox/mask of a parked evaluation?
+__device__ __forceinline__ bool log_hit(const GrowShared& sh, int e, unsigned int bb0, unsigned int bb1, unsigned long long mask) {
+    const unsigned int b0 = sh.logBox[e & (LOG_CAP - 1)][0], b1 = sh.logBox[e & (LOG_CAP - 1)][1];
+    const int bx0 = b0 & 0xffff, by0 = b0 >> 16, bx1 = b1 & 0xffff, by1 = b1 >> 16;
+    const int ax0 = (int)(bb0 & 0xffff), ay0 = (int)(bb0 >> 16), ax1 = (int)(bb1 & 0xffff), ay1 = (int)(bb1 >> 16);
+    return bx0 <= ax1 && bx1 >= ax0 && by0 <= ay1 && by1 >= ay0 && (sh.logMask[e & (LOG_CAP - 1)] & mask) != 0ull;
+}
+
+// retire one READY chunk at the frontier: in seed order, validate or re-evaluate, commit.
+// The common case — seed still live, parked outcome "no change", no accepted region since the evaluation
+// started anywhere near it — is decided for all 32 cells at once (one state load, one pass over the log);
+// only commits, coarse-filter hits and missing evaluations are walked serially, in order.
+__device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int nCells, const ChunkRecs& R, int* lab, LsdbRect* rc, int maxSeg) {
+    GrowShared& sh = *c.sh;
+    const int lane = c.lane;
+    const int slot = chunk & (RING - 1);
+    const int ci = chunk * LSDB_CHUNK + lane;
+    const int myp = ci < nCells ? (int)cl[ci] : -1;
+    const size_t ri = (size_t)slot * 32 + lane;
+    const int recOc = R.oc[ri], recL0 = R.L0[ri], recChk = R.chk[ri];
+    const unsigned int recB0 = R.b0[ri], recB1 = R.b1[ri], recOff = R.off[ri];
+    const unsigned long long recMask = R.mask[ri];
+    const int ew = sh.chunkWarp[slot];
+    const unsigned int* earena = c.listsBase + (size_t)ew * c.warpStride + c.listCap + (2 * (size_t)c.listCap + 64);
+    bool live = myp >= 0 && (lsdb_ld_state(&c.state[myp]) & 3u) == 0;   // :222
+    int logSeen = sh.logCount;
+    bool hit = false;
+    if (live && recOc != OC_NONE) {
+        if (logSeen - recL0 > LOG_CAP) hit = true;
+        else for (int e = recL0; e < logSeen && !hit; e++) hit = log_hit(sh, e, recB0, recB1, recMask);
+    }
+    unsigned int liveAtTurn = __ballot_sync(FULL, live);
+    unsigned int work = __ballot_sync(FULL, live && !(recOc == OC_NOCHANGE && !hit));
+    BBox bb; int used = 0, chk = -1;
+    while (work) {
+        const int k = __ffs(work) - 1;
+        work &= work - 1;
+        const int p = __shfl_sync(FULL, myp, k);
+        const int oc = __shfl_sync(FULL, recOc, k);
+        const unsigned int* recp = earena + __shfl_sync(FULL, recOff, k);
+        bool valid = oc != OC_NONE;
+        if (valid && __shfl_sync(FULL, (int)hit, k)) {   // coarse filter hit: look at the accepted pixels themselves
+            const int nchk = __shfl_sync(FULL, recChk, k);
+            valid = nchk >= 0 && !any_banned(c, recp + ARENA_HDR, nchk);
+        }
+        bool changed = false;
+        if (valid) {
+            if (oc != OC_NOCHANGE) { commit_region(c, recp, lab, rc, maxSeg); changed = true; }
+        } else {
+            long long t0 = clock64();
+            const int oc2 = eval_seed(c, p, c.scratch, 2 * c.listCap + 64, false, bb, used, chk);
+            STAT(c, ST_RESPEC, 1);
+            if (oc2 == OC_DEFER) { sh.abortFlag = LSDB_ERR_CAPACITY; break; }
+            if (oc2 == OC_REJECT || oc2 == OC_ACCEPT) { commit_region(c, c.scratch, lab, rc, maxSeg); changed = true; }
+            if (lane == 0) atomicAdd(&sh.stats[TM_RESPEC], (unsigned long long)(clock64() - t0));
+            if (sh.abortFlag) break;
+        }
+        if (changed && (work != 0 || (liveAtTurn >> (k + 1)) != 0)) {
+            // usedMap changed: refresh the cells that come after k in this chunk
+            __threadfence_block();
+            if (lane > k && live) {
+                live = (lsdb_ld_state(&c.state[myp]) & 3u) == 0;
+                const int L1 = sh.logCount;
+                if (live && recOc != OC_NONE && !hit)
+                    for (int e = logSeen; e < L1 && !hit; e++) hit = log_hit(sh, e, recB0, recB1, recMask);
+            }
+            logSeen = sh.logCount;
+            const unsigned int later = ~((2u << k) - 1u);
+            liveAtTurn = (liveAtTurn & ~later) | (__ballot_sync(FULL, live) & later);
+            work = __ballot_sync(FULL, lane > k && live && !(recOc == OC_NOCHANGE && !hit));
+        }
+    }
+    STAT(c, ST_LIVE, __popc(liveAtTurn));
+    __syncwarp();
+}
+
+// drain the READY prefix at the frontier if nobody else is doing it
+__device__ void try_retire(WarpCtx& c, const unsigned int* cl, int nCells, int nChunks, const ChunkRecs& R, int* lab, LsdbRect* rc, int maxSeg) {
+    GrowShared& sh = *c.sh;
+    int go = 0;
+    if (c.lane == 0) {
+        const int f = sh.frontier;
+        if (f < nChunks && sh.chunkFlag[f & (RING - 1)] == 1 && atomicCAS(&sh.retireLock, 0, 1) == 0) go = 1;
+    }
+    go = __shfl_sync(FULL, go, 0);
+    if (!go) return;
+    long long t0 = clock64();
+    __threadfence_block();
+    while (!sh.abortFlag) {
+        const int f = sh.frontier;
+        if (f >= nChunks || sh.chunkFlag[f & (RING - 1)] != 1) break;
+        __threadfence();
+        retire_chunk(c, f, cl, nCells, R, lab, rc, maxSeg);
+        __threadfence_block();
+        if (c.lane == 0) {
+            const int slot = f & (RING - 1);
+            sh.arenaTail[sh.chunkWarp[slot]] = sh.chunkEnd[slot];   // that warp's parked records up to here are dead
+            sh.chunkFlag[slot] = 0;
+            atomicAdd(&sh.stats[ST_CHUNKS], 1ull);
+            __threadfence_block();
+            sh.frontier = f + 1;
+        }
+        __syncwarp();
+    }
+    if (c.lane == 0) {
+        atomicAdd(&sh.stats[TM_RETIRE], (unsigned long long)(clock64() - t0));
+        __threadfence_block();
+        atomicExch(&sh.retireLock, 0);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, const LsdbImg* __restrict__ imgs, LsdbImgDyn* __restrict__ dyn,
+                                                                   const LsdbLsdConst* __restrict__ kc, const double* __restrict__ mag,
+                                                                   const double* __restrict__ deg, const double* __restrict__ cosm,
+                                                                   const double* __restrict__ sinm, unsigned int* __restrict__ state,
+                                                                   const unsigned int* __restrict__ cells, int* __restrict__ labels,
+                                                                   LsdbRect* __restrict__ rects, int maxSeg, unsigned int* __restrict__ lists,
+                                                                   int listCap, int arenaCap, int runAhead, unsigned char* __restrict__ recBuf,
+                                                                   const double* __restrict__ lgammaTab, int lgammaN, int* __restrict__ imgCounter) {
     __shared__ GrowShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
     WarpCtx c;
     c.lane = lane; c.w = w; c.mybit = 1u << (LSDB_ST_WARP_SHIFT + w);
     c.kc = kc; c.lgammaTab = lgammaTab; c.lgammaN = lgammaN; c.sh = &sh;
-    c.listCap = listCap;
-    c.list = lists + ((size_t)blockIdx.x * NW + w) * 2 * (size_t)listCap;
-    c.tlist = c.list + listCap;
+    c.listCap = listCap; c.arenaCap = arenaCap;
+    c.warpStride = 3 * (size_t)listCap + 64 + (size_t)arenaCap;
+    c.listsBase = lists + (size_t)blockIdx.x * nw * c.warpStride;
+    c.list = c.listsBase + (size_t)w * c.warpStride;
+    c.scratch = c.list + listCap;
+    c.arena = c.scratch + 2 * (size_t)listCap + 64;
+    ChunkRecs R;
+    {
+        unsigned char* base = recBuf + (size_t)blockIdx.x * (RING * 32 * 32);
+        R.mask = reinterpret_cast<unsigned long long*>(base);
+        R.oc = reinterpret_cast<int*>(base + RING * 32 * 8);
+        R.L0 = R.oc + RING * 32; R.b0 = reinterpret_cast<unsigned int*>(R.L0 + RING * 32); R.b1 = R.b0 + RING * 32;
+        R.off = R.b1 + RING * 32; R.chk = reinterpret_cast<int*>(R.off + RING * 32);
+    }
 
     while (true) {
         __syncthreads();
@@ -642,103 +980,56 @@ __global__ void __launch_bounds__(NW * 32, 1) lsdb_grow_kernel(int nImgs, const 
             const int img = atomicAdd(imgCounter, 1);
             sh.img = img;
             if (img < nImgs) {
-                sh.frontier = 0; sh.nextChunk = 0; sh.logCount = 0; sh.nSeg = 0; sh.abortFlag = 0;
+                sh.frontier = 0; sh.nextChunk = 0; sh.logCount = 0; sh.nSeg = 0; sh.abortFlag = 0; sh.retireLock = 0;
                 sh.nCells = dyn[img].nCells;
                 sh.nChunks = (sh.nCells + LSDB_CHUNK - 1) / LSDB_CHUNK;
             }
         }
         if (tid < TM_N) sh.stats[tid] = 0;
+        if (tid < NW_MAX) sh.arenaTail[tid] = 0;
+        for (int i = tid; i < RING; i += blockDim.x) sh.chunkFlag[i] = 0;
         __syncthreads();
         const int img = sh.img;
         if (img >= nImgs) break;
         const LsdbImg im = imgs[img];
         c.W = im.W; c.H = im.H; c.logNT = im.logNT; c.regThre = im.regThre;
-        c.state = state + im.nOff; c.deg = deg + im.nOff; c.mag = mag + im.nOff;
+        {
+            int k = 0;
+            while (((max(im.W, im.H) - 1) >> k) > 7) k++;
+            c.cellShift = k;
+        }
+        c.state = state + im.nOff; c.deg = deg + im.nOff; c.mag = mag + im.nOff; c.cosm = cosm + im.nOff; c.sinm = sinm + im.nOff;
         int* lab = labels + im.nOff;
         const unsigned int* cl = cells + im.nOff;
         LsdbRect* rc = rects + im.segOff;
         const int nCells = sh.nCells, nChunks = sh.nChunks;
+        unsigned int head = 0;      // this warp's virtual arena write offset
+        unsigned int idle = 0;
 
-        while (true) {
-            int chunk = 0;
-            if (lane == 0) chunk = atomicAdd(&sh.nextChunk, 1);
-            chunk = __shfl_sync(FULL, chunk, 0);
-            if (chunk >= nChunks || sh.abortFlag) break;
-            const int ci = chunk * LSDB_CHUNK + lane;
-            const int myp = ci < nCells ? (int)cl[ci] : -1;
-            const bool live = myp >= 0 && (lsdb_ld_state(&c.state[myp]) & 3u) == 0;
-            const unsigned int liveMask = __ballot_sync(FULL, live);
-            // per-lane record of the speculative evaluation of "my" cell
-            int recOc = OC_NONE, recL0 = 0;
-            unsigned int recB0 = 0, recB1 = 0;
-            // stash (at most one non-NOCHANGE speculative result per chunk)
-            int stashLane = -1, stashOc = OC_NONE, stashN = 0;
-            Rect stashRec; double stashNfa = 0;
-            Rect rec; double nfa = 0; BBox bb; int nCommit = 0; bool touchedT = false;
-
-            // ---------------- speculative phase
-            unsigned int rem = liveMask;
-            long long tSpec = clock64();
-            while (rem && sh.frontier != chunk && !sh.abortFlag) {
-                const int k = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const int p = __shfl_sync(FULL, myp, k);
-                if (lsdb_ld_state(&c.state[p]) & 3u) continue;
-                const int L0 = sh.logCount;
-                __threadfence_block();
-                const int oc = eval_seed(c, p, stashLane < 0, rec, nfa, bb, nCommit, touchedT);
-                STAT(c, ST_SPEC, 1);
-                if (oc == OC_DEFER) break;
-                if (lane == k) { recOc = oc; recL0 = L0; recB0 = pack_xy(bb.x0, bb.y0); recB1 = pack_xy(bb.x1, bb.y1); }
-                if (oc != OC_NOCHANGE) { stashLane = k; stashOc = oc; stashN = nCommit; stashRec = rec; stashNfa = nfa; }
-            }
-
-            // ---------------- wait for every earlier chunk to retire
-            long long tWait = clock64();
-            if (lane == 0) atomicAdd(&sh.stats[TM_SPEC], (unsigned long long)(tWait - tSpec));
+        while (!sh.abortFlag) {
+            try_retire(c, cl, nCells, nChunks, R, lab, rc, maxSeg);
+            if (sh.frontier >= nChunks) break;
+            int chunk = -1;
             if (lane == 0) {
-                unsigned int spins = 0;
-                while (sh.frontier != chunk && !sh.abortFlag) {
-                    __nanosleep(64);
-                    if (++spins > (1u << 26)) sh.abortFlag = LSDB_ERR_TIMEOUT;
+                // claim a ticket only while the ring has room
+                if (sh.nextChunk < nChunks && sh.nextChunk - sh.frontier < runAhead) {
+                    chunk = atomicAdd(&sh.nextChunk, 1);
+                    if (chunk >= nChunks) chunk = -1;
                 }
             }
-            __syncwarp();
-            __threadfence_block();
-            if (sh.abortFlag) break;
-
-            // ---------------- retire phase: in seed order, validate or re-evaluate, commit
-            long long tRet = clock64();
-            if (lane == 0) atomicAdd(&sh.stats[TM_WAIT], (unsigned long long)(tRet - tWait));
-            rem = liveMask;
-            while (rem) {
-                const int k = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const int p = __shfl_sync(FULL, myp, k);
-                if (lsdb_ld_state(&c.state[p]) & 3u) continue;  // :222
-                STAT(c, ST_LIVE, 1);
-                const int oc = __shfl_sync(FULL, recOc, k);
-                const int L0 = __shfl_sync(FULL, recL0, k);
-                const unsigned int b0 = __shfl_sync(FULL, recB0, k), b1 = __shfl_sync(FULL, recB1, k);
-                if (oc != OC_NONE && !has_conflict(c, L0, b0, b1)) {
-                    if (oc == OC_NOCHANGE) continue;
-                    if (k == stashLane) {
-                        commit_region(c, stashOc, stashN, stashRec, stashNfa, lab, rc, maxSeg);
-                        stashLane = -1;
-                        continue;
-                    }
+            chunk = __shfl_sync(FULL, chunk, 0);
+            if (chunk < 0) {   // nothing to claim: wait for the frontier to move (or for work to drain)
+                long long tw = clock64();
+                __nanosleep(200);
+                if (lane == 0) {
+                    atomicAdd(&sh.stats[TM_WAIT], (unsigned long long)(clock64() - tw));
+                    if (++idle > (1u << 24)) sh.abortFlag = LSDB_ERR_TIMEOUT;
                 }
-                if (k == stashLane) stashLane = -1;  // stale stash: bits are already cleared
-                const int oc2 = eval_seed(c, p, true, rec, nfa, bb, nCommit, touchedT);
-                if (touchedT && stashLane >= 0) stashLane = -2;  // the buffer of a later stash was overwritten
-                STAT(c, ST_RESPEC, 1);
-                if (oc2 == OC_REJECT || oc2 == OC_ACCEPT) commit_region(c, oc2, nCommit, rec, nfa, lab, rc, maxSeg);
-                if (sh.abortFlag) break;
+                __syncwarp();
+                continue;
             }
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0) { atomicAdd(&sh.stats[ST_CHUNKS], 1ull); sh.frontier = chunk + 1; }
-            if (lane == 0) atomicAdd(&sh.stats[TM_RETIRE], (unsigned long long)(clock64() - tRet));
+            idle = 0;
+            speculate_chunk(c, chunk, cl, nCells, R, head);
         }
         __syncthreads();
         if (tid == 0) {
@@ -759,14 +1050,20 @@ __global__ void lsdb_used_plane_kernel(const unsigned int* __restrict__ state, u
     }
 }
 
-void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, const LsdbImg* imgs, LsdbImgDyn* dyn,
-                      const LsdbLsdConst* kc, const double* mag, const double* deg, unsigned int* state,
-                      const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
-                      unsigned int* lists, int listCap, const double* lgammaTab, int lgammaN, int* imgCounter) {
+void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, const LsdbImg* imgs, LsdbImgDyn* dyn,
+                      const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
+                      unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
+                      unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
+                      int* imgCounter) {
+    if (runAhead > RING - NW_MAX) runAhead = RING - NW_MAX;
+    if (runAhead < 1) runAhead = 1;
     if (nImgs > 0)
-        lsdb_grow_kernel<<<nCtas, NW * 32, 0, s>>>(nImgs, imgs, dyn, kc, mag, deg, state, cells, labels, rects, maxSeg,
-                                                   lists, listCap, lgammaTab, lgammaN, imgCounter);
+        lsdb_grow_kernel<<<nCtas, warpsPerCta * 32, 0, s>>>(nImgs, imgs, dyn, kc, mag, deg, cosm, sinm, state, cells, labels, rects, maxSeg,
+                                                            lists, listCap, arenaCap, runAhead, recBuf, lgammaTab, lgammaN, imgCounter);
 }
+
+size_t lsdb_grow_rec_bytes_per_cta(void) { return (size_t)RING * 32 * 32; }
+size_t lsdb_grow_list_words_per_warp(int listCap, int arenaCap) { return 3 * (size_t)listCap + 64 + (size_t)arenaCap; }
 
 void lsdb_launch_lgamma_table(cudaStream_t s, double* tab, int n) {
     lsdb_lgamma_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(tab, n);
@@ -776,10 +1073,11 @@ void lsdb_launch_used_plane(cudaStream_t s, const unsigned int* state, uint8_t* 
     lsdb_used_plane_kernel<<<(n + 255) / 256, 256, 0, s>>>(state, used, n);
 }
 
-int lsdb_grow_max_ctas(int device) {
+// how many CTAs of `warpsPerCta` warps fit on the device at once (the kernel is persistent)
+int lsdb_grow_max_ctas(int device, int warpsPerCta) {
     int sms = 0, per = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lsdb_grow_kernel, NW * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lsdb_grow_kernel, warpsPerCta * 32, 0);
     if (per < 1) per = 1;
     return sms * per;
 }

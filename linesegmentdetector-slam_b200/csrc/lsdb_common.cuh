@@ -27,7 +27,7 @@ struct LsdbImgDyn {
     int nSeg;                        // accepted segments
     int err;                         // LSDB_ERR_* raised by a kernel for this map
     int pad_;
-    long long stat[20];              // lsdb_stats fields
+    long long stat[21];              // lsdb_stats fields
 };
 
 struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec logNFA
@@ -38,6 +38,7 @@ struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec l
 //   bit 8+w : pixel is in the region warp w of the owning CTA is currently growing (curMap)
 #define LSDB_ST_BAN 1u
 #define LSDB_ST_REJ 2u
+#define LSDB_ST_HINT 4u    // pixel belongs to a parked (not yet retired) accept/reject candidate — speculation hint only
 #define LSDB_ST_WARP_SHIFT 8
 
 #define LSDB_TILE 32            // stencil output tile (scaled pixels)
@@ -45,8 +46,11 @@ struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec l
 #define LSDB_GROW_WARPS 16
 #define LSDB_CHUNK 32           // seed-list cells per ordered-commit chunk
 
+#define LSDB_NP 12
 struct LsdbLsdConst {
     double sca, degThre, gradThre, pi, aliPro, denThre;
+    double cosDegThre;           // lsdm_cos(degThre)
+    double pTab[LSDB_NP], logP[LSDB_NP], log1mP[LSDB_NP], log10P[LSDB_NP];  // p = aliPro/2^k and its logs
     int pseBin, h;
     double taps[3 * 17];
 };
@@ -66,17 +70,20 @@ __device__ __forceinline__ int lsdb_x86_d2i(double v) {
 
 // launchers (defined in the .cu files, called from api.cu)
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
-                         const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg,
+                         const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
                          unsigned int* state, double* gaussOut);
 void lsdb_launch_order(cudaStream_t s, int nImgs, const LsdbImg* imgs, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
                        const double* mag, unsigned short* bins, unsigned int* cells);
-void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, const LsdbImg* imgs, LsdbImgDyn* dyn,
-                      const LsdbLsdConst* kc, const double* mag, const double* deg, unsigned int* state,
-                      const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
-                      unsigned int* lists, int listCap, const double* lgammaTab, int lgammaN, int* imgCounter);
+void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, const LsdbImg* imgs, LsdbImgDyn* dyn,
+                      const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
+                      unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
+                      unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
+                      int* imgCounter);
+size_t lsdb_grow_rec_bytes_per_cta(void);
+size_t lsdb_grow_list_words_per_warp(int listCap, int arenaCap);
 void lsdb_launch_lgamma_table(cudaStream_t s, double* tab, int n);
 void lsdb_launch_used_plane(cudaStream_t s, const unsigned int* state, uint8_t* used, int n);
-int lsdb_grow_max_ctas(int device);
+int lsdb_grow_max_ctas(int device, int warpsPerCta);
 
 struct LsdbFaTask { int frame, iScan, iMap, pad; };
 struct LsdbFaHyp { int frame, iScan, iMap, iPair; double x, y, ang, score; };  // == lsdb_hypothesis

@@ -54,7 +54,8 @@ __device__ __forceinline__ void lsdb_window(int c0, int c1, int h, int lim, int*
 __global__ void __launch_bounds__(256) lsdb_stencil_kernel(const LsdbImg* __restrict__ imgs, const int* __restrict__ tileImg,
                                                            LsdbImgDyn* __restrict__ dyn, const LsdbLsdConst* __restrict__ kc,
                                                            const uint8_t* __restrict__ src, double* __restrict__ mag,
-                                                           double* __restrict__ deg, unsigned int* __restrict__ state,
+                                                           double* __restrict__ deg, double* __restrict__ cosm,
+                                                           double* __restrict__ sinm, unsigned int* __restrict__ state,
                                                            double* __restrict__ gaussOut) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StencilSmem& S = *reinterpret_cast<StencilSmem*>(smem_raw);
@@ -183,6 +184,10 @@ __global__ void __launch_bounds__(256) lsdb_stencil_kernel(const LsdbImg* __rest
             mag[p] = m;
             deg[p] = d;
             state[p] = st;
+            if (st == 0) {  // growable pixel: the addends of RegionGrower's running sums (:515-516,:545-546)
+                cosm[p] = lsdm_cos(d);
+                sinm[p] = lsdm_sin(d);
+            }
         }
     }
 #pragma unroll
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(256) lsdb_stencil_kernel(const LsdbImg* __rest
 }
 
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
-                         const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg,
+                         const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
                          unsigned int* state, double* gaussOut) {
     static bool attr = false;
     if (!attr) {
@@ -205,5 +210,5 @@ void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const 
         attr = true;
     }
     if (nTiles > 0)
-        lsdb_stencil_kernel<<<nTiles, 256, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, state, gaussOut);
+        lsdb_stencil_kernel<<<nTiles, 256, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, gaussOut);
 }

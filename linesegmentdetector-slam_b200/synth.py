@@ -22,13 +22,17 @@ def _draw_wall(m, x0, y0, x1, y1, thick, val=1):
         m[yi[ok], xi[ok]] = val
 
 
-def occupancy_grid(cols, rows, seed, occ_frac=0.012, speckle=0.0005):
+def occupancy_grid(cols, rows, seed, occ_frac=0.012, speckle=0.0005, border_walls=False):
     rng = np.random.default_rng(seed)
     m = np.zeros((rows, cols), np.uint8)
     # unknown: outer margin of random width + a few rectangular blobs  (~20 %)
     mx0, mx1 = rng.integers(int(cols * 0.02), int(cols * 0.07) + 2, 2)
     my0, my1 = rng.integers(int(rows * 0.02), int(rows * 0.07) + 2, 2)
     m[:my0, :] = 255; m[rows - my1:, :] = 255; m[:, :mx0] = 255; m[:, cols - mx1:] = 255
+    if not border_walls:
+        # like every bundled map, the first row / column themselves are 0: the reference leaves them un-remapped,
+        # so a 255 border line would be a ring-shaped edge that every one of its ~2(W'+H') pixels re-floods
+        m[0, :] = 0; m[:, 0] = 0
     for _ in range(6):
         w, h = rng.integers(cols // 20, cols // 7 + 2), rng.integers(rows // 20, rows // 7 + 2)
         x, y = rng.integers(0, cols - w), rng.integers(0, rows - h)
@@ -61,11 +65,15 @@ def occupancy_grid(cols, rows, seed, occ_frac=0.012, speckle=0.0005):
                 occ += int(L) * thick
                 x, y = x2, y2
                 ang += rng.choice([-np.pi / 2, np.pi / 2, rng.uniform(-0.6, 0.6)])
-    # walls running into the first row / column
+    # walls running INTO the first row / column (the reference never remaps or thresholds row 0 / col 0,
+    # LSD/myLSD.cpp:135-136,153-154, so regions may grow along the border).  `border_walls` additionally
+    # lays walls ALONG row 0 / col 0: every one of their pixels then seeds a flood of the whole border ring
+    # in the reference algorithm — a parity edge case (tests), not part of the throughput workload.
     _draw_wall(m, 0, rows * 0.3, cols * 0.2, rows * 0.3, 2)
     _draw_wall(m, cols * 0.4, 0, cols * 0.4, rows * 0.15, 2)
-    _draw_wall(m, 0, 0, cols * 0.1, 0, 1)
-    _draw_wall(m, 0, rows * 0.6, 0, rows * 0.8, 1)
+    if border_walls:
+        _draw_wall(m, 0, 0, cols * 0.1, 0, 1)
+        _draw_wall(m, 0, rows * 0.6, 0, rows * 0.8, 1)
     ns = int(speckle * rows * cols)
     m[rng.integers(0, rows, ns), rng.integers(0, cols, ns)] = 1
     return m

@@ -11,6 +11,7 @@
  * Documented deviations (all are undefined behaviour in the reference):
  *  - maxGrad == 0 (blank map): the reference iterates over an uninitialised list; here 0 seeds.
  *  - RegionRadiusReducer's read of slot [num] before any removal (heap over-read) sees (0,0).
+ *  - RegionRadiusReducer with an emptied list stops instead of indexing [-1].
  *  - uninitialised yLow/yHigh entries (NaN vertices) and the epilogue's possible 1-slot
  *    over-read read as 0.
  */
@@ -240,6 +241,7 @@ static int region_radius_reducer(ctx_t* c, reg_t* reg, rec_t* rec, double denThr
         rad *= 0.75;
         int i = 0;
         while (i <= reg->num) {
+            if (reg->num <= 0) break; /* the reference would index [-1] here (heap underflow, UB) */
             if (dist_i(oriX, oriY, (double)reg->px[i], (double)reg->py[i]) > rad) {
                 c->cur[(size_t)reg->py[i] * W + reg->px[i]] = 0;
                 reg->px[i] = reg->px[reg->num - 1];
