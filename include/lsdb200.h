@@ -67,6 +67,8 @@ typedef struct {
      * RegionGrower / RectangleConverter / RectangleNFACalculator, waiting for the commit frontier,
      * in the retire phase, in the speculative phase, and in frontier re-evaluations */
     long long cyc_grow, cyc_rect, cyc_nfa, cyc_wait, cyc_retire, cyc_spec, cyc_respec;
+    /* per map, summed: SM cycles and wall nanoseconds (globaltimer) a CTA spent on the map; and one spare */
+    long long cyc_map, ns_map, spare_;
 } lsdb_stats;
 
 /* ---- context ---- */

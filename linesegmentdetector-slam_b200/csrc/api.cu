@@ -32,14 +32,14 @@ struct lsdb_batch {
     lsdb_ctx* ctx;
     int n;
     lsdb_lsd_params params;
-    int maxSeg, listCap, arenaCap, nTiles, nCtas, nWarps, runAhead;
-    size_t totalN, totalSrc;
+    int maxSeg, listCap, arenaCap, nTiles, nCtas, nWarps, runAhead, bmCapWords;
+    size_t totalN, totalSrc, totalBan;
     std::vector<LsdbImg> imgs;
     LsdbLsdConst kc;
     // device
     uint8_t* src; double* mag; double* deg; double* cosm; double* sinm; unsigned int* state; unsigned short* bins; unsigned int* cells;
     int* labels; LsdbRect* rects; LsdbImgDyn* dyn; LsdbImg* imgsD; int* tileImg; unsigned int* lists;
-    int* imgCounter; LsdbLsdConst* kcD; double* gaussDbg; unsigned char* recBuf;
+    int* imgCounter; LsdbLsdConst* kcD; double* gaussDbg; unsigned char* recBuf; unsigned int* banBits;
     // host (pinned)
     LsdbImgDyn* dynH; LsdbRect* rectsH;
     cudaEvent_t ev[4];
@@ -132,7 +132,7 @@ extern "C" void lsdb_batch_destroy(lsdb_batch* b) {
     cudaSetDevice(b->ctx->device);
     cudaFree(b->src); cudaFree(b->mag); cudaFree(b->deg); cudaFree(b->cosm); cudaFree(b->sinm); cudaFree(b->state); cudaFree(b->bins); cudaFree(b->cells);
     cudaFree(b->labels); cudaFree(b->rects); cudaFree(b->dyn); cudaFree(b->imgsD); cudaFree(b->tileImg); cudaFree(b->lists);
-    cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg); cudaFree(b->recBuf);
+    cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg); cudaFree(b->recBuf); cudaFree(b->banBits);
     cudaFreeHost(b->dynH); cudaFreeHost(b->rectsH);
     for (int i = 0; i < 4; i++) cudaEventDestroy(b->ev[i]);
     if (b->ctx->cached == b) b->ctx->cached = 0;
@@ -150,7 +150,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     memset(&b->kc, 0, sizeof b->kc);
     b->ctx = ctx; b->n = n; b->params = *prm; b->ran = false; b->downloaded = false; b->launches = 0;
     b->src = 0; b->mag = 0; b->deg = 0; b->cosm = 0; b->sinm = 0; b->state = 0; b->bins = 0; b->cells = 0; b->labels = 0; b->rects = 0; b->dyn = 0;
-    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->dynH = 0; b->rectsH = 0;
+    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->banBits = 0; b->dynH = 0; b->rectsH = 0;
     for (int i = 0; i < 4; i++) cudaEventCreate(&b->ev[i]);
     b->maxSeg = maxLines > 0 ? maxLines : 4096;
 
@@ -171,8 +171,8 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     }
 
     b->imgs.resize(n);
-    size_t srcOff = 0, nOff = 0;
-    int tile0 = 0, maxN = 0;
+    size_t srcOff = 0, nOff = 0, banOff = 0;
+    int tile0 = 0, maxN = 0, maxBanWords = 0;
     std::vector<int> tileImgH;
     for (int i = 0; i < n; i++) {
         LsdbImg& im = b->imgs[i];
@@ -184,6 +184,9 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         im.n = im.W * im.H;
         im.srcPitch = (cols[i] + 15) & ~15;
         im.srcOff = srcOff; im.nOff = nOff; im.segOff = (size_t)i * b->maxSeg;
+        im.pw = (im.W + 31) / 32; im.banOff = banOff;
+        banOff += ((size_t)im.H * im.pw + 3) & ~(size_t)3;
+        if (im.H * im.pw > maxBanWords) maxBanWords = im.H * im.pw;
         im.tilesX = (im.W + LSDB_TILE - 1) / LSDB_TILE; im.tilesY = (im.H + LSDB_TILE - 1) / LSDB_TILE;
         im.tile0 = tile0;
         im.logNT = 5 * (lsdm_log10(im.H) + lsdm_log10(im.W)) / 2.0;         // :207
@@ -194,20 +197,28 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         nOff += ((size_t)im.n + 31) & ~(size_t)31;
         if (im.n > maxN) maxN = im.n;
     }
-    b->nTiles = tile0; b->totalN = nOff; b->totalSrc = srcOff;
+    b->nTiles = tile0; b->totalN = nOff; b->totalSrc = srcOff; b->totalBan = banOff;
     b->listCap = maxN + 2 < (1 << 16) ? ((maxN + 2 + 1) & ~1) : (1 << 16);  // even: the arena behind it holds doubles
+    if (b->listCap < 32 * LSDB_SUPER) b->listCap = 32 * LSDB_SUPER;          // the scratch behind it also holds a super-chunk's seed queue
     {   // team size: spread the device's warp slots over the maps of the batch (16 warps for a lone map,
         // 8 when ~2 maps share an SM, ...); every CTA grows one map at a time
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        // the ban plane of a map (one bit per scaled pixel) lives in shared memory while the map is grown, if it fits
+        const int bmMax = lsdb_grow_max_bitmap_words(ctx->device);
+        b->bmCapWords = maxBanWords <= bmMax ? maxBanWords : 0;
+        if (getenv("LSDB_NO_SMEM_BAN")) b->bmCapWords = 0;
         int nw = LSDB_GROW_WARPS;
-        while (nw > 4 && (long long)n * nw > (long long)sms * LSDB_GROW_WARPS) nw >>= 1;
+        // halve the team while that puts more maps on the device at once (shared memory or registers permitting)
+        while (nw > 4 && (long long)n > lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords) &&
+               lsdb_grow_max_ctas(ctx->device, nw / 2, b->bmCapWords) > lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords)) nw >>= 1;
         if (getenv("LSDB_GROW_WARPS")) { int v = atoi(getenv("LSDB_GROW_WARPS")); if (v >= 1 && v <= LSDB_GROW_WARPS) nw = v; }
         b->nWarps = nw;
-        b->runAhead = 8 * nw;   // chunks a map's team may speculate ahead of its commit frontier
+        b->runAhead = 2 * LSDB_SUPER * nw;   // chunks a map's team may speculate ahead of its commit frontier
         if (getenv("LSDB_RUNAHEAD")) b->runAhead = atoi(getenv("LSDB_RUNAHEAD"));
-        const int maxCtas = lsdb_grow_max_ctas(ctx->device, nw);
+        const int maxCtas = lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords);
         b->nCtas = n < maxCtas ? n : maxCtas;
+        (void)sms;
     }
 
     cudaError_t e = cudaSuccess;
@@ -219,7 +230,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     b->arenaCap = 2 * b->listCap < (1 << 15) ? (1 << 15) : 2 * b->listCap;
     AL(b->lists, (size_t)b->nCtas * b->nWarps * lsdb_grow_list_words_per_warp(b->listCap, b->arenaCap) * 4);
     AL(b->recBuf, (size_t)b->nCtas * lsdb_grow_rec_bytes_per_cta());
-    AL(b->imgCounter, 64); AL(b->kcD, sizeof(LsdbLsdConst));
+    AL(b->imgCounter, 64); AL(b->kcD, sizeof(LsdbLsdConst)); AL(b->banBits, (b->totalBan + 4) * 4);
 #undef AL
     if (e == cudaSuccess) e = cudaMallocHost((void**)&b->dynH, (size_t)n * sizeof(LsdbImgDyn));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&b->rectsH, (size_t)n * b->maxSeg * sizeof(LsdbRect));
@@ -256,12 +267,13 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaMemsetAsync(b->labels, 0, b->totalN * 4, s));
     CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
     CK(ctx, cudaEventRecord(b->ev[0], s));
-    lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->gaussDbg);
+    lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->banBits, b->gaussDbg);
     CK(ctx, cudaEventRecord(b->ev[1], s));
     lsdb_launch_order(s, b->n, b->imgsD, b->dyn, b->kcD, b->mag, b->bins, b->cells);
     CK(ctx, cudaEventRecord(b->ev[2], s));
     lsdb_launch_grow(s, b->n, b->nCtas, b->nWarps, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->cosm, b->sinm, b->state, b->cells, b->labels, b->rects,
-                     b->maxSeg, b->lists, b->listCap, b->arenaCap, b->runAhead, b->recBuf, ctx->lgammaTab, ctx->lgammaN, b->imgCounter);
+                     b->maxSeg, b->lists, b->listCap, b->arenaCap, b->runAhead, b->recBuf, ctx->lgammaTab, ctx->lgammaN, b->imgCounter, b->banBits,
+                     b->bmCapWords);
     CK(ctx, cudaEventRecord(b->ev[3], s));
     CK(ctx, cudaGetLastError());
     b->ran = true; b->downloaded = false; b->launches = 3;
@@ -399,9 +411,9 @@ extern "C" int lsdb_batch_stats(lsdb_batch* b, lsdb_stats* total) {
     int rc = fetch_dyn(b);
     if (rc) return rc;
     long long* t = (long long*)total;
-    for (int k = 0; k < 21; k++) t[k] = 0;
+    for (int k = 0; k < 24; k++) t[k] = 0;
     for (int i = 0; i < b->n; i++)
-        for (int k = 0; k < 21; k++) t[k] += b->dynH[i].stat[k];
+        for (int k = 0; k < 24; k++) t[k] += b->dynH[i].stat[k];
     return LSDB_OK;
 }
 

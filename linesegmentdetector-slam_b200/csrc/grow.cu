@@ -34,16 +34,17 @@
 
 #define NW_MAX LSDB_GROW_WARPS
 #define ARENA_HDR 32  // words: 13 doubles (rect + logNFA), nCommit, outcome
-#define LOG_CAP 1024
+#define LOG_CAP 512
 #define FULL 0xffffffffu
 
 enum { OC_NONE = 0, OC_NOCHANGE = 1, OC_REJECT = 2, OC_ACCEPT = 3, OC_DEFER = 4 };
 enum { ST_CELLS = 0, ST_LIVE, ST_GROWS, ST_GROWNPX, ST_SMALL, ST_REGROWS, ST_RRR, ST_NFACALLS, ST_NFAPX, ST_REJECTS,
        ST_ACCEPTS, ST_SPEC, ST_RESPEC, ST_CHUNKS, ST_N,
        // cycle counters (lane 0 of every warp, summed): only kept in LSDB_TIMING builds, reported through stat[] slots 14..19
-       TM_GROW = ST_N, TM_RECT, TM_NFA, TM_WAIT, TM_RETIRE, TM_SPEC, TM_RESPEC, TM_N };
+       TM_GROW = ST_N, TM_RECT, TM_NFA, TM_WAIT, TM_RETIRE, TM_SPEC, TM_RESPEC, TM_MAPCYC, TM_MAPNS, TM_SPARE, TM_N };
 
-#define RING 1024          // chunks a CTA may run ahead of the commit frontier
+#define RING 512           // chunks a CTA may run ahead of the commit frontier
+#define SG_CAP 32          // lane-per-seed growth handles regions below min(regThre, SG_CAP) pixels
 struct GrowShared {
     volatile int frontier;     // first chunk not yet retired
     int nextChunk;             // ticket counter
@@ -62,6 +63,13 @@ struct GrowShared {
     unsigned long long logMask[LOG_CAP];
     unsigned long long stats[TM_N];
 };
+
+#define LSDB_REJ_CAP (1 << 16)   // words per reject list of grow_region (two per warp)
+__host__ __device__ inline size_t grow_words_per_warp(int listCap, int arenaCap) {
+    return 3 * (size_t)listCap + 64 + (size_t)arenaCap + 2 * (size_t)LSDB_REJ_CAP;
+}
+// dynamic shared memory of the kernel: the ban plane, then 1 KB of staging per warp
+static inline size_t grow_dyn_smem(int bmCapWords, int warpsPerCta) { return (size_t)((bmCapWords + 1) & ~1) * 4 + (size_t)warpsPerCta * 1024; }
 
 struct Rect { double x1, y1, x2, y2, wid, cX, cY, deg, dx, dy, p, prec; };
 
@@ -94,6 +102,11 @@ struct WarpCtx {
     const double* lgammaTab;
     int lgammaN;
     GrowShared* sh;
+    unsigned int* rej[2];   // reject lists of grow_region (ping-pong), rejCap words each
+    int rejCap;
+    double* stage;          // 32 x 4 doubles of shared memory: operands of the ordered sums in rect_from_region
+    volatile unsigned int* bm;   // shared-memory copy of the ban plane (usedMap==1), one bit per pixel, pw words per row; NULL: use `state`
+    int pw;
     double logNT, regThre;
     int cellShift;        // coarse-grid cell = 2^cellShift pixels, grid <= 8x8
 };
@@ -128,158 +141,354 @@ __device__ void clear_bits(const WarpCtx& c, const unsigned int* lst, int num) {
     __syncwarp();
 }
 
+// ------------------------------------------------------------------ ban plane (usedMap == 1)
+// The hot question of the grower — "is this neighbour banned?" (:537) — is answered from a one-bit-per-pixel
+// copy of the plane in shared memory when the map fits (c.bm), else from the global state words.
+__device__ __forceinline__ bool ban_at(const WarpCtx& c, int x, int y) {
+    if (c.bm) return (c.bm[(size_t)y * c.pw + (x >> 5)] >> (x & 31)) & 1u;
+    return (lsdb_ld_state(&c.state[(size_t)y * c.W + x]) & LSDB_ST_BAN) != 0;
+}
+// bits (x-1, x, x+1) of row y, bit 0 = x-1; out-of-image pixels read as banned
+__device__ __forceinline__ unsigned int ban_row3(const WarpCtx& c, int x, int y) {
+    if (y < 0 || y >= c.H) return 7u;
+    unsigned int out;
+    if (c.bm) {
+        const volatile unsigned int* r = c.bm + (size_t)y * c.pw;
+        if (x == 0) out = ((r[0] << 1) | 1u) & 7u;
+        else {
+            const int xl = x - 1, wi = xl >> 5, sh = xl & 31;
+            const unsigned int lo = r[wi];
+            const unsigned int hi = (sh > 29 && wi + 1 < c.pw) ? r[wi + 1] : 0xffffffffu;
+            out = __funnelshift_r(lo, hi, sh) & 7u;
+        }
+    } else {
+        const unsigned int* r = c.state + (size_t)y * c.W;
+        out = 0;
+        if (x == 0 || (lsdb_ld_state(&r[x - 1]) & LSDB_ST_BAN)) out |= 1u;
+        if (lsdb_ld_state(&r[x]) & LSDB_ST_BAN) out |= 2u;
+        if (x + 1 >= c.W || (lsdb_ld_state(&r[x + 1]) & LSDB_ST_BAN)) out |= 4u;
+    }
+    if (x + 1 >= c.W) out |= 4u;
+    return out;
+}
+// the 3x3 neighbourhood of (x,y) in the reference's scan order (:533-535): bit (dy+1)*3+(dx+1) set = banned / outside
+__device__ __forceinline__ unsigned int ban9(const WarpCtx& c, int x, int y) {
+    return ban_row3(c, x, y - 1) | (ban_row3(c, x, y) << 3) | (ban_row3(c, x, y + 1) << 6);
+}
+__device__ __forceinline__ void ban_set(const WarpCtx& c, int x, int y) {
+    if (c.bm) atomicOr(const_cast<unsigned int*>(c.bm) + (size_t)y * c.pw + (x >> 5), 1u << (x & 31));
+}
+
 // ------------------------------------------------------------------ RegionGrower (:491-590)
 // Returns the region size (points in c.list), -1 on list overflow.  regDeg in (= deg[seed] at both
-// call sites :225,:857) / out (atan2 of the final sums, :547).
+// call sites :225,:857) / out (atan2 of the final sums, :547).  bb = bounding box / coarse cells of the region.
 //
 // The reference re-estimates regDeg = atan2(sinDeg, cosDeg) after EVERY accepted pixel and tests the
 // next neighbour with |regDeg - deg| < tol (:540-543).  Evaluating that literally puts ~300 dependent
 // double-double flops on the accept chain.  Here the test is decided from the running sums directly:
 //     cos(angle between (cosDeg,sinDeg) and the candidate) = (cosDeg*cos d + sinDeg*sin d)/|(cosDeg,sinDeg)|
 // compared with cos(tol), using the per-pixel cos/sin planes written by the stencil stage (the same
-// lsdm_cos/lsdm_sin values the reference adds to its sums).  The comparison is accepted only when it
-// clears the threshold by 1e-13 (the reference's own rounding moves the decision by < 2e-15); the rare
-// knife-edge candidate, tolerances above pi/2 near the reference's un-wrapped band (pi, 3pi/2], and
-// degenerate sums fall back to the literal atan2 test.  Decisions — and therefore the pixel order,
-// the sums and the final regDeg — are identical to the literal evaluation.
-__device__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double degThre, BBox& bb) {
-    const int W = c.W, H = c.H;
+// lsdm_cos/lsdm_sin values the reference adds to its sums).  For tol <= pi/2 the comparison is made on
+// the squares (dot > 0 and dot^2 > cos^2(tol)*|sum|^2: no square root on the chain); it is accepted only
+// when it clears the threshold by a margin that corresponds to > 2e-13 in the cosine (the reference's own
+// rounding moves the decision by < 2e-15); the rare knife-edge candidate, tolerances above pi/2 near the
+// reference's un-wrapped band (pi, 3pi/2], and degenerate sums fall back to the literal atan2 test.
+// Decisions — and therefore the pixel order, the sums and the final regDeg — are identical to the
+// literal evaluation.
+//
+// The reference re-scans the whole list until a pass adds nothing (:525-565).  A neighbour that was
+// outside the image, banned or already in the region stays so, therefore only the candidates that failed
+// the ANGLE test can change their outcome in a later pass: those are kept, in scan order, in a reject
+// list (ping-pong buffers c.rej[0/1]); a later pass re-tests exactly them, then scans the points that
+// joined during the pass.  Same accept sequence as the literal re-scan, a fraction of the work.
+struct GrowSums {
+    double cosDeg, sinDeg;   // running sums (:515-516,:545-546)
+    double n2, c2n2, m2;     // |sum|^2, cos^2(tol)*|sum|^2, decision margin on the squares
+    double nrm, thr, margin; // sqrt forms (tol > pi/2 only)
+    float regA;
+    bool nrmOK;
+};
+
+__device__ __forceinline__ void sums_refresh(GrowSums& g, double c2, double cTau, bool tauSmall) {
+    g.n2 = g.cosDeg * g.cosDeg + g.sinDeg * g.sinDeg;
+    g.nrmOK = g.n2 > 1e-18;
+    if (tauSmall) {
+        g.c2n2 = c2 * g.n2;
+        g.m2 = 4e-13 * g.n2;
+    } else {
+        g.nrm = sqrt(g.n2);
+        g.thr = cTau * g.nrm; g.margin = 1e-13 * g.nrm;
+        g.regA = atan2f((float)g.sinDeg, (float)g.cosDeg);
+    }
+}
+
+// accept loop over the (up to 32) candidates the lanes hold, in lane order.  cand: lane holds a live candidate
+// (in the image, not banned, not in the region); p/n/m its pixel; dg/cd/sd its angle data.  On return cand is
+// true exactly for the candidates that failed the angle test (the rest joined the region or dropped out).
+__device__ __forceinline__ int accept_lanes(WarpCtx& c, GrowSums& g, bool& cand, size_t p, int n, int m, double dg, double cd, double sd,
+                                            int& num, bool& haveExact, double& regExact, double degThre, double c2, double cTau,
+                                            bool tauSmall, bool tauGtPi, float tauF) {
     const double pi = c.kc->pi;
     const double pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
+    int start = 0;
+    while (true) {
+        const bool active = cand && c.lane >= start;
+        bool pass = false, unc = false;
+        if (active) {
+            const double dot = g.cosDeg * cd + g.sinDeg * sd;
+            if (tauSmall) {
+                const double d2 = dot * dot - g.c2n2;
+                pass = dot > 0 && d2 > 0;
+                unc = dot > 0 && !(fabs(d2) > g.m2);
+            } else {
+                const double diff = dot - g.thr;
+                const bool cosCertain = fabs(diff) > g.margin;
+                const float aA = fabsf(g.regA - (float)dg);
+                if (fabsf(aA - 3.14159265f) < 1e-3f || fabsf(aA - 4.71238898f) < 1e-3f) unc = true;
+                else if (aA > 3.14159265f && aA < 4.71238898f) {  // the reference keeps a in (pi,3pi/2] un-wrapped
+                    if (fabsf(aA - tauF) < 1e-3f) unc = true; else pass = aA < tauF;
+                } else if (tauGtPi) pass = true;
+                else { pass = diff > 0; unc = !cosCertain; }
+            }
+            if (!g.nrmOK) unc = true;
+        }
+        if (__any_sync(FULL, unc)) {
+            if (!haveExact) { regExact = d_atan2(g.sinDeg, g.cosDeg); haveExact = true; }
+            if (unc) {  // the literal test, :540-543
+                double degDif = fabs(regExact - dg);
+                if (degDif > pi32) degDif = fabs(degDif - pi2);
+                pass = degDif < degThre;
+            }
+        }
+        const unsigned int b = __ballot_sync(FULL, pass);
+        if (!b) break;
+        const int f = __ffs(b) - 1;
+        const int fn = __shfl_sync(FULL, n, f), fm = __shfl_sync(FULL, m, f);
+        g.cosDeg += __shfl_sync(FULL, cd, f);  // :545-546
+        g.sinDeg += __shfl_sync(FULL, sd, f);
+        sums_refresh(g, c2, cTau, tauSmall);
+        haveExact = false;
+        if (num >= c.listCap - 1) return -1;
+        if (c.lane == f) {
+            atomicOr(&c.state[p], c.mybit);
+            c.list[num] = pack_xy(n, m);
+        }
+        if (cand && n == fn && m == fm) cand = false;   // the accepted pixel itself, and the same pixel seen from another point
+        num++;
+        start = f + 1;
+    }
+    return 0;
+}
+
+__device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double degThre, BBox& bb) {
+    const int W = c.W, H = c.H;
+    const double pi = c.kc->pi;
     TIC;
     const size_t sp = (size_t)sy * W + sx;
     const double regDeg0 = regDeg;
-    double sinDeg = c.sinm[sp], cosDeg = c.cosm[sp];  // sin(regDeg), cos(regDeg)  (:515-516)
+    GrowSums g;
+    g.sinDeg = c.sinm[sp]; g.cosDeg = c.cosm[sp];  // sin(regDeg), cos(regDeg)  (:515-516)
     const bool tauSmall = degThre <= pi / 2.0;
     const bool tauGtPi = degThre > pi;
     const double cTau = degThre == c.kc->degThre ? c.kc->cosDegThre : (tauGtPi ? -1.0 : d_cos(degThre));
+    const double c2 = cTau * cTau;
     const float tauF = (float)degThre;
     if (c.lane == 0) {
         c.list[0] = pack_xy(sx, sy);
         atomicOr(&c.state[sp], c.mybit);
     }
     __syncwarp();
-    bbox_add(c, bb, sx, sy);
-    int num = 1, exNum = 0;
-    // uniform quantities derived from the running sums
-    double nrm = sqrt(cosDeg * cosDeg + sinDeg * sinDeg);
-    double thr = cTau * nrm, margin = 1e-13 * nrm;
-    float regA = tauSmall ? 0.f : atan2f((float)sinDeg, (float)cosDeg);
-    bool nrmOK = nrm > 1e-9;
+    int num = 1;
+    sums_refresh(g, c2, cTau, tauSmall);
     bool haveExact = true;
     double regExact = regDeg0;
-    while (exNum != num) {
-        exNum = num;
-        int cur = 0;
-        while (cur < 9 * num) {
-            const int lim = 9 * num;
-            const int myc = cur + c.lane;
-            const bool valid = myc < lim;
-            const int pt = myc / 9, nb = myc - pt * 9;
-            const unsigned int pv = valid ? c.list[pt] : 0u;
-            const int m = py_of(pv) + nb / 3 - 1, n = px_of(pv) + (nb - (nb / 3) * 3) - 1;
-            const bool inb = valid && m >= 0 && n >= 0 && m < H && n < W;
-            const size_t p = inb ? (size_t)m * W + n : 0;
-            const unsigned int st = inb ? lsdb_ld_state(&c.state[p]) : LSDB_ST_BAN;
+    const unsigned int lt = (1u << c.lane) - 1u;
+    int startNum = 0, nPrev = 0, cur = 0;   // cur = which reject buffer is being filled
+    bool literal = false;                   // reject list overflowed: literal full re-scans from now on
+    while (true) {
+        const int numAtStart = num;
+        unsigned int* rPrev = c.rej[cur ^ 1];
+        unsigned int* rNext = c.rej[cur];
+        int nNext = 0;
+        // (i) the candidates that failed the angle test in the previous pass, in scan order, then
+        // (ii) the points that have not been scanned yet (all of them while `literal`)
+        int base = 0;
+        int pos = 9 * (literal ? 0 : startNum);
+        while (true) {
+            const bool rescan = base < nPrev;
+            const int lim = 9 * num;   // candidates of the points listed so far; accepts of this batch extend it for the next
+            if (!rescan && pos >= lim) break;
+            int n, m;
+            bool cand;
+            unsigned int banMask;
+            if (rescan) {
+                const int e = base + c.lane;
+                cand = e < nPrev;
+                const unsigned int pv = cand ? rPrev[e] : 0u;
+                n = px_of(pv); m = py_of(pv);
+                banMask = c.mybit;               // may have joined the region meanwhile
+            } else {
+                const int myc = pos + c.lane;
+                const bool valid = myc < lim;
+                const int pt = myc / 9, nb = myc - pt * 9;
+                const unsigned int pv = valid ? c.list[pt] : 0u;
+                const int r3 = nb / 3;
+                m = py_of(pv) + r3 - 1; n = px_of(pv) + (nb - r3 * 3) - 1;
+                // banned? — from the shared-memory bit plane; only un-banned candidates touch global memory
+                cand = valid && m >= 0 && n >= 0 && m < H && n < W && !(c.bm && ban_at(c, n, m));
+                banMask = LSDB_ST_BAN | c.mybit;
+            }
+            const size_t p = cand ? (size_t)m * W + n : 0;
+            const unsigned int st = cand ? lsdb_ld_state(&c.state[p]) : 0u;
             double dg = 0.0, cd = 0.0, sd = 0.0;
-            if (inb) { dg = c.deg[p]; cd = c.cosm[p]; sd = c.sinm[p]; }  // issued with the state load, not after it
-            bool cand = inb && !(st & (LSDB_ST_BAN | c.mybit));
-            int start = 0;
-            while (true) {
-                const bool active = cand && c.lane >= start;
-                bool pass = false, unc = false;
-                if (active) {
-                    const double diff = (cosDeg * cd + sinDeg * sd) - thr;
-                    const bool cosCertain = fabs(diff) > margin;
-                    if (tauSmall) {
-                        pass = diff > 0; unc = !cosCertain;
-                    } else {
-                        const float aA = fabsf(regA - (float)dg);
-                        if (fabsf(aA - 3.14159265f) < 1e-3f || fabsf(aA - 4.71238898f) < 1e-3f) unc = true;
-                        else if (aA > 3.14159265f && aA < 4.71238898f) {  // the reference keeps a in (pi,3pi/2] un-wrapped
-                            if (fabsf(aA - tauF) < 1e-3f) unc = true; else pass = aA < tauF;
-                        } else if (tauGtPi) pass = true;
-                        else { pass = diff > 0; unc = !cosCertain; }
-                    }
-                    if (!nrmOK) unc = true;
+            if (cand) { dg = c.deg[p]; cd = c.cosm[p]; sd = c.sinm[p]; }  // issued with the state load, not after it
+            cand = cand && !(st & banMask);
+            if (accept_lanes(c, g, cand, p, n, m, dg, cd, sd, num, haveExact, regExact, degThre, c2, cTau, tauSmall, tauGtPi, tauF) < 0) return -1;
+            if (!literal) {
+                const unsigned int rb = __ballot_sync(FULL, cand);
+                if (rb) {
+                    if (nNext + 32 > c.rejCap) literal = true;
+                    else { if (cand) rNext[nNext + __popc(rb & lt)] = pack_xy(n, m); nNext += __popc(rb); }
                 }
-                if (__any_sync(FULL, unc)) {
-                    if (!haveExact) { regExact = d_atan2(sinDeg, cosDeg); haveExact = true; }
-                    if (unc) {  // the literal test, :540-543
-                        double degDif = fabs(regExact - dg);
-                        if (degDif > pi32) degDif = fabs(degDif - pi2);
-                        pass = degDif < degThre;
-                    }
-                }
-                const unsigned int b = __ballot_sync(FULL, pass);
-                if (!b) break;
-                const int f = __ffs(b) - 1;
-                const int fn = __shfl_sync(FULL, n, f), fm = __shfl_sync(FULL, m, f);
-                cosDeg += __shfl_sync(FULL, cd, f);  // :545-546
-                sinDeg += __shfl_sync(FULL, sd, f);
-                nrm = sqrt(cosDeg * cosDeg + sinDeg * sinDeg);
-                thr = cTau * nrm; margin = 1e-13 * nrm; nrmOK = nrm > 1e-9;
-                if (!tauSmall) regA = atan2f((float)sinDeg, (float)cosDeg);
-                haveExact = false;
-                if (num >= c.listCap - 1) return -1;
-                if (c.lane == f) {
-                    atomicOr(&c.state[p], c.mybit);
-                    c.list[num] = pack_xy(n, m);
-                }
-                if (inb && n == fn && m == fm) cand = false;
-                bbox_add(c, bb, fn, fm);
-                num++;
-                start = f + 1;
             }
             __syncwarp();
-            cur = min(cur + 32, lim);
+            if (rescan) base += 32; else pos = min(pos + 32, lim);
         }
+        if (num == numAtStart) break;   // a pass that added nothing (:525)
+        startNum = num;
+        nPrev = literal ? 0 : nNext;
+        cur ^= 1;
     }
-    if (num > 1) regDeg = haveExact ? regExact : d_atan2(sinDeg, cosDeg);  // :547 after the last accept
+    if (num > 1) regDeg = haveExact ? regExact : d_atan2(g.sinDeg, g.cosDeg);  // :547 after the last accept
+    for (int k = c.lane; k < num; k += 32) {   // bounding box / coarse cells of the accepted pixels
+        const unsigned int v = c.list[k];
+        bbox_add(c, bb, px_of(v), py_of(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bb.x0 = min(bb.x0, __shfl_xor_sync(FULL, bb.x0, o)); bb.y0 = min(bb.y0, __shfl_xor_sync(FULL, bb.y0, o));
+        bb.x1 = max(bb.x1, __shfl_xor_sync(FULL, bb.x1, o)); bb.y1 = max(bb.y1, __shfl_xor_sync(FULL, bb.y1, o));
+        bb.mask |= __shfl_xor_sync(FULL, bb.mask, o);
+    }
     STAT(c, ST_GROWS, 1); STAT(c, ST_GROWNPX, num);
     TOC(c, TM_GROW);
     return num;
 }
 
+// ------------------------------------------------------------------ RegionGrower, one LANE per seed
+// ~97 % of the live seeds grow a region below regThre pixels, which the reference then drops without touching
+// any state (:228-231).  Those are decided here with one seed per lane: each lane replays RegionGrower for its
+// own seed, literally (same scan order, same running sums, same re-scan passes), in a private list of at most
+// T-1 points, and stops as soon as the region reaches T = ceil(regThre) points ("large": the warp-cooperative
+// path then grows it in full).  Later passes only re-test the neighbours that failed the ANGLE test before:
+// out-of-image, banned and own pixels stay so (bans only grow; a pixel that gets banned meanwhile invalidates
+// the evaluation at retire time anyway).
+// Returns the region size (T when large).  lst[] holds the accepted pixels (packed y<<16|x).
+__device__ __noinline__ int small_grow(const WarpCtx& c, int p0, int T, unsigned int* lst) {
+    const int W = c.W;
+    const double pi = c.kc->pi, pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
+    const double degThre = c.kc->degThre, cTau = c.kc->cosDegThre;
+    unsigned short rej[SG_CAP];
+    const int sx = p0 % W, sy = p0 / W;
+    const double c2 = cTau * cTau;
+    double cosS = c.cosm[p0], sinS = c.sinm[p0];
+    double n2 = cosS * cosS + sinS * sinS, c2n2 = c2 * n2, m2 = 4e-13 * n2;   // see grow_region: the test on the squares
+    bool nrmOK = n2 > 1e-18;
+    lst[0] = pack_xy(sx, sy);
+    rej[0] = 0;
+    int num = 1, exNum = 0, startNum = 0;
+    while (exNum != num) {
+        exNum = num;
+        for (int i = 0; i < num; i++) {
+            const unsigned int v = lst[i];
+            const int x = px_of(v), y = py_of(v);
+            unsigned int cm = i >= startNum ? (~ban9(c, x, y)) & 0x1efu : (unsigned int)rej[i];
+            unsigned int nr = 0;
+            while (cm) {
+                const int nb = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const int r3 = nb / 3;
+                const int m = y + r3 - 1, n = x + (nb - r3 * 3) - 1;
+                const unsigned int pk = pack_xy(n, m);
+                bool own = false;
+                for (int k = 0; k < num; k++) own |= lst[k] == pk;
+                if (own) continue;
+                const size_t p = (size_t)m * W + n;
+                const double cd = c.cosm[p], sd = c.sinm[p];
+                const double dot = cosS * cd + sinS * sd;
+                const double d2 = dot * dot - c2n2;
+                bool pass = dot > 0 && d2 > 0;
+                if ((dot > 0 && !(fabs(d2) > m2)) || !nrmOK) {  // knife edge: the literal test of :540-543
+                    const double regDeg = num == 1 ? c.deg[p0] : d_atan2(sinS, cosS);
+                    double degDif = fabs(regDeg - c.deg[p]);
+                    if (degDif > pi32) degDif = fabs(degDif - pi2);
+                    pass = degDif < degThre;
+                }
+                if (pass) {
+                    lst[num] = pk;
+                    rej[num] = 0;
+                    num++;
+                    cosS += cd;  // :545-546
+                    sinS += sd;
+                    if (num >= T) return num;
+                    n2 = cosS * cosS + sinS * sinS;
+                    c2n2 = c2 * n2; m2 = 4e-13 * n2; nrmOK = n2 > 1e-18;
+                } else {
+                    nr |= 1u << nb;
+                }
+            }
+            rej[i] = (unsigned short)nr;
+        }
+        startNum = num;
+    }
+    return num;
+}
+
 // ------------------------------------------------------------------ RectangleConverter (:592-734)
-__device__ Rect rect_from_region(const WarpCtx& c, const unsigned int* lst, int num, double regDeg, double aliPro,
+__device__ __noinline__ Rect rect_from_region(const WarpCtx& c, const unsigned int* lst, int num, double regDeg, double aliPro,
                                  double degThre) {
     const int W = c.W;
     const double pi = c.kc->pi;
     TIC;
-    // Sums are accumulated in list order like the reference (:608-613, :637-643): lanes form the addends of 32
-    // points in parallel (same operations on the same inputs, so the same bits), the adds run serially.
-    double cenX = 0, cenY = 0, weiSum = 0;
-    for (int base = 0; base < num; base += 32) {  // CenterGetter :608-613
+    // Sums are accumulated in list order like the reference (:608-613, :637-643).  The lanes form the addends of 32
+    // points in parallel (same operations on the same inputs, so the same bits) and stage them in shared memory;
+    // lanes 0..3 then each run ONE of the sums serially over the staged values, in list order.
+    double* stg = c.stage;
+    double acc = 0.0;
+    for (int base = 0; base < num; base += 32) {  // CenterGetter :608-613: lane 0 cenX, lane 1 cenY, lane 2 weiSum
         const int k = base + c.lane;
         const unsigned int v = k < num ? lst[k] : 0u;
         const double wv = k < num ? c.mag[(size_t)py_of(v) * W + px_of(v)] : 0.0;
-        const double tx = wv * px_of(v), ty = wv * py_of(v);
+        stg[c.lane * 4 + 0] = wv * px_of(v);
+        stg[c.lane * 4 + 1] = wv * py_of(v);
+        stg[c.lane * 4 + 2] = wv;
+        __syncwarp();
         const int cnt = min(32, num - base);
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const double wj = __shfl_sync(FULL, wv, j), xj = __shfl_sync(FULL, tx, j), yj = __shfl_sync(FULL, ty, j);
-            if (j < cnt) { cenX += xj; cenY += yj; weiSum += wj; }
-        }
+        if (c.lane < 3)
+            for (int j = 0; j < cnt; j++) acc += stg[j * 4 + c.lane];
+        __syncwarp();
     }
+    double cenX = __shfl_sync(FULL, acc, 0), cenY = __shfl_sync(FULL, acc, 1), weiSum = __shfl_sync(FULL, acc, 2);
     cenX = cenX / weiSum;
     cenY = cenY / weiSum;
-    double Ixx = 0, Iyy = 0, Ixy = 0;
-    weiSum = 0;
-    for (int base = 0; base < num; base += 32) {  // OrientationGetter :637-643
+    acc = 0.0;
+    for (int base = 0; base < num; base += 32) {  // OrientationGetter :637-643: lane 0 Ixx, 1 Iyy, 2 Ixy, 3 weiSum
         const int k = base + c.lane;
         const unsigned int v = k < num ? lst[k] : 0u;
         const double wv = k < num ? c.mag[(size_t)py_of(v) * W + px_of(v)] : 0.0;
         const double ey = py_of(v) - cenY, ex = px_of(v) - cenX;
-        const double t1 = wv * (ey * ey), t2 = wv * (ex * ex), t3 = wv * ex * ey;
+        stg[c.lane * 4 + 0] = wv * (ey * ey);
+        stg[c.lane * 4 + 1] = wv * (ex * ex);
+        stg[c.lane * 4 + 2] = -(wv * ex * ey);   // Ixy -= t  ==  Ixy += -t
+        stg[c.lane * 4 + 3] = wv;
+        __syncwarp();
         const int cnt = min(32, num - base);
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const double wj = __shfl_sync(FULL, wv, j), a1 = __shfl_sync(FULL, t1, j), a2 = __shfl_sync(FULL, t2, j),
-                         a3 = __shfl_sync(FULL, t3, j);
-            if (j < cnt) { Ixx += a1; Iyy += a2; Ixy -= a3; weiSum += wj; }
-        }
+        if (c.lane < 4)
+            for (int j = 0; j < cnt; j++) acc += stg[j * 4 + c.lane];
+        __syncwarp();
     }
+    double Ixx = __shfl_sync(FULL, acc, 0), Iyy = __shfl_sync(FULL, acc, 1), Ixy = __shfl_sync(FULL, acc, 2);
+    weiSum = __shfl_sync(FULL, acc, 3);
     Ixx /= weiSum; Iyy /= weiSum; Ixy /= weiSum;
     const double dI = Ixx - Iyy;
     const double lamb = (Ixx + Iyy - sqrt(dI * dI + 4 * Ixy * Ixy)) / 2.0;
@@ -362,7 +571,7 @@ __global__ void lsdb_lgamma_table_kernel(double* tab, int n) {
 }
 
 // ------------------------------------------------------------------ RectangleNFACalculator (:926-1059)
-__device__ double rect_nfa_impl(WarpCtx& c, const Rect& rec, double logNT) {
+__device__ __noinline__ double rect_nfa_impl(WarpCtx& c, const Rect& rec, double logNT) {
     const int xLim = c.W, yLim = c.H;
     const double pi = c.kc->pi;
     const double pi32 = pi * 3 / 2.0, pi2 = 2 * pi;
@@ -697,7 +906,7 @@ __device__ bool any_banned(const WarpCtx& c, const unsigned int* px, int n) {
     bool hit = false;
     for (int k = c.lane; k < n; k += 32) {
         const unsigned int v = px[k];
-        if (lsdb_ld_state(&c.state[(size_t)py_of(v) * c.W + px_of(v)]) & LSDB_ST_BAN) hit = true;
+        if (ban_at(c, px_of(v), py_of(v))) hit = true;
     }
     return __any_sync(FULL, hit);
 }
@@ -739,6 +948,7 @@ __device__ void commit_region(WarpCtx& c, const unsigned int* recp, int* labels,
         const unsigned int v = px[k];
         const size_t p = (size_t)py_of(v) * W + px_of(v);
         atomicOr(&c.state[p], LSDB_ST_BAN);
+        ban_set(c, px_of(v), py_of(v));
         labels[p] += idx + 1;  // regIdx += curMap*(regCnt+1), :261 (int32 here, u8 there)
         x0 = min(x0, px_of(v)); y0 = min(y0, py_of(v)); x1 = max(x1, px_of(v)); y1 = max(y1, py_of(v));
         mask |= cell_bit(px_of(v), py_of(v), c.cellShift);
@@ -778,60 +988,139 @@ __device__ void commit_region(WarpCtx& c, const unsigned int* recp, int* labels,
 }
 
 // per-seed record of a parked evaluation (one per lane of a chunk), SoA in global memory: [RING][32]
+//   oc      outcome (OC_NONE: not evaluated — decided at the frontier)
+//   L0      length of the accept log when the evaluation started
+//   b0,b1,mask  bounding box / coarse-grid cells of the pixels the evaluation accepted
+//   off     arena offset of the result header (OC_ACCEPT / OC_REJECT)
+//   chkOff,chk  arena offset and length of the accepted-pixel list to re-validate (chk < 0: none kept)
 struct ChunkRecs {
-    int* oc; int* L0; unsigned int* b0; unsigned int* b1; unsigned long long* mask; unsigned int* off; int* chk;
+    int* oc; int* L0; unsigned int* b0; unsigned int* b1; unsigned long long* mask; unsigned int* off; int* chk; unsigned int* chkOff;
 };
+#define REC_BYTES_PER_CELL 40
 
-// speculative evaluation of every live seed of `chunk`; parks the results and flags the chunk READY
-__device__ void speculate_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int nCells, const ChunkRecs& R, unsigned int& head) {
+// contiguous room for `need` words in this warp's arena ring; returns the physical offset or -1 (h2 = new virtual head base)
+__device__ __forceinline__ int arena_room(const WarpCtx& c, unsigned int head, unsigned int need, unsigned int& h2, int& avail) {
+    const unsigned int cap = (unsigned int)c.arenaCap;
+    const unsigned int tail = c.sh->arenaTail[c.w];
+    unsigned int phys = head % cap;
+    unsigned int room = cap - phys;                   // contiguous words at phys
+    h2 = head;
+    if (room < need && cap - (head + room - tail) >= need) { h2 = head + room; phys = 0; room = cap; }
+    const unsigned int freeW = cap - (h2 - tail);     // words not holding parked records
+    avail = (int)min(room, freeW);
+    return avail >= (int)need ? (int)phys : -1;
+}
+
+// Speculative evaluation of the live seeds of `nSub` consecutive chunks (up to 256 cells); parks the results and flags
+// the chunks READY.  Three phases:
+//   A  collect the live cells (seed order) into a queue;
+//   B  one seed per LANE: small_grow decides the ~97 % of seeds whose region stays below regThre ("no change"; the
+//      accepted pixels are parked for re-validation) and flags the rest as large;
+//   C  the large seeds, in order, one at a time with the whole warp (grow, rectangle, refine, NFA).
+__device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned int* cl, int nCells, const ChunkRecs& R, unsigned int& head, int T) {
     GrowShared& sh = *c.sh;
     const int lane = c.lane;
-    const int slot = chunk & (RING - 1);
-    const int ci = chunk * LSDB_CHUNK + lane;
-    const int myp = ci < nCells ? (int)cl[ci] : -1;
-    const bool live = myp >= 0 && (lsdb_ld_state(&c.state[myp]) & 3u) == 0;
-    unsigned int rem = __ballot_sync(FULL, live);
-    int recOc = OC_NONE, recL0 = 0, recChk = -1;
-    unsigned int recB0 = 0, recB1 = 0, recOff = 0;
-    unsigned long long recMask = 0ull;
-    BBox bb; int used = 0, chk = -1;
-    const unsigned int cap = (unsigned int)c.arenaCap;
+    const unsigned int lt = (1u << lane) - 1u;
     long long tSpec = clock64();
-    while (rem && !sh.abortFlag) {
-        const int k = __ffs(rem) - 1;
-        rem &= rem - 1;
-        const int p = __shfl_sync(FULL, myp, k);
-        if (lsdb_ld_state(&c.state[p]) & (3u | LSDB_ST_HINT)) continue;   // used, or inside a parked region: leave to the frontier
-        // contiguous room in the ring: skip the tail of the buffer if the record could straddle it
-        const unsigned int tail = sh.arenaTail[c.w];
-        unsigned int phys = head % cap;
-        unsigned int room = cap - phys;                   // contiguous words at phys
-        unsigned int h2 = head;
-        if (room < 4096u && cap - (head + room - tail) >= 4096u) { h2 = head + room; phys = 0; room = cap; }
-        const unsigned int freeW = cap - (h2 - tail);     // words not holding parked records
-        const int avail = (int)min(room, freeW);
-        if (avail < ARENA_HDR + 64) continue;             // arena full: this seed is decided at the frontier
+    const unsigned int head0 = head;
+    unsigned int* q = c.scratch;   // [2k] pixel index, [2k+1] (sub << 5 | lane) | large flag
+    int qn = 0;
+    for (int s = 0; s < nSub; s++) {   // ---- A
+        const int ci = (chunk0 + s) * LSDB_CHUNK + lane;
+        const int p = ci < nCells ? (int)cl[ci] : -1;
+        // used (:222), or inside a parked accept/reject candidate: leave those to the frontier
+        const bool live = p >= 0 && (lsdb_ld_state(&c.state[p]) & (3u | LSDB_ST_HINT)) == 0;
+        const unsigned int bal = __ballot_sync(FULL, live);
+        if (live) {
+            const int k = qn + __popc(bal & lt);
+            q[2 * k] = (unsigned int)p;
+            q[2 * k + 1] = (unsigned int)((s << 5) | lane);
+        }
+        qn += __popc(bal);
+        R.oc[(size_t)((chunk0 + s) & (RING - 1)) * 32 + lane] = OC_NONE;
+    }
+    __syncwarp();
+    for (int base = 0; base < qn && !sh.abortFlag; base += 32) {   // ---- B
+        const int k = base + lane;
+        const bool act = k < qn;
+        unsigned int lst[SG_CAP];
+        int num = 0;
+        bool large = act;
+        const int L0 = sh.logCount;
+        __threadfence_block();
+        if (act && T <= SG_CAP) {
+            num = small_grow(c, (int)q[2 * k], T, lst);
+            large = num >= T;
+        }
+        __syncwarp();
+        const bool small = act && !large;
+        // park the accepted pixels of the small regions (re-validated at retire time if a region was accepted nearby)
+        const int need = small ? num : 0;
+        int incl = need;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int tot = __shfl_sync(FULL, incl, 31);
+        unsigned int h2; int avail;
+        const int phys = tot > 0 ? arena_room(c, head, (unsigned int)tot + 2u, h2, avail) : -1;
+        if (small) {
+            const unsigned int rel = q[2 * k + 1];
+            const size_t ri = (size_t)((chunk0 + (int)(rel >> 5)) & (RING - 1)) * 32 + (rel & 31u);
+            if (phys >= 0) {
+                BBox bb; bb.x0 = bb.y0 = 0x7fffffff; bb.x1 = bb.y1 = -1; bb.mask = 0ull;
+                unsigned int* dst = c.arena + phys + (incl - need);
+                for (int j = 0; j < num; j++) { dst[j] = lst[j]; bbox_add(c, bb, px_of(lst[j]), py_of(lst[j])); }
+                R.L0[ri] = L0; R.b0[ri] = pack_xy(bb.x0, bb.y0); R.b1[ri] = pack_xy(bb.x1, bb.y1); R.mask[ri] = bb.mask;
+                R.off[ri] = 0; R.chk[ri] = num; R.chkOff[ri] = (unsigned int)(phys + (incl - need));
+                R.oc[ri] = OC_NOCHANGE;
+            }   // else: arena full — this seed is decided at the frontier
+        } else if (act) {
+            q[2 * k + 1] |= 0x80000000u;
+        }
+        if (phys >= 0) head = h2 + (unsigned int)((tot + 1) & ~1);
+        const unsigned int nSmall = __popc(__ballot_sync(FULL, small));
+        int pxs = small ? num : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pxs += __shfl_xor_sync(FULL, pxs, o);
+        if (lane == 0) {
+            atomicAdd(&sh.stats[ST_SPEC], (unsigned long long)nSmall); atomicAdd(&sh.stats[ST_GROWS], (unsigned long long)nSmall);
+            atomicAdd(&sh.stats[ST_SMALL], (unsigned long long)nSmall); atomicAdd(&sh.stats[ST_GROWNPX], (unsigned long long)pxs);
+        }
+    }
+    __syncwarp();
+    BBox bb; int used = 0, chk = -1;
+    for (int k = 0; k < qn && !sh.abortFlag; k++) {   // ---- C
+        const unsigned int rel = q[2 * k + 1];
+        if (!(rel & 0x80000000u)) continue;
+        const int p = (int)q[2 * k];
+        if (lsdb_ld_state(&c.state[p]) & (3u | LSDB_ST_HINT)) continue;   // swallowed by a region parked a moment ago
+        unsigned int h2; int avail;
+        const int phys = arena_room(c, head, 4096u, h2, avail);
+        if (phys < 0) continue;                             // arena full: this seed is decided at the frontier
         const int L0 = sh.logCount;
         __threadfence_block();
         const int oc = eval_seed(c, p, c.arena + phys, avail, true, bb, used, chk);
         STAT(c, ST_SPEC, 1);
         if (oc == OC_DEFER) continue;
-        if (lane == k) {
-            recOc = oc; recL0 = L0; recB0 = pack_xy(bb.x0, bb.y0); recB1 = pack_xy(bb.x1, bb.y1); recMask = bb.mask;
-            recOff = phys; recChk = chk;
+        if (lane == 0) {
+            const size_t ri = (size_t)((chunk0 + (int)((rel & 0x7fffffffu) >> 5)) & (RING - 1)) * 32 + (rel & 31u);
+            R.L0[ri] = L0; R.b0[ri] = pack_xy(bb.x0, bb.y0); R.b1[ri] = pack_xy(bb.x1, bb.y1); R.mask[ri] = bb.mask;
+            R.off[ri] = (unsigned int)phys; R.chk[ri] = chk; R.chkOff[ri] = (unsigned int)phys + ARENA_HDR;
+            R.oc[ri] = oc;
         }
         head = h2 + (unsigned int)used;
     }
-    const size_t ri = (size_t)slot * 32 + lane;
-    R.oc[ri] = recOc; R.L0[ri] = recL0; R.b0[ri] = recB0; R.b1[ri] = recB1; R.mask[ri] = recMask; R.off[ri] = recOff; R.chk[ri] = recChk;
-    if (lane == 0) {
+    if (lane < nSub) {
+        const int slot = (chunk0 + lane) & (RING - 1);
         sh.chunkWarp[slot] = (unsigned char)c.w;
-        sh.chunkEnd[slot] = head;
-        atomicAdd(&sh.stats[TM_SPEC], (unsigned long long)(clock64() - tSpec));
+        sh.chunkEnd[slot] = lane == nSub - 1 ? head : head0;   // the arena space is released when the last chunk retires
     }
-    __threadfence();   // records + arena contents visible before the flag
+    if (lane == 0) atomicAdd(&sh.stats[TM_SPEC], (unsigned long long)(clock64() - tSpec));
+    __threadfence();   // records + arena contents visible before the flags
     __syncwarp();
-    if (lane == 0) sh.chunkFlag[slot] = 1;
+    if (lane < nSub) sh.chunkFlag[(chunk0 + lane) & (RING - 1)] = 1;
 }
 
 // does log entry e overlap the accepted-pixel bbox/mask of a parked evaluation?
@@ -854,7 +1143,7 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
     const int myp = ci < nCells ? (int)cl[ci] : -1;
     const size_t ri = (size_t)slot * 32 + lane;
     const int recOc = R.oc[ri], recL0 = R.L0[ri], recChk = R.chk[ri];
-    const unsigned int recB0 = R.b0[ri], recB1 = R.b1[ri], recOff = R.off[ri];
+    const unsigned int recB0 = R.b0[ri], recB1 = R.b1[ri], recOff = R.off[ri], recChkOff = R.chkOff[ri];
     const unsigned long long recMask = R.mask[ri];
     const int ew = sh.chunkWarp[slot];
     const unsigned int* earena = c.listsBase + (size_t)ew * c.warpStride + c.listCap + (2 * (size_t)c.listCap + 64);
@@ -877,7 +1166,7 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
         bool valid = oc != OC_NONE;
         if (valid && __shfl_sync(FULL, (int)hit, k)) {   // coarse filter hit: look at the accepted pixels themselves
             const int nchk = __shfl_sync(FULL, recChk, k);
-            valid = nchk >= 0 && !any_banned(c, recp + ARENA_HDR, nchk);
+            valid = nchk >= 0 && !any_banned(c, earena + __shfl_sync(FULL, recChkOff, k), nchk);
         }
         bool changed = false;
         if (valid) {
@@ -953,25 +1242,31 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
                                                                    const unsigned int* __restrict__ cells, int* __restrict__ labels,
                                                                    LsdbRect* __restrict__ rects, int maxSeg, unsigned int* __restrict__ lists,
                                                                    int listCap, int arenaCap, int runAhead, unsigned char* __restrict__ recBuf,
-                                                                   const double* __restrict__ lgammaTab, int lgammaN, int* __restrict__ imgCounter) {
+                                                                   const double* __restrict__ lgammaTab, int lgammaN, int* __restrict__ imgCounter,
+                                                                   const unsigned int* __restrict__ banBits, int bmCapWords) {
     __shared__ GrowShared sh;
+    extern __shared__ unsigned int bmShared[];   // the map's ban plane, one bit per pixel (bmCapWords words)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
     WarpCtx c;
     c.lane = lane; c.w = w; c.mybit = 1u << (LSDB_ST_WARP_SHIFT + w);
     c.kc = kc; c.lgammaTab = lgammaTab; c.lgammaN = lgammaN; c.sh = &sh;
     c.listCap = listCap; c.arenaCap = arenaCap;
-    c.warpStride = 3 * (size_t)listCap + 64 + (size_t)arenaCap;
+    c.rejCap = LSDB_REJ_CAP;
+    c.warpStride = grow_words_per_warp(listCap, arenaCap);
     c.listsBase = lists + (size_t)blockIdx.x * nw * c.warpStride;
     c.list = c.listsBase + (size_t)w * c.warpStride;
     c.scratch = c.list + listCap;
     c.arena = c.scratch + 2 * (size_t)listCap + 64;
+    c.rej[0] = c.arena + arenaCap;
+    c.rej[1] = c.rej[0] + LSDB_REJ_CAP;
+    c.stage = reinterpret_cast<double*>(bmShared + ((bmCapWords + 1) & ~1)) + (size_t)w * 128;
     ChunkRecs R;
     {
-        unsigned char* base = recBuf + (size_t)blockIdx.x * (RING * 32 * 32);
+        unsigned char* base = recBuf + (size_t)blockIdx.x * (RING * 32 * REC_BYTES_PER_CELL);
         R.mask = reinterpret_cast<unsigned long long*>(base);
         R.oc = reinterpret_cast<int*>(base + RING * 32 * 8);
         R.L0 = R.oc + RING * 32; R.b0 = reinterpret_cast<unsigned int*>(R.L0 + RING * 32); R.b1 = R.b0 + RING * 32;
-        R.off = R.b1 + RING * 32; R.chk = reinterpret_cast<int*>(R.off + RING * 32);
+        R.off = R.b1 + RING * 32; R.chk = reinterpret_cast<int*>(R.off + RING * 32); R.chkOff = reinterpret_cast<unsigned int*>(R.chk + RING * 32);
     }
 
     while (true) {
@@ -991,6 +1286,8 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
         __syncthreads();
         const int img = sh.img;
         if (img >= nImgs) break;
+        long long mapC0 = 0; unsigned long long mapT0 = 0;
+        if (tid == 0) { mapC0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(mapT0)); }
         const LsdbImg im = imgs[img];
         c.W = im.W; c.H = im.H; c.logNT = im.logNT; c.regThre = im.regThre;
         {
@@ -999,6 +1296,19 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
             c.cellShift = k;
         }
         c.state = state + im.nOff; c.deg = deg + im.nOff; c.mag = mag + im.nOff; c.cosm = cosm + im.nOff; c.sinm = sinm + im.nOff;
+        c.pw = im.pw;
+        {   // the ban plane written by the stencil stage moves into shared memory when it fits
+            const int words = im.H * im.pw;
+            if (words <= bmCapWords) {
+                const unsigned int* srcB = banBits + im.banOff;
+                for (int i = tid; i < words; i += blockDim.x) bmShared[i] = srcB[i];
+                c.bm = bmShared;
+            } else {
+                c.bm = 0;
+            }
+        }
+        const int T = (int)ceil(im.regThre);   // regions below regThre pixels are dropped (:228)
+        __syncthreads();
         int* lab = labels + im.nOff;
         const unsigned int* cl = cells + im.nOff;
         LsdbRect* rc = rects + im.segOff;
@@ -1013,7 +1323,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
             if (lane == 0) {
                 // claim a ticket only while the ring has room
                 if (sh.nextChunk < nChunks && sh.nextChunk - sh.frontier < runAhead) {
-                    chunk = atomicAdd(&sh.nextChunk, 1);
+                    chunk = atomicAdd(&sh.nextChunk, LSDB_SUPER);
                     if (chunk >= nChunks) chunk = -1;
                 }
             }
@@ -1029,13 +1339,15 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
                 continue;
             }
             idle = 0;
-            speculate_chunk(c, chunk, cl, nCells, R, head);
+            speculate_super(c, chunk, min(LSDB_SUPER, nChunks - chunk), cl, nCells, R, head, T);
         }
         __syncthreads();
         if (tid == 0) {
             dyn[img].nSeg = sh.nSeg;
             if (sh.abortFlag) dyn[img].err = sh.abortFlag;
             sh.stats[ST_CELLS] = nCells;
+            unsigned long long mapT1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(mapT1));
+            sh.stats[TM_MAPCYC] = (unsigned long long)(clock64() - mapC0); sh.stats[TM_MAPNS] = mapT1 - mapT0;
         }
         __syncthreads();
         if (tid < TM_N) dyn[img].stat[tid] = (long long)sh.stats[tid];
@@ -1054,16 +1366,23 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
                       unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
-                      int* imgCounter) {
-    if (runAhead > RING - NW_MAX) runAhead = RING - NW_MAX;
+                      int* imgCounter, const unsigned int* banBits, int bmCapWords) {
+    if (runAhead > RING - (NW_MAX + 1) * LSDB_SUPER) runAhead = RING - (NW_MAX + 1) * LSDB_SUPER;
     if (runAhead < 1) runAhead = 1;
+    static int attrSet = -1;
+    if (attrSet < bmCapWords) {
+        cudaFuncSetAttribute(lsdb_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
+        attrSet = bmCapWords;
+    }
     if (nImgs > 0)
-        lsdb_grow_kernel<<<nCtas, warpsPerCta * 32, 0, s>>>(nImgs, imgs, dyn, kc, mag, deg, cosm, sinm, state, cells, labels, rects, maxSeg,
-                                                            lists, listCap, arenaCap, runAhead, recBuf, lgammaTab, lgammaN, imgCounter);
+        lsdb_grow_kernel<<<nCtas, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta), s>>>(nImgs, imgs, dyn, kc, mag, deg, cosm, sinm, state, cells, labels, rects,
+                                                                                maxSeg, lists, listCap, arenaCap, runAhead, recBuf, lgammaTab, lgammaN,
+                                                                                imgCounter, banBits, bmCapWords);
 }
 
-size_t lsdb_grow_rec_bytes_per_cta(void) { return (size_t)RING * 32 * 32; }
-size_t lsdb_grow_list_words_per_warp(int listCap, int arenaCap) { return 3 * (size_t)listCap + 64 + (size_t)arenaCap; }
+size_t lsdb_grow_list_words_per_warp(int listCap, int arenaCap) { return grow_words_per_warp(listCap, arenaCap); }
+size_t lsdb_grow_rec_bytes_per_cta(void) { return (size_t)RING * 32 * REC_BYTES_PER_CELL; }
+
 
 void lsdb_launch_lgamma_table(cudaStream_t s, double* tab, int n) {
     lsdb_lgamma_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(tab, n);
@@ -1074,10 +1393,21 @@ void lsdb_launch_used_plane(cudaStream_t s, const unsigned int* state, uint8_t* 
 }
 
 // how many CTAs of `warpsPerCta` warps fit on the device at once (the kernel is persistent)
-int lsdb_grow_max_ctas(int device, int warpsPerCta) {
+int lsdb_grow_max_ctas(int device, int warpsPerCta, int bmCapWords) {
     int sms = 0, per = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lsdb_grow_kernel, warpsPerCta * 32, 0);
+    cudaFuncSetAttribute(lsdb_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lsdb_grow_kernel, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta));
     if (per < 1) per = 1;
     return sms * per;
+}
+
+// largest ban plane (in 32-bit words) that fits in shared memory next to the kernel's static data
+int lsdb_grow_max_bitmap_words(int device) {
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, lsdb_grow_kernel) != cudaSuccess) return 0;
+    const long long room = (long long)optin - (long long)fa.sharedSizeBytes - 256 - NW_MAX * 1024;
+    return room > 0 ? (int)(room / 4) : 0;
 }

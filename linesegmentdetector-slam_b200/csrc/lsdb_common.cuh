@@ -12,7 +12,8 @@ struct LsdbImg {
     int srcPitch;         // bytes per source row in the device copy
     int tile0;            // first stencil tile of this map
     int tilesX, tilesY;
-    int pad_;
+    int pw;               // words per row of the ban bitmap: ceil(W/32)
+    unsigned long long banOff;   // word offset of the map's ban bitmap (H*pw words)
     unsigned long long srcOff;   // byte offset of the map in the source buffer
     unsigned long long nOff;     // element offset of the map in every per-pixel plane
     unsigned long long segOff;   // element offset into the rect output
@@ -27,7 +28,7 @@ struct LsdbImgDyn {
     int nSeg;                        // accepted segments
     int err;                         // LSDB_ERR_* raised by a kernel for this map
     int pad_;
-    long long stat[21];              // lsdb_stats fields
+    long long stat[24];              // lsdb_stats fields
 };
 
 struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec logNFA
@@ -45,6 +46,7 @@ struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec l
 #define LSDB_SRC_MAX 136        // max source-window edge of one tile
 #define LSDB_GROW_WARPS 16
 #define LSDB_CHUNK 32           // seed-list cells per ordered-commit chunk
+#define LSDB_SUPER 8            // chunks a warp claims and speculates on at once (256 cells)
 
 #define LSDB_NP 12
 struct LsdbLsdConst {
@@ -71,19 +73,20 @@ __device__ __forceinline__ int lsdb_x86_d2i(double v) {
 // launchers (defined in the .cu files, called from api.cu)
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
-                         unsigned int* state, double* gaussOut);
+                         unsigned int* state, unsigned int* banBits, double* gaussOut);
 void lsdb_launch_order(cudaStream_t s, int nImgs, const LsdbImg* imgs, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
                        const double* mag, unsigned short* bins, unsigned int* cells);
 void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, const LsdbImg* imgs, LsdbImgDyn* dyn,
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
                       unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
-                      int* imgCounter);
+                      int* imgCounter, const unsigned int* banBits, int bmCapWords);
 size_t lsdb_grow_rec_bytes_per_cta(void);
 size_t lsdb_grow_list_words_per_warp(int listCap, int arenaCap);
 void lsdb_launch_lgamma_table(cudaStream_t s, double* tab, int n);
 void lsdb_launch_used_plane(cudaStream_t s, const unsigned int* state, uint8_t* used, int n);
-int lsdb_grow_max_ctas(int device, int warpsPerCta);
+int lsdb_grow_max_ctas(int device, int warpsPerCta, int bmCapWords);
+int lsdb_grow_max_bitmap_words(int device);
 
 struct LsdbFaTask { int frame, iScan, iMap, pad; };
 struct LsdbFaHyp { int frame, iScan, iMap, iPair; double x, y, ang, score; };  // == lsdb_hypothesis

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) lsdb_stencil_kernel(const LsdbImg* __rest
                                                            const uint8_t* __restrict__ src, double* __restrict__ mag,
                                                            double* __restrict__ deg, double* __restrict__ cosm,
                                                            double* __restrict__ sinm, unsigned int* __restrict__ state,
-                                                           double* __restrict__ gaussOut) {
+                                                           unsigned int* __restrict__ banBits, double* __restrict__ gaussOut) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StencilSmem& S = *reinterpret_cast<StencilSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) lsdb_stencil_kernel(const LsdbImg* __rest
     const int lx = tid & 31;
     for (int ly = tid >> 5; ly < LSDB_TILE; ly += 8) {
         int x = x0 + lx, y = y0 + ly;
+        bool banned = true;   // pixels beyond the row end read as banned in the bitmap
         if (x < x1 && y < y1) {
             double m = 0.0, d = 0.0;
             unsigned int st = 0;
@@ -184,11 +185,15 @@ __global__ void __launch_bounds__(256) lsdb_stencil_kernel(const LsdbImg* __rest
             mag[p] = m;
             deg[p] = d;
             state[p] = st;
+            banned = st != 0;
             if (st == 0) {  // growable pixel: the addends of RegionGrower's running sums (:515-516,:545-546)
                 cosm[p] = lsdm_cos(d);
                 sinm[p] = lsdm_sin(d);
             }
         }
+        // usedMap==1 as one bit per pixel, row-pitched: the region pipeline keeps this plane in shared memory
+        const unsigned int bal = __ballot_sync(0xffffffffu, banned);
+        if (lx == 0 && y < y1) banBits[im.banOff + (size_t)y * im.pw + (x0 >> 5)] = bal;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
@@ -203,12 +208,12 @@ __global__ void __launch_bounds__(256) lsdb_stencil_kernel(const LsdbImg* __rest
 
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
-                         unsigned int* state, double* gaussOut) {
+                         unsigned int* state, unsigned int* banBits, double* gaussOut) {
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(lsdb_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StencilSmem));
         attr = true;
     }
     if (nTiles > 0)
-        lsdb_stencil_kernel<<<nTiles, 256, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, gaussOut);
+        lsdb_stencil_kernel<<<nTiles, 256, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, gaussOut);
 }

@@ -1,0 +1,146 @@
+// Drop-in body for myfa::FeatureAssociation (reference LSD/myFA.h:83, LSD/myFA.cpp:13-184).
+//
+// The scoring half — the pair filter :29-41, the pthread pool dispatch :22-63 and, per task,
+// thread_ScanToMapMatch :186-272 (NormalizedLineDirection :274-305, rotateScanIm :307-355, CalcScore
+// :357-396) — runs as ONE kernel launch through lsdb_fa_score.  What the north star keeps on the host
+// stays on the host: the hidden-Markov gating / weighted mean below (this file, re-stated from :65-171)
+// and the reference's own myfa::ukf (:404-536), which is called, not re-implemented.
+//
+// Build: compile against the reference's myFA.h; the reference's myFA.cpp stays in the build for ukf()
+// with its FeatureAssociation renamed away (-DFeatureAssociation=FeatureAssociation_cpu on that TU, see
+// INTEGRATION.md).  Differences a caller can observe:
+//   * hypotheses are ordered (scan line, map line, pairing) instead of by thread arrival, so equal-score
+//     ties sort deterministically (the reference's order is timing-dependent);
+//   * structScore::rotateScanImPoint is NULL (the reference stores a pointer it has already freed, :256-258);
+//   * the device copy of mapCache / mapLinesInfo is cached across frames, keyed by the Mat's data pointer,
+//     its size and a hash of the map lines (the reference's drivers build both once per map).
+#include <myFA.h>
+
+#include <algorithm>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "lsdb_host.h"
+
+static_assert(sizeof(structLinesInfo) == sizeof(lsdb_line), "structLinesInfo layout (LSD/baseFunc.h:33-44)");
+
+namespace {
+
+struct MapKey {
+    const void* data; int rows, cols, nLines; unsigned long long hash;
+    bool operator==(const MapKey& o) const { return data == o.data && rows == o.rows && cols == o.cols && nLines == o.nLines && hash == o.hash; }
+};
+MapKey g_key = {0, 0, 0, 0, 0};
+lsdb_fa_map* g_map = 0;
+
+unsigned long long fnv1a(const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    unsigned long long h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+lsdb_fa_map* device_map(lsdb_ctx* ctx, myfa::structFAInput* in) {
+    const int nLines = (int)in->mapLinesInfo.size();
+    MapKey k = {in->mapCache.data, in->mapCache.size[0], in->mapCache.size[1], nLines,
+                nLines ? fnv1a(&in->mapLinesInfo[0], sizeof(structLinesInfo) * (size_t)nLines) : 0ull};
+    if (g_map && k == g_key && !getenv("LSDB_FA_NO_CACHE")) return g_map;
+    if (g_map) lsdb_fa_map_destroy(g_map);
+    g_map = 0;
+    const int rows = k.rows, cols = k.cols;
+    std::vector<double> packed;
+    const double* cache = in->mapCache.ptr<double>(0);
+    if (in->mapCache.step != (size_t)cols * sizeof(double)) {   // padded rows: pack
+        packed.resize((size_t)rows * cols);
+        for (int y = 0; y < rows; y++) memcpy(&packed[(size_t)y * cols], in->mapCache.ptr<double>(y), sizeof(double) * (size_t)cols);
+        cache = packed.data();
+    }
+    const int rc = lsdb_fa_map_create(ctx, cache, cols, rows, nLines ? (const lsdb_line*)&in->mapLinesInfo[0] : 0, nLines, &g_map);
+    if (rc != LSDB_OK) lsdb_host::die("lsdb_fa_map_create", rc);
+    g_key = k;
+    return g_map;
+}
+
+myfa::structFAOutput lost_track() {   // "no match: start a new chain", LSD/myFA.cpp:70-90 and :131-151
+    myfa::structFAOutput o;
+    const double px[9] = {-1, -1, 0, 0, 0, 0, 0, 0, 0};
+    const double pd[9] = {100, 100, 100, 1, 1, 1, 0.1, 0.1, 0.1};
+    for (int i = 0; i < 9; i++) {
+        o.kalman_x(i) = px[i];
+        for (int j = 0; j < 9; j++) o.kalman_P(i, j) = i == j ? pd[i] : 0.0;
+    }
+    return o;
+}
+
+}  // namespace
+
+namespace myfa {
+
+structFAOutput FeatureAssociation(structFAInput* FAInput) {
+    lsdb_ctx* ctx = lsdb_host::context();
+    lsdb_fa_map* m = device_map(ctx, FAInput);
+
+    const int nScan = (int)FAInput->scanLinesInfo.size(), nPts = (int)FAInput->scanImPoint.size();
+    const int nMap = (int)FAInput->mapLinesInfo.size();
+    const int lineOff[2] = {0, nScan}, ptOff[2] = {0, nPts};
+    std::vector<double> pts(2 * (size_t)(nPts > 0 ? nPts : 1));
+    for (int i = 0; i < nPts; i++) { pts[2 * i] = FAInput->scanImPoint[i].x; pts[2 * i + 1] = FAInput->scanImPoint[i].y; }
+    const double lidar[2] = {FAInput->lidarPose.x, FAInput->lidarPose.y};
+    const double last[3] = {FAInput->lastPose.x, FAInput->lastPose.y, FAInput->lastPose.ang};
+    const int cap = 4 * (nScan > 0 ? nScan : 1) * (nMap > 0 ? nMap : 1);
+    std::vector<lsdb_hypothesis> hyp(cap);
+    int nHyp = 0;
+    const int rc = lsdb_fa_score(ctx, m, 1, nScan ? (const lsdb_line*)&FAInput->scanLinesInfo[0] : 0, lineOff, pts.data(), ptOff,
+                                 lidar, last, hyp.data(), cap, &nHyp);
+    if (rc != LSDB_OK) lsdb_host::die("lsdb_fa_score", rc);
+
+    // keep what thread_ScanToMapMatch keeps: score < 3 (LSD/myFA.cpp:261)
+    std::vector<structScore> Score;
+    for (int i = 0; i < nHyp; i++) {
+        if (!(hyp[i].score < 3)) continue;
+        structScore s;
+        s.pos.x = hyp[i].x; s.pos.y = hyp[i].y; s.pos.ang = hyp[i].ang;
+        s.rotateScanImPoint = 0;
+        s.score = hyp[i].score;
+        Score.push_back(s);
+    }
+    if (Score.empty()) return lost_track();
+
+    // ascending by score (CompScore, :398-402); stable, so ties keep (scan, map, pairing) order
+    std::stable_sort(Score.begin(), Score.end(), [](const structScore& a, const structScore& b) { return a.score < b.score; });
+
+    structFAOutput out;
+    if (fabs(FAInput->lastPose.x + 1) < 0.0001) {   // first frame of a chain: take the best hypothesis (:100-110)
+        out.kalman_x = FAInput->kalman_x;
+        out.kalman_P = FAInput->kalman_P;
+        out.kalman_x(0) = Score[0].pos.x;
+        out.kalman_x(1) = Score[0].pos.y;
+        out.kalman_x(2) = Score[0].pos.ang;
+        printf("Score:%lf\n", Score[0].score);
+        return out;
+    }
+
+    // later frames: 1/score^2 weighted mean of every kept hypothesis (:160-171), then the reference's UKF
+    double sumX = 0, sumY = 0, sumAng = 0, sumW = 0;
+    const int n = (int)Score.size();
+    for (int i = 0; i < n; i++) {
+        const double w = 1 / (Score[i].score * Score[i].score);
+        sumX += Score[i].pos.x * w;
+        sumY += Score[i].pos.y * w;
+        sumAng += Score[i].pos.ang * w;
+        sumW += w;
+    }
+    structScore est;
+    est.pos.x = sumX / sumW;
+    est.pos.y = sumY / sumW;
+    est.pos.ang = sumAng / sumW;
+    est.rotateScanImPoint = 0;
+    est.score = 1 / sqrt(sumW / n);
+    printf("Score:%lf\n", est.score);
+    return ukf(FAInput, est);
+}
+
+}  // namespace myfa

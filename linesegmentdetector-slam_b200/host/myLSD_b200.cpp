@@ -1,0 +1,59 @@
+// Drop-in body for mylsd::myLineSegmentDetector (reference LSD/myLSD.h:132, LSD/myLSD.cpp:129-376).
+//
+// Compiled against the reference's own myLSD.h (so the signature, structLSD and structLinesInfo are the
+// reference's, not copies) and linked with liblsdb200.so.  The reference's myLSD.cpp stays in the build
+// for createMapCache unless LSDB_DEVICE_MAP_CACHE is defined; its own myLineSegmentDetector is renamed
+// out of the way at compile time (-DmyLineSegmentDetector=myLineSegmentDetector_cpu on that one TU, see
+// INTEGRATION.md) or simply deleted by the maintainer.
+//
+// Contract kept from the reference:
+//   * MapGray is a shallow, ref-counted copy, so the 1->255 / 255->0 remap (rows, cols >= 1 only) is
+//     written back into the CALLER's pixels (LSD/myLSD.cpp:135-142); main_on_windows.cpp relies on
+//     createMapCache having run first (LSD/main_on_windows.cpp:67-70).
+//   * linesInfo is malloc'd here and owned by the caller (never freed by the reference's callers, :281).
+//   * lineIm is a fresh CV_8UC1 Mat of oriMapRow x oriMapCol (:215).
+//   * no error channel: failures abort with the library's message.
+#include <myLSD.h>
+
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "lsdb_host.h"
+
+static_assert(sizeof(structLinesInfo) == sizeof(lsdb_line), "structLinesInfo layout (LSD/baseFunc.h:33-44)");
+
+namespace mylsd {
+
+structLSD myLineSegmentDetector(Mat MapGray, int oriMapCol, int oriMapRow, double sca, double sig, double angThre,
+                                double denThre, int pseBin) {
+    lsdb_ctx* ctx = lsdb_host::context();
+    const size_t npx = (size_t)oriMapCol * oriMapRow;
+    std::vector<uint8_t> in(npx), remapped(npx), lineIm(npx);
+    for (int y = 0; y < oriMapRow; y++) memcpy(&in[(size_t)y * oriMapCol], MapGray.ptr<uint8_t>(y), (size_t)oriMapCol);
+
+    lsdb_lsd_params prm;
+    prm.sca = sca; prm.sig = sig; prm.angThre = angThre; prm.denThre = denThre; prm.pseBin = pseBin; prm._pad = 0;
+    const int cap = 4096;
+    std::vector<lsdb_line> lines(cap);
+    int n = 0;
+    const int rc = lsdb_lsd(ctx, in.data(), oriMapCol, oriMapRow, &prm, lines.data(), cap, &n, lineIm.data(), remapped.data());
+    if (rc != LSDB_OK) lsdb_host::die("lsdb_lsd", rc);
+
+    for (int y = 0; y < oriMapRow; y++) memcpy(MapGray.ptr<uint8_t>(y), &remapped[(size_t)y * oriMapCol], (size_t)oriMapCol);
+
+    structLSD out;
+    out.lineIm = Mat::zeros(oriMapRow, oriMapCol, CV_8UC1);
+    for (int y = 0; y < oriMapRow; y++) memcpy(out.lineIm.ptr<uint8_t>(y), &lineIm[(size_t)y * oriMapCol], (size_t)oriMapCol);
+    out.len_linesInfo = n;
+    out.linesInfo = (structLinesInfo*)malloc(sizeof(structLinesInfo) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        structLinesInfo& L = out.linesInfo[i];
+        const lsdb_line& s = lines[i];
+        L.k = s.k; L.b = s.b; L.dx = s.dx; L.dy = s.dy; L.x1 = s.x1; L.y1 = s.y1; L.x2 = s.x2; L.y2 = s.y2;
+        L.len = s.len; L.orient = s.orient;
+    }
+    return out;
+}
+
+}  // namespace mylsd

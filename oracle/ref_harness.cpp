@@ -52,7 +52,9 @@ static void copy_mat(const cv::Mat& m, void* dst) {
 extern "C" {
 
 const char* ref_variant(void) {
-#ifdef REF_VARIANT_LSDM
+#if defined(REF_VARIANT_DROPIN)
+    return "dropin"; // myLineSegmentDetector / FeatureAssociation are this repo's B200 drop-in bodies
+#elif defined(REF_VARIANT_LSDM)
     return "lsdm";   // libm calls interposed by the repo's portable math (oracle ii)
 #else
     return "glibc";  // stock libm of this box (oracle i)

@@ -19,6 +19,7 @@ def run(name, maps, reps=3):
     print(f"{name}: n={len(maps)} wall={dt*1e3:.2f} ms stages={ {k: round(v,3) for k,v in ms.items()} } Mpx/s={px/dt/1e6:.1f}")
     print("   ", {k: st[k] for k in ("cells","live_seeds","grows","grown_px","nfa_calls","nfa_px","accepts","spec_evals","respec_evals","chunks")})
     print("    Mcycles:", {k: round(st[k]/1e6,2) for k in st if k.startswith("cyc_")})
+    print("    per-map avg: %.2f ms, SM clock seen by clock64: %.0f MHz" % (st["ns_map"] / 1e6 / len(maps), st["cyc_map"] / max(1, st["ns_map"]) * 1e3))
     b.close()
 
 g = np.load(os.path.join(ROOT, "tests", "golden", "bundled_maps.npz"))
