@@ -161,6 +161,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from __graft_entry__ import load_package
     lsdb = load_package()
+    from lsdb200 import shard
     stream = torch.cuda.Stream()          # an explicit stream: its handle is what the library launches on
     torch.cuda.set_stream(stream)
     ctx = lsdb.Context(local, stream.cuda_stream)
@@ -168,8 +169,10 @@ def main():
     n, size = args.maps_per_gpu, args.size
     host = torch.empty((n, size, size), dtype=torch.uint8).pin_memory()
     hnp = host.numpy()
+    first, cnt = shard.shard_range(world * n, rank, world)   # weak scaling: every rank owns n maps of the global batch
+    assert cnt == n
     for i in range(n):
-        hnp[i] = make_map(size, rank * n + i)
+        hnp[i] = make_map(size, first + i)
     ptrs = [int(hnp[i].ctypes.data) for i in range(n)]
     batch = lsdb.Batch(ctx, [(size, size)] * n)
     W = batch.scaled(0)[0]; npx = W * batch.scaled(0)[1]

@@ -69,6 +69,9 @@ typedef struct {
     long long cyc_grow, cyc_rect, cyc_nfa, cyc_wait, cyc_retire, cyc_spec, cyc_respec;
     /* per map, summed: SM cycles and wall nanoseconds (globaltimer) a CTA spent on the map; and one spare */
     long long cyc_map, ns_map, spare_;
+    /* frontier re-evaluations by cause: never evaluated / parked result invalidated; how many of them committed a region;
+     * parked accept/reject results that were invalidated */
+    long long rs_none, rs_conflict, rs_commit, rs_lost_commit, rs_pad[4];
 } lsdb_stats;
 
 /* ---- context ---- */

@@ -411,9 +411,9 @@ extern "C" int lsdb_batch_stats(lsdb_batch* b, lsdb_stats* total) {
     int rc = fetch_dyn(b);
     if (rc) return rc;
     long long* t = (long long*)total;
-    for (int k = 0; k < 24; k++) t[k] = 0;
+    for (int k = 0; k < 32; k++) t[k] = 0;
     for (int i = 0; i < b->n; i++)
-        for (int k = 0; k < 24; k++) t[k] += b->dynH[i].stat[k];
+        for (int k = 0; k < 32; k++) t[k] += b->dynH[i].stat[k];
     return LSDB_OK;
 }
 

@@ -41,7 +41,7 @@ enum { OC_NONE = 0, OC_NOCHANGE = 1, OC_REJECT = 2, OC_ACCEPT = 3, OC_DEFER = 4 
 enum { ST_CELLS = 0, ST_LIVE, ST_GROWS, ST_GROWNPX, ST_SMALL, ST_REGROWS, ST_RRR, ST_NFACALLS, ST_NFAPX, ST_REJECTS,
        ST_ACCEPTS, ST_SPEC, ST_RESPEC, ST_CHUNKS, ST_N,
        // cycle counters (lane 0 of every warp, summed): only kept in LSDB_TIMING builds, reported through stat[] slots 14..19
-       TM_GROW = ST_N, TM_RECT, TM_NFA, TM_WAIT, TM_RETIRE, TM_SPEC, TM_RESPEC, TM_MAPCYC, TM_MAPNS, TM_SPARE, TM_N };
+       TM_GROW = ST_N, TM_RECT, TM_NFA, TM_WAIT, TM_RETIRE, TM_SPEC, TM_RESPEC, TM_MAPCYC, TM_MAPNS, TM_SPARE, RS_NONE, RS_CONFLICT, RS_COMMIT, RS_LOST, RS_P0, RS_P1, RS_P2, RS_P3, TM_N };
 
 #define RING 512           // chunks a CTA may run ahead of the commit frontier
 #define SG_CAP 32          // lane-per-seed growth handles regions below min(regThre, SG_CAP) pixels
@@ -1175,6 +1175,9 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
             long long t0 = clock64();
             const int oc2 = eval_seed(c, p, c.scratch, 2 * c.listCap + 64, false, bb, used, chk);
             STAT(c, ST_RESPEC, 1);
+            STAT(c, oc == OC_NONE ? RS_NONE : RS_CONFLICT, 1);
+            if (oc == OC_ACCEPT || oc == OC_REJECT) STAT(c, RS_LOST, 1);
+            if (oc2 == OC_REJECT || oc2 == OC_ACCEPT) STAT(c, RS_COMMIT, 1);
             if (oc2 == OC_DEFER) { sh.abortFlag = LSDB_ERR_CAPACITY; break; }
             if (oc2 == OC_REJECT || oc2 == OC_ACCEPT) { commit_region(c, c.scratch, lab, rc, maxSeg); changed = true; }
             if (lane == 0) atomicAdd(&sh.stats[TM_RESPEC], (unsigned long long)(clock64() - t0));

@@ -28,7 +28,7 @@ struct LsdbImgDyn {
     int nSeg;                        // accepted segments
     int err;                         // LSDB_ERR_* raised by a kernel for this map
     int pad_;
-    long long stat[24];              // lsdb_stats fields
+    long long stat[32];              // lsdb_stats fields
 };
 
 struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec logNFA

@@ -218,6 +218,20 @@ void ref_feature_association(const double* scan_lines, int n_scan, const double*
     for (int i = 0; i < 9; i++) for (int j = 0; j < 9; j++) kalman_P81[9 * i + j] = out.kalman_P(i, j);
 }
 
+// myfa::ukf (LSD/myFA.cpp:404) alone: kalman_x9 / kalman_P81 in/out (row-major), scan_pose = odometry increment,
+// est = x, y, ang of the pose estimate.  Deterministic (no thread pool involved).
+void ref_ukf(double* kalman_x9, double* kalman_P81, const double* scan_pose, const double* est) {
+    myfa::structFAInput in;
+    in.ScanPose.x = scan_pose[0]; in.ScanPose.y = scan_pose[1]; in.ScanPose.ang = scan_pose[2];
+    for (int i = 0; i < 9; i++) in.kalman_x(i) = kalman_x9[i];
+    for (int i = 0; i < 9; i++) for (int j = 0; j < 9; j++) in.kalman_P(i, j) = kalman_P81[9 * i + j];
+    myfa::structScore e;
+    e.pos.x = est[0]; e.pos.y = est[1]; e.pos.ang = est[2]; e.score = 0; e.rotateScanImPoint = 0;
+    myfa::structFAOutput out = myfa::ukf(&in, e);
+    for (int i = 0; i < 9; i++) kalman_x9[i] = out.kalman_x(i);
+    for (int i = 0; i < 9; i++) for (int j = 0; j < 9; j++) kalman_P81[9 * i + j] = out.kalman_P(i, j);
+}
+
 // myrdp::FeatureScan on one frame (finite ranges only, as LSD/main_on_windows.cpp:110-123
 // filters them).  map_param = cols rows resol oriX oriY.  Outputs: lines [max_lines][10],
 // pts [max_pts][2], lidar_pos[2], im_size[2] = cols,rows of the scan raster.

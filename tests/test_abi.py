@@ -52,3 +52,19 @@ def test_product_does_not_touch_the_oracle():
                 if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py", "Makefile")):
                     txt = open(os.path.join(dp, f), errors="ignore").read()
                     assert "lsd_oracle" not in txt and "oraclebind" not in txt and "oracle/" not in txt, os.path.join(dp, f)
+
+
+def test_dropin_library_keeps_the_reference_entry_points():
+    """oracle/_ref/libref_dropin.so = the reference's callers + this repo's C++ bodies for myLSD.h / myFA.h: it must load
+    (liblsdb200.so resolves through its rpath) and still define the reference's mangled entry points."""
+    import subprocess
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_dropin.so")
+    if not os.path.exists(so):
+        pytest.skip("libref_dropin.so not built (needs /root/reference)")
+    L = C.CDLL(so)
+    L.ref_variant.restype = C.c_char_p
+    assert L.ref_variant() == b"dropin"
+    syms = subprocess.run(["nm", "-DC", "--defined-only", so], capture_output=True, text=True).stdout
+    assert "mylsd::myLineSegmentDetector(cv::Mat, int, int, double, double, double, double, int)" in syms
+    assert "myfa::FeatureAssociation(myfa::_structFAInput*)" in syms
+    assert "mylsd::myLineSegmentDetector_cpu" in syms and "myfa::FeatureAssociation_cpu" in syms   # the reference bodies, renamed

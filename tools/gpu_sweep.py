@@ -13,11 +13,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for _ in range(2):
         b.run(); b.sync()
     st = b.stats(); ms = b.stage_ms()
-    keys = ("live_seeds", "grows", "grown_px", "small", "regrows", "nfa_calls", "rejects", "accepts", "spec_evals", "respec_evals")
+    keys = ("live_seeds", "grows", "grown_px", "small", "regrows", "nfa_calls", "rejects", "accepts", "spec_evals", "respec_evals", "rs_none", "rs_conflict", "rs_commit", "rs_lost_commit")
     print("grow %.1f ms | " % ms["grow"] + " ".join(f"{k}={st[k]}" for k in keys) + " | Mcyc " +
           " ".join(f"{k[4:]}={st[k]/1e6:.0f}" for k in st if k.startswith("cyc_")))
     sys.exit(0)
-for nw, ra in [(1, 8), (2, 16), (4, 64), (8, 128), (16, 256), (16, 64), (16, 16)]:
+for nw, ra in [(1, 8), (4, 64), (16, 256)]:
     env = dict(os.environ, LSDB_GROW_WARPS=str(nw), LSDB_RUNAHEAD=str(ra))
     out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
     print(f"nw={nw:2d} runAhead={ra:3d}: {out.stdout.strip()} {out.stderr.strip()[-300:]}")
