@@ -163,6 +163,8 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     b->kc.aliPro = prm->angThre / 180.0;                   // :209
     b->kc.denThre = prm->denThre;
     b->kc.cosDegThre = lsdm_cos(b->kc.degThre);
+    b->kc.axisDeg[0] = 0.0; b->kc.axisDeg[1] = lsdm_atan2(1.0, 0.0); b->kc.axisDeg[2] = lsdm_atan2(-1.0, 0.0);
+    for (int k = 0; k < 3; k++) { b->kc.axisCS[2 * k] = lsdm_cos(b->kc.axisDeg[k]); b->kc.axisCS[2 * k + 1] = lsdm_sin(b->kc.axisDeg[k]); }
     {
         double p = b->kc.aliPro;
         for (int k = 0; k < LSDB_NP; k++, p /= 2.0) {

@@ -55,6 +55,8 @@ struct LsdbLsdConst {
     double pTab[LSDB_NP], logP[LSDB_NP], log1mP[LSDB_NP], log10P[LSDB_NP];  // p = aliPro/2^k and its logs
     int pseBin, h;
     double taps[3 * 17];
+    double axisDeg[3];           // lsdm_atan2 of axis-aligned gradients: 0, +pi/2, -pi/2
+    double axisCS[6];            // lsdm_cos, lsdm_sin of those
 };
 
 #ifdef __CUDACC__
