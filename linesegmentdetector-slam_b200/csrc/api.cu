@@ -207,7 +207,12 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
         // the ban plane of a map (one bit per scaled pixel) lives in shared memory while the map is grown, if it fits
-        const int bmMax = lsdb_grow_max_bitmap_words(ctx->device);
+        // — but only while it leaves most of the SM's 256 KB to the L1 cache: the growers live on L1 hits for their lists
+        // and the angle planes, and a 192 KB plane (4096^2 map) costs more there than it saves (measured: 248 vs 167 ms)
+        int bmMax = lsdb_grow_max_bitmap_words(ctx->device);
+        int bmLimit = 48 * 1024 / 4;
+        if (getenv("LSDB_SMEM_BAN_KB")) bmLimit = atoi(getenv("LSDB_SMEM_BAN_KB")) * 1024 / 4;
+        if (bmMax > bmLimit) bmMax = bmLimit;
         b->bmCapWords = maxBanWords <= bmMax ? maxBanWords : 0;
         if (getenv("LSDB_NO_SMEM_BAN")) b->bmCapWords = 0;
         int nw = LSDB_GROW_WARPS;

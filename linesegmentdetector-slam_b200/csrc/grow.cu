@@ -65,8 +65,10 @@ struct GrowShared {
 };
 
 #define LSDB_REJ_CAP (1 << 16)   // words per reject list of grow_region (two per warp)
+#define LSDB_PND_CAP (1 << 12)   // words of the pending-dependency list per warp
+#define SG_PND 24                // same, per lane, in small_grow
 __host__ __device__ inline size_t grow_words_per_warp(int listCap, int arenaCap) {
-    return 3 * (size_t)listCap + 64 + (size_t)arenaCap + 2 * (size_t)LSDB_REJ_CAP;
+    return 3 * (size_t)listCap + 64 + (size_t)arenaCap + 2 * (size_t)LSDB_REJ_CAP + LSDB_PND_CAP;
 }
 // dynamic shared memory of the kernel: the ban plane, then 1 KB of staging per warp
 static inline size_t grow_dyn_smem(int bmCapWords, int warpsPerCta) { return (size_t)((bmCapWords + 1) & ~1) * 4 + (size_t)warpsPerCta * 1024; }
@@ -104,6 +106,10 @@ struct WarpCtx {
     GrowShared* sh;
     unsigned int* rej[2];   // reject lists of grow_region (ping-pong), rejCap words each
     int rejCap;
+    unsigned int* pnd;      // pixels the current speculative evaluation skipped because a PARKED accept covers them
+    int npnd;               //   (must turn out banned for the evaluation to stand), LSDB_PND_CAP words; -1 = overflow
+    int specChunk;          // seed-list chunk of the seed being evaluated speculatively; -1 at the frontier (parked
+                            //   regions are then ignored: the state is final)
     double* stage;          // 32 x 4 doubles of shared memory: operands of the ordered sums in rect_from_region
     volatile unsigned int* bm;   // shared-memory copy of the ban plane (usedMap==1), one bit per pixel, pw words per row; NULL: use `state`
     int pw;
@@ -177,6 +183,40 @@ __device__ __forceinline__ unsigned int ban9(const WarpCtx& c, int x, int y) {
 }
 __device__ __forceinline__ void ban_set(const WarpCtx& c, int x, int y) {
     if (c.bm) atomicOr(const_cast<unsigned int*>(c.bm) + (size_t)y * c.pw + (x >> 5), 1u << (x & 31));
+}
+
+// ------------------------------------------------------------------ parked regions
+// does the parked-accept mark in state word `st` come from a seed at or before chunk `myChunk` (window order mod 4096)?
+__device__ __forceinline__ bool pend_applies(unsigned int st, unsigned int kinds, int myChunk) {
+    return (st & kinds) && myChunk >= 0 && (((unsigned int)myChunk - (st >> LSDB_ST_TAG_SHIFT)) & 4095u) < 2048u;
+}
+// mark the pixels of a parked accept / reject candidate (kind = LSDB_ST_PACC / LSDB_ST_PREJ); the earliest chunk tag wins
+__device__ void park_pixels(const WarpCtx& c, const unsigned int* px, int n, unsigned int kind, int chunk) {
+    const unsigned int tag = (unsigned int)chunk & 4095u;
+    for (int k = c.lane; k < n; k += 32) {
+        unsigned int* w = &c.state[(size_t)py_of(px[k]) * c.W + px_of(px[k])];
+        unsigned int old = lsdb_ld_state(w);
+        while (true) {
+            unsigned int neu;
+            if ((old & (LSDB_ST_PACC | LSDB_ST_PREJ)) && ((tag - (old >> LSDB_ST_TAG_SHIFT)) & 4095u) < 2048u) neu = old | kind;   // an earlier seed marked it
+            else neu = (old & ((1u << LSDB_ST_TAG_SHIFT) - 1u)) | kind | (tag << LSDB_ST_TAG_SHIFT);
+            if (neu == old) break;
+            const unsigned int seen = atomicCAS(w, old, neu);
+            if (seen == old) break;
+            old = seen;
+        }
+    }
+    __syncwarp();
+}
+// a parked candidate was dropped (its seed died, or the evaluation was invalidated): take its marks back
+__device__ void unpark_pixels(const WarpCtx& c, const unsigned int* px, int n, int chunk) {
+    const unsigned int tag = (unsigned int)chunk & 4095u;
+    for (int k = c.lane; k < n; k += 32) {
+        unsigned int* w = &c.state[(size_t)py_of(px[k]) * c.W + px_of(px[k])];
+        const unsigned int old = lsdb_ld_state(w);
+        if ((old & (LSDB_ST_PACC | LSDB_ST_PREJ)) && (old >> LSDB_ST_TAG_SHIFT) == tag) atomicAnd(w, ~(LSDB_ST_PACC | LSDB_ST_PREJ));
+    }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------ RegionGrower (:491-590)
@@ -343,6 +383,19 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
             double dg = 0.0, cd = 0.0, sd = 0.0;
             if (cand) { dg = c.deg[p]; cd = c.cosm[p]; sd = c.sinm[p]; }  // issued with the state load, not after it
             cand = cand && !(st & banMask);
+            if (c.specChunk >= 0) {
+                // speculation: a pixel inside a region an earlier seed has parked for acceptance counts as banned;
+                // it is listed so that the guess can be checked when this evaluation retires
+                const bool pend = cand && pend_applies(st, LSDB_ST_PACC, c.specChunk);
+                const unsigned int pb = __ballot_sync(FULL, pend);
+                if (pb) {
+                    if (c.npnd >= 0 && c.npnd + 32 <= LSDB_PND_CAP) {
+                        if (pend) c.pnd[c.npnd + __popc(pb & lt)] = pack_xy(n, m);
+                        c.npnd += __popc(pb);
+                    } else c.npnd = -1;
+                    if (pend) cand = false;
+                }
+            }
             if (accept_lanes(c, g, cand, p, n, m, dg, cd, sd, num, haveExact, regExact, degThre, c2, cTau, tauSmall, tauGtPi, tauF) < 0) return -1;
             if (!literal) {
                 const unsigned int rb = __ballot_sync(FULL, cand);
@@ -383,8 +436,9 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
 // path then grows it in full).  Later passes only re-test the neighbours that failed the ANGLE test before:
 // out-of-image, banned and own pixels stay so (bans only grow; a pixel that gets banned meanwhile invalidates
 // the evaluation at retire time anyway).
-// Returns the region size (T when large).  lst[] holds the accepted pixels (packed y<<16|x).
-__device__ __noinline__ int small_grow(const WarpCtx& c, int p0, int T, unsigned int* lst) {
+// Returns the region size (T when large).  lst[] holds the accepted pixels (packed y<<16|x), pnd[0..npnd) the pixels
+// skipped because an earlier seed's parked accept covers them (npnd = -1: more than SG_PND of them).
+__device__ __noinline__ int small_grow(const WarpCtx& c, int p0, int T, unsigned int* lst, int myChunk, unsigned int* pnd, int& npnd) {
     const int W = c.W;
     const double pi = c.kc->pi, pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
     const double degThre = c.kc->degThre, cTau = c.kc->cosDegThre;
@@ -414,7 +468,15 @@ __device__ __noinline__ int small_grow(const WarpCtx& c, int p0, int T, unsigned
                 for (int k = 0; k < num; k++) own |= lst[k] == pk;
                 if (own) continue;
                 const size_t p = (size_t)m * W + n;
+                const unsigned int st = lsdb_ld_state(&c.state[p]);
                 const double cd = c.cosm[p], sd = c.sinm[p];
+                if (st & LSDB_ST_BAN) continue;
+                if (pend_applies(st, LSDB_ST_PACC, myChunk)) {   // parked for acceptance by an earlier seed: counts as banned,
+                    bool dup = false;                            // to be confirmed when this evaluation retires
+                    for (int j = 0; j < npnd; j++) dup |= pnd[j] == pk;
+                    if (!dup) { if (npnd >= 0 && npnd < SG_PND) pnd[npnd++] = pk; else npnd = -1; }
+                    continue;
+                }
                 const double dot = cosS * cd + sinS * sd;
                 const double d2 = dot * dot - c2n2;
                 bool pass = dot > 0 && d2 > 0;
@@ -730,7 +792,19 @@ __device__ double rectangle_improver(WarpCtx& c, Rect& rec, double logNT) {
 //   :242-248/:259-265 visit); chk = number of words after the header to re-validate.  Without wantChk
 //   (frontier evaluation) only the re-grow backup and the commit list are written.
 // The warp's curMap bits are cleared on return.  OC_DEFER = `cap` too small (nothing was changed).
-__device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wantChk, BBox& bb, int& used, int& chk) {
+// copies the pending-dependency list of the evaluation behind the `aw` words already written after the header
+__device__ bool park_pend(WarpCtx& c, unsigned int* body, int& aw, int cap, int& pndOff, int& pndN) {
+    pndOff = 0; pndN = 0;
+    if (c.npnd < 0 || ARENA_HDR + aw + c.npnd + 2 > cap) return false;
+    for (int k = c.lane; k < c.npnd; k += 32) body[aw + k] = c.pnd[k];
+    __syncwarp();
+    pndOff = ARENA_HDR + aw; pndN = c.npnd;
+    aw += c.npnd;
+    return true;
+}
+
+__device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wantChk, BBox& bb, int& used, int& chk, int& pndOff, int& pndN) {
+    c.npnd = 0; pndOff = 0; pndN = 0;
     const LsdbLsdConst* kc = c.kc;
     const int W = c.W;
     const int sx = p0 % W, sy = p0 / W;
@@ -743,13 +817,14 @@ __device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wa
     unsigned int* body = out + ARENA_HDR;
     int aw = 0;  // words written after the header
     if (num < c.regThre) {  // :228
-        if (wantChk) {
-            if (ARENA_HDR + num + 2 > cap) { clear_bits(c, c.list, num); return OC_DEFER; }
-            for (int k = c.lane; k < num; k += 32) body[k] = c.list[k];
-            chk = num;
-            used = (ARENA_HDR + num + 1) & ~1;
-        }
         clear_bits(c, c.list, num);
+        if (wantChk) {
+            if (ARENA_HDR + num + 2 > cap) return OC_DEFER;
+            for (int k = c.lane; k < num; k += 32) body[k] = c.list[k];
+            chk = num; aw = num;
+            if (!park_pend(c, body, aw, cap, pndOff, pndN)) return OC_DEFER;
+            used = (ARENA_HDR + aw + 1) & ~1;
+        }
         STAT(c, ST_SMALL, 1);
         return OC_NOCHANGE;
     }
@@ -805,7 +880,7 @@ __device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wa
         aw += num;
         if (num < 2) {
             clear_bits(c, c.list, num);
-            if (wantChk) { chk = aw; used = (ARENA_HDR + aw + 1) & ~1; }
+            if (wantChk) { chk = aw; if (!park_pend(c, body, aw, cap, pndOff, pndN)) return OC_DEFER; used = (ARENA_HDR + aw + 1) & ~1; }
             return OC_NOCHANGE;
         }
         rec = rect_from_region(c, c.list, num, regDeg, rec.p, rec.prec);
@@ -846,7 +921,7 @@ __device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wa
             }
             if (!ok) {
                 clear_bits(c, backup, tnum);
-                if (wantChk) { chk = aw; used = (ARENA_HDR + aw + 1) & ~1; }
+                if (wantChk) { chk = aw; if (!park_pend(c, body, aw, cap, pndOff, pndN)) return OC_DEFER; used = (ARENA_HDR + aw + 1) & ~1; }
                 return OC_NOCHANGE;
             }
         }
@@ -887,19 +962,25 @@ __device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wa
         out[28] = (unsigned int)(ARENA_HDR + aw);
     }
     __syncwarp();
-    if (wantChk) {
-        // speculative result parked: tell other warps that these pixels are about to leave the seed pool
-        // (usedMap 1 or 2 once this record retires), so evaluating them as seeds now would be wasted work.
-        // A hint only steers speculation; stale hints merely move an evaluation to the frontier.
-        for (int k = c.lane; k < outN; k += 32) {
-            const unsigned int v = commit[k];
-            atomicOr(&c.state[(size_t)py_of(v) * W + px_of(v)], LSDB_ST_HINT);
-        }
-    }
     aw += outN;
+    if (wantChk) {
+        chk = aw;
+        if (!park_pend(c, body, aw, cap, pndOff, pndN)) return OC_DEFER;
+        // speculative result parked: later seeds speculate as if these pixels already were usedMap 1 (accept) or 2
+        // (reject).  The marks only steer speculation; every evaluation that relied on them is re-checked at retire.
+        park_pixels(c, commit, outN, oc == OC_ACCEPT ? LSDB_ST_PACC : LSDB_ST_PREJ, c.specChunk);
+    }
     used = (ARENA_HDR + aw + 1) & ~1;
-    if (wantChk) chk = aw;
     return oc;
+}
+
+__device__ bool any_unbanned(const WarpCtx& c, const unsigned int* px, int n) {
+    bool hit = false;
+    for (int k = c.lane; k < n; k += 32) {
+        const unsigned int v = px[k];
+        if (!ban_at(c, px_of(v), py_of(v))) hit = true;
+    }
+    return __any_sync(FULL, hit);
 }
 
 __device__ bool any_banned(const WarpCtx& c, const unsigned int* px, int n) {
@@ -992,11 +1073,13 @@ __device__ void commit_region(WarpCtx& c, const unsigned int* recp, int* labels,
 //   L0      length of the accept log when the evaluation started
 //   b0,b1,mask  bounding box / coarse-grid cells of the pixels the evaluation accepted
 //   off     arena offset of the result header (OC_ACCEPT / OC_REJECT)
-//   chkOff,chk  arena offset and length of the accepted-pixel list to re-validate (chk < 0: none kept)
+//   chkOff,chk  arena offset and length of the accepted-pixel list: must all still be un-banned (chk < 0: none kept)
+//   pndOff,pnd  arena offset and length of the pending-dependency list: must all be banned by now
 struct ChunkRecs {
     int* oc; int* L0; unsigned int* b0; unsigned int* b1; unsigned long long* mask; unsigned int* off; int* chk; unsigned int* chkOff;
+    unsigned int* pndOff; int* pnd;
 };
-#define REC_BYTES_PER_CELL 40
+#define REC_BYTES_PER_CELL 48
 
 // contiguous room for `need` words in this warp's arena ring; returns the physical offset or -1 (h2 = new virtual head base)
 __device__ __forceinline__ int arena_room(const WarpCtx& c, unsigned int head, unsigned int need, unsigned int& h2, int& avail) {
@@ -1011,12 +1094,18 @@ __device__ __forceinline__ int arena_room(const WarpCtx& c, unsigned int head, u
     return avail >= (int)need ? (int)phys : -1;
 }
 
+// should speculation leave this seed alone?  used (:222), or inside a region that an earlier seed has parked
+__device__ __forceinline__ bool seed_taken(unsigned int st, int chunk) {
+    return (st & 3u) != 0 || pend_applies(st, LSDB_ST_PACC | LSDB_ST_PREJ, chunk);
+}
+
 // Speculative evaluation of the live seeds of `nSub` consecutive chunks (up to 256 cells); parks the results and flags
-// the chunks READY.  Three phases:
-//   A  collect the live cells (seed order) into a queue;
+// the chunks READY.
+//   A  collect the live cells (seed order) into a queue; then, 32 queued seeds at a time:
 //   B  one seed per LANE: small_grow decides the ~97 % of seeds whose region stays below regThre ("no change"; the
 //      accepted pixels are parked for re-validation) and flags the rest as large;
-//   C  the large seeds, in order, one at a time with the whole warp (grow, rectangle, refine, NFA).
+//   C  the large seeds of the group, in order, one at a time with the whole warp (grow, rectangle, refine, NFA).  Each
+//      result is parked before the next seed starts, so later seeds already see it as a pending accept / reject.
 __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned int* cl, int nCells, const ChunkRecs& R, unsigned int& head, int T) {
     GrowShared& sh = *c.sh;
     const int lane = c.lane;
@@ -1028,8 +1117,7 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
     for (int s = 0; s < nSub; s++) {   // ---- A
         const int ci = (chunk0 + s) * LSDB_CHUNK + lane;
         const int p = ci < nCells ? (int)cl[ci] : -1;
-        // used (:222), or inside a parked accept/reject candidate: leave those to the frontier
-        const bool live = p >= 0 && (lsdb_ld_state(&c.state[p]) & (3u | LSDB_ST_HINT)) == 0;
+        const bool live = p >= 0 && !seed_taken(lsdb_ld_state(&c.state[p]), chunk0 + s);
         const unsigned int bal = __ballot_sync(FULL, live);
         if (live) {
             const int k = qn + __popc(bal & lt);
@@ -1040,22 +1128,29 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
         R.oc[(size_t)((chunk0 + s) & (RING - 1)) * 32 + lane] = OC_NONE;
     }
     __syncwarp();
-    for (int base = 0; base < qn && !sh.abortFlag; base += 32) {   // ---- B
+    BBox bb; int used = 0, chk = -1;
+    for (int base = 0; base < qn && !sh.abortFlag; base += 32) {
+        // ---- B
         const int k = base + lane;
-        const bool act = k < qn;
+        bool act = k < qn;
+        const unsigned int rel = act ? q[2 * k + 1] : 0u;
+        const int myChunk = chunk0 + (int)(rel >> 5);
+        const int myp = act ? (int)q[2 * k] : 0;
+        if (act && seed_taken(lsdb_ld_state(&c.state[myp]), myChunk)) act = false;   // swallowed by a region parked a moment ago
         unsigned int lst[SG_CAP];
-        int num = 0;
+        unsigned int pnd[SG_PND];
+        int num = 0, npnd = 0;
         bool large = act;
         const int L0 = sh.logCount;
         __threadfence_block();
         if (act && T <= SG_CAP) {
-            num = small_grow(c, (int)q[2 * k], T, lst);
+            num = small_grow(c, myp, T, lst, myChunk, pnd, npnd);
             large = num >= T;
         }
         __syncwarp();
-        const bool small = act && !large;
-        // park the accepted pixels of the small regions (re-validated at retire time if a region was accepted nearby)
-        const int need = small ? num : 0;
+        const bool small = act && !large && npnd >= 0;
+        // park the accepted pixels (re-validated at retire time if a region was accepted nearby) and the pending dependencies
+        const int need = small ? num + npnd : 0;
         int incl = need;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1065,21 +1160,19 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
         const int tot = __shfl_sync(FULL, incl, 31);
         unsigned int h2; int avail;
         const int phys = tot > 0 ? arena_room(c, head, (unsigned int)tot + 2u, h2, avail) : -1;
-        if (small) {
-            const unsigned int rel = q[2 * k + 1];
-            const size_t ri = (size_t)((chunk0 + (int)(rel >> 5)) & (RING - 1)) * 32 + (rel & 31u);
-            if (phys >= 0) {
-                BBox bb; bb.x0 = bb.y0 = 0x7fffffff; bb.x1 = bb.y1 = -1; bb.mask = 0ull;
-                unsigned int* dst = c.arena + phys + (incl - need);
-                for (int j = 0; j < num; j++) { dst[j] = lst[j]; bbox_add(c, bb, px_of(lst[j]), py_of(lst[j])); }
-                R.L0[ri] = L0; R.b0[ri] = pack_xy(bb.x0, bb.y0); R.b1[ri] = pack_xy(bb.x1, bb.y1); R.mask[ri] = bb.mask;
-                R.off[ri] = 0; R.chk[ri] = num; R.chkOff[ri] = (unsigned int)(phys + (incl - need));
-                R.oc[ri] = OC_NOCHANGE;
-            }   // else: arena full — this seed is decided at the frontier
-        } else if (act) {
-            q[2 * k + 1] |= 0x80000000u;
-        }
+        if (small && phys >= 0) {
+            const size_t ri = (size_t)(myChunk & (RING - 1)) * 32 + (rel & 31u);
+            BBox sb; sb.x0 = sb.y0 = 0x7fffffff; sb.x1 = sb.y1 = -1; sb.mask = 0ull;
+            unsigned int* dst = c.arena + phys + (incl - need);
+            for (int j = 0; j < num; j++) { dst[j] = lst[j]; bbox_add(c, sb, px_of(lst[j]), py_of(lst[j])); }
+            for (int j = 0; j < npnd; j++) dst[num + j] = pnd[j];
+            R.L0[ri] = L0; R.b0[ri] = pack_xy(sb.x0, sb.y0); R.b1[ri] = pack_xy(sb.x1, sb.y1); R.mask[ri] = sb.mask;
+            R.off[ri] = 0; R.chk[ri] = num; R.chkOff[ri] = (unsigned int)(phys + (incl - need));
+            R.pnd[ri] = npnd; R.pndOff[ri] = (unsigned int)(phys + (incl - need) + num);
+            R.oc[ri] = OC_NOCHANGE;
+        }   // else: arena full / too many dependencies — this seed is decided at the frontier
         if (phys >= 0) head = h2 + (unsigned int)((tot + 1) & ~1);
+        const unsigned int largeMask = __ballot_sync(FULL, act && large);
         const unsigned int nSmall = __popc(__ballot_sync(FULL, small));
         int pxs = small ? num : 0;
 #pragma unroll
@@ -1088,29 +1181,36 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
             atomicAdd(&sh.stats[ST_SPEC], (unsigned long long)nSmall); atomicAdd(&sh.stats[ST_GROWS], (unsigned long long)nSmall);
             atomicAdd(&sh.stats[ST_SMALL], (unsigned long long)nSmall); atomicAdd(&sh.stats[ST_GROWNPX], (unsigned long long)pxs);
         }
-    }
-    __syncwarp();
-    BBox bb; int used = 0, chk = -1;
-    for (int k = 0; k < qn && !sh.abortFlag; k++) {   // ---- C
-        const unsigned int rel = q[2 * k + 1];
-        if (!(rel & 0x80000000u)) continue;
-        const int p = (int)q[2 * k];
-        if (lsdb_ld_state(&c.state[p]) & (3u | LSDB_ST_HINT)) continue;   // swallowed by a region parked a moment ago
-        unsigned int h2; int avail;
-        const int phys = arena_room(c, head, 4096u, h2, avail);
-        if (phys < 0) continue;                             // arena full: this seed is decided at the frontier
-        const int L0 = sh.logCount;
-        __threadfence_block();
-        const int oc = eval_seed(c, p, c.arena + phys, avail, true, bb, used, chk);
-        STAT(c, ST_SPEC, 1);
-        if (oc == OC_DEFER) continue;
-        if (lane == 0) {
-            const size_t ri = (size_t)((chunk0 + (int)((rel & 0x7fffffffu) >> 5)) & (RING - 1)) * 32 + (rel & 31u);
-            R.L0[ri] = L0; R.b0[ri] = pack_xy(bb.x0, bb.y0); R.b1[ri] = pack_xy(bb.x1, bb.y1); R.mask[ri] = bb.mask;
-            R.off[ri] = (unsigned int)phys; R.chk[ri] = chk; R.chkOff[ri] = (unsigned int)phys + ARENA_HDR;
-            R.oc[ri] = oc;
+        // ---- C
+        unsigned int todo = largeMask;
+        while (todo && !sh.abortFlag) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int p = __shfl_sync(FULL, myp, j);
+            const unsigned int relJ = __shfl_sync(FULL, rel, j);
+            const int chunkJ = chunk0 + (int)(relJ >> 5);
+            if (seed_taken(lsdb_ld_state(&c.state[p]), chunkJ)) continue;   // swallowed by a region parked a moment ago
+            unsigned int h3; int av;
+            const int ph = arena_room(c, head, 4096u, h3, av);
+            if (ph < 0) continue;                             // arena full: this seed is decided at the frontier
+            const int L1 = sh.logCount;
+            __threadfence_block();
+            int pndOff, pndN;
+            c.specChunk = chunkJ;
+            const int oc = eval_seed(c, p, c.arena + ph, av, true, bb, used, chk, pndOff, pndN);
+            c.specChunk = -1;
+            STAT(c, ST_SPEC, 1);
+            if (oc == OC_DEFER) continue;
+            if (lane == 0) {
+                const size_t ri = (size_t)(chunkJ & (RING - 1)) * 32 + (relJ & 31u);
+                R.L0[ri] = L1; R.b0[ri] = pack_xy(bb.x0, bb.y0); R.b1[ri] = pack_xy(bb.x1, bb.y1); R.mask[ri] = bb.mask;
+                R.off[ri] = (unsigned int)ph; R.chk[ri] = chk; R.chkOff[ri] = (unsigned int)ph + ARENA_HDR;
+                R.pnd[ri] = pndN; R.pndOff[ri] = (unsigned int)(ph + pndOff);
+                R.oc[ri] = oc;
+            }
+            head = h3 + (unsigned int)used;
         }
-        head = h2 + (unsigned int)used;
+        __syncwarp();
     }
     if (lane < nSub) {
         const int slot = (chunk0 + lane) & (RING - 1);
@@ -1145,6 +1245,9 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
     const int recOc = R.oc[ri], recL0 = R.L0[ri], recChk = R.chk[ri];
     const unsigned int recB0 = R.b0[ri], recB1 = R.b1[ri], recOff = R.off[ri], recChkOff = R.chkOff[ri];
     const unsigned long long recMask = R.mask[ri];
+    const int recPnd = recOc != OC_NONE ? R.pnd[ri] : 0;
+    const unsigned int recPndOff = R.pndOff[ri];
+    bool committedParked = false;   // this lane's parked accept / reject was committed as parked
     const int ew = sh.chunkWarp[slot];
     const unsigned int* earena = c.listsBase + (size_t)ew * c.warpStride + c.listCap + (2 * (size_t)c.listCap + 64);
     bool live = myp >= 0 && (lsdb_ld_state(&c.state[myp]) & 3u) == 0;   // :222
@@ -1155,7 +1258,7 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
         else for (int e = recL0; e < logSeen && !hit; e++) hit = log_hit(sh, e, recB0, recB1, recMask);
     }
     unsigned int liveAtTurn = __ballot_sync(FULL, live);
-    unsigned int work = __ballot_sync(FULL, live && !(recOc == OC_NOCHANGE && !hit));
+    unsigned int work = __ballot_sync(FULL, live && !(recOc == OC_NOCHANGE && !hit && recPnd == 0));
     BBox bb; int used = 0, chk = -1;
     while (work) {
         const int k = __ffs(work) - 1;
@@ -1168,12 +1271,17 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
             const int nchk = __shfl_sync(FULL, recChk, k);
             valid = nchk >= 0 && !any_banned(c, earena + __shfl_sync(FULL, recChkOff, k), nchk);
         }
+        if (valid) {   // every pixel the evaluation took for banned because of a parked accept must be banned by now
+            const int npn = __shfl_sync(FULL, recPnd, k);
+            if (npn > 0) valid = !any_unbanned(c, earena + __shfl_sync(FULL, recPndOff, k), npn);
+        }
         bool changed = false;
         if (valid) {
-            if (oc != OC_NOCHANGE) { commit_region(c, recp, lab, rc, maxSeg); changed = true; }
+            if (oc != OC_NOCHANGE) { commit_region(c, recp, lab, rc, maxSeg); changed = true; if (lane == k) committedParked = true; }
         } else {
             long long t0 = clock64();
-            const int oc2 = eval_seed(c, p, c.scratch, 2 * c.listCap + 64, false, bb, used, chk);
+            int po_, pn_;
+            const int oc2 = eval_seed(c, p, c.scratch, 2 * c.listCap + 64, false, bb, used, chk, po_, pn_);
             STAT(c, ST_RESPEC, 1);
             STAT(c, oc == OC_NONE ? RS_NONE : RS_CONFLICT, 1);
             if (oc == OC_ACCEPT || oc == OC_REJECT) STAT(c, RS_LOST, 1);
@@ -1195,8 +1303,17 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
             logSeen = sh.logCount;
             const unsigned int later = ~((2u << k) - 1u);
             liveAtTurn = (liveAtTurn & ~later) | (__ballot_sync(FULL, live) & later);
-            work = __ballot_sync(FULL, lane > k && live && !(recOc == OC_NOCHANGE && !hit));
+            work = __ballot_sync(FULL, lane > k && live && !(recOc == OC_NOCHANGE && !hit && recPnd == 0));
         }
+    }
+    // parked accepts / rejects that were not committed as parked (seed dead at its turn, or evaluation invalidated):
+    // take their marks back so that later speculation stops counting on them
+    unsigned int drop = __ballot_sync(FULL, (recOc == OC_ACCEPT || recOc == OC_REJECT) && !committedParked);
+    while (drop) {
+        const int k = __ffs(drop) - 1;
+        drop &= drop - 1;
+        const unsigned int* recp = earena + __shfl_sync(FULL, recOff, k);
+        unpark_pixels(c, recp + recp[28], (int)recp[26], chunk);
     }
     STAT(c, ST_LIVE, __popc(liveAtTurn));
     __syncwarp();
@@ -1251,7 +1368,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
     extern __shared__ unsigned int bmShared[];   // the map's ban plane, one bit per pixel (bmCapWords words)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
     WarpCtx c;
-    c.lane = lane; c.w = w; c.mybit = 1u << (LSDB_ST_WARP_SHIFT + w);
+    c.lane = lane; c.w = w; c.mybit = 1u << (LSDB_ST_WARP_SHIFT + w);   // bits 4..19
     c.kc = kc; c.lgammaTab = lgammaTab; c.lgammaN = lgammaN; c.sh = &sh;
     c.listCap = listCap; c.arenaCap = arenaCap;
     c.rejCap = LSDB_REJ_CAP;
@@ -1262,6 +1379,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
     c.arena = c.scratch + 2 * (size_t)listCap + 64;
     c.rej[0] = c.arena + arenaCap;
     c.rej[1] = c.rej[0] + LSDB_REJ_CAP;
+    c.pnd = c.rej[1] + LSDB_REJ_CAP; c.npnd = 0; c.specChunk = -1;
     c.stage = reinterpret_cast<double*>(bmShared + ((bmCapWords + 1) & ~1)) + (size_t)w * 128;
     ChunkRecs R;
     {
@@ -1270,6 +1388,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
         R.oc = reinterpret_cast<int*>(base + RING * 32 * 8);
         R.L0 = R.oc + RING * 32; R.b0 = reinterpret_cast<unsigned int*>(R.L0 + RING * 32); R.b1 = R.b0 + RING * 32;
         R.off = R.b1 + RING * 32; R.chk = reinterpret_cast<int*>(R.off + RING * 32); R.chkOff = reinterpret_cast<unsigned int*>(R.chk + RING * 32);
+        R.pndOff = R.chkOff + RING * 32; R.pnd = reinterpret_cast<int*>(R.pndOff + RING * 32);
     }
 
     while (true) {

@@ -34,13 +34,19 @@ struct LsdbImgDyn {
 struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec logNFA
 
 // state word per scaled pixel (u32):
-//   bit 0   : usedMap == 1 (below gradient threshold, or member of an accepted region)
-//   bit 1   : usedMap == 2 (member of an NFA-rejected region)  [bit 0 wins]
-//   bit 8+w : pixel is in the region warp w of the owning CTA is currently growing (curMap)
+//   bit 0      : usedMap == 1 (below gradient threshold, or member of an accepted region)
+//   bit 1      : usedMap == 2 (member of an NFA-rejected region)  [bit 0 wins]
+//   bit 2 / 3  : pixel belongs to a PARKED (evaluated, not yet retired) accept / reject candidate.  Speculation by
+//                later seeds treats a parked accept as already banned and skips seeds inside either kind; whether
+//                that guess was right is re-checked pixel by pixel when the dependent evaluation retires.
+//   bits 4-19  : pixel is in the region warp w of the owning CTA is currently growing (curMap)
+//   bits 20-31 : seed-list chunk (mod 4096) of the seed whose parked region set bit 2/3 (the earliest one)
 #define LSDB_ST_BAN 1u
 #define LSDB_ST_REJ 2u
-#define LSDB_ST_HINT 4u    // pixel belongs to a parked (not yet retired) accept/reject candidate — speculation hint only
-#define LSDB_ST_WARP_SHIFT 8
+#define LSDB_ST_PACC 4u
+#define LSDB_ST_PREJ 8u
+#define LSDB_ST_WARP_SHIFT 4
+#define LSDB_ST_TAG_SHIFT 20
 
 #define LSDB_TILE 32            // stencil output tile (scaled pixels)
 #define LSDB_SRC_MAX 136        // max source-window edge of one tile
