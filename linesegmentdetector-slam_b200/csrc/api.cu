@@ -32,7 +32,7 @@ struct lsdb_batch {
     lsdb_ctx* ctx;
     int n;
     lsdb_lsd_params params;
-    int maxSeg, listCap, arenaCap, nTiles, nCtas, nWarps, runAhead, bmCapWords;
+    int maxSeg, listCap, arenaCap, nTiles, nCtas, nWarps, runAhead, bmCapWords, steal;
     size_t totalN, totalSrc, totalBan;
     std::vector<LsdbImg> imgs;
     LsdbLsdConst kc;
@@ -221,8 +221,10 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
                lsdb_grow_max_ctas(ctx->device, nw / 2, b->bmCapWords) > lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords)) nw >>= 1;
         if (getenv("LSDB_GROW_WARPS")) { int v = atoi(getenv("LSDB_GROW_WARPS")); if (v >= 1 && v <= LSDB_GROW_WARPS) nw = v; }
         b->nWarps = nw;
-        b->runAhead = 2 * LSDB_SUPER * nw;   // chunks a map's team may speculate ahead of its commit frontier
+        b->runAhead = 0;   // chunks a map's team may speculate ahead of its commit frontier (0 = as far as the ring allows)
         if (getenv("LSDB_RUNAHEAD")) b->runAhead = atoi(getenv("LSDB_RUNAHEAD"));
+        b->steal = 1;
+        if (getenv("LSDB_STEAL")) b->steal = atoi(getenv("LSDB_STEAL"));
         const int maxCtas = lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords);
         b->nCtas = n < maxCtas ? n : maxCtas;
         (void)sms;
@@ -234,8 +236,8 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     AL(b->bins, b->totalN * 2); AL(b->cells, b->totalN * 4); AL(b->labels, b->totalN * 4);
     AL(b->rects, (size_t)n * b->maxSeg * sizeof(LsdbRect)); AL(b->dyn, (size_t)n * sizeof(LsdbImgDyn));
     AL(b->imgsD, (size_t)n * sizeof(LsdbImg)); AL(b->tileImg, (size_t)b->nTiles * sizeof(int));
-    b->arenaCap = 2 * b->listCap < (1 << 15) ? (1 << 15) : 2 * b->listCap;
-    AL(b->lists, (size_t)b->nCtas * b->nWarps * lsdb_grow_list_words_per_warp(b->listCap, b->arenaCap) * 4);
+    b->arenaCap = 8 * b->listCap < (1 << 14) ? (1 << 14) : (8 * b->listCap > (1 << 16) ? (1 << 16) : 8 * b->listCap);  // per super-chunk in flight
+    AL(b->lists, (size_t)b->nCtas * lsdb_grow_words_per_cta(b->listCap, b->arenaCap, b->nWarps) * 4);
     AL(b->recBuf, (size_t)b->nCtas * lsdb_grow_rec_bytes_per_cta());
     AL(b->imgCounter, 64); AL(b->kcD, sizeof(LsdbLsdConst)); AL(b->banBits, (b->totalBan + 4) * 4);
 #undef AL
@@ -280,7 +282,7 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaEventRecord(b->ev[2], s));
     lsdb_launch_grow(s, b->n, b->nCtas, b->nWarps, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->cosm, b->sinm, b->state, b->cells, b->labels, b->rects,
                      b->maxSeg, b->lists, b->listCap, b->arenaCap, b->runAhead, b->recBuf, ctx->lgammaTab, ctx->lgammaN, b->imgCounter, b->banBits,
-                     b->bmCapWords);
+                     b->bmCapWords, b->steal);
     CK(ctx, cudaEventRecord(b->ev[3], s));
     CK(ctx, cudaGetLastError());
     b->ran = true; b->downloaded = false; b->launches = 3;

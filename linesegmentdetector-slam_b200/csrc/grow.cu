@@ -34,7 +34,7 @@
 
 #define NW_MAX LSDB_GROW_WARPS
 #define ARENA_HDR 32  // words: 13 doubles (rect + logNFA), nCommit, outcome
-#define LOG_CAP 512
+#define GRID 32            // coarse cells per axis of the accept grid
 #define FULL 0xffffffffu
 
 enum { OC_NONE = 0, OC_NOCHANGE = 1, OC_REJECT = 2, OC_ACCEPT = 3, OC_DEFER = 4 };
@@ -44,38 +44,47 @@ enum { ST_CELLS = 0, ST_LIVE, ST_GROWS, ST_GROWNPX, ST_SMALL, ST_REGROWS, ST_RRR
        TM_GROW = ST_N, TM_RECT, TM_NFA, TM_WAIT, TM_RETIRE, TM_SPEC, TM_RESPEC, TM_MAPCYC, TM_MAPNS, TM_SPARE, RS_NONE, RS_CONFLICT, RS_COMMIT, RS_LOST, RS_P0, RS_P1, RS_P2, RS_P3, TM_N };
 
 #define RING 512           // chunks a CTA may run ahead of the commit frontier
+#define NSLOTS (RING / LSDB_SUPER)
+#define LQ_CAP 256
 #define SG_CAP 32          // lane-per-seed growth handles regions below min(regThre, SG_CAP) pixels
 struct GrowShared {
     volatile int frontier;     // first chunk not yet retired
     int nextChunk;             // ticket counter
     int retireLock;
-    volatile int logCount;
     volatile int nSeg;
     volatile int abortFlag;
     int img;
     int nChunks;
     int nCells;
     volatile int chunkFlag[RING];            // 1 = evaluated, records parked
-    unsigned char chunkWarp[RING];           // which warp's arena holds the records
-    unsigned int chunkEnd[RING];             // that warp's virtual arena offset after the chunk
-    volatile unsigned int arenaTail[NW_MAX]; // virtual offset up to which warp w's arena is free again
-    unsigned int logBox[LOG_CAP][2];
-    unsigned long long logMask[LOG_CAP];
+    // every super-chunk in flight owns one record arena (slot = super-chunk index mod NSLOTS), filled by bump allocation
+    unsigned int slotHead[NSLOTS];
+    volatile int slotPending[NSLOTS];        // large seeds of the super-chunk that are queued or being evaluated
+    // large seeds found by the scouts, in (roughly) seed order; any warp of the team evaluates them
+    volatile unsigned int lq[LQ_CAP][2];     // pixel index, cell index
+    volatile unsigned int lqReady[LQ_CAP];   // sequence number + 1 once the entry is written
+    unsigned int lqHead, lqTail;
+    unsigned int grid[GRID * GRID];          // per coarse cell: 1 + index of the LAST accepted region that touched the cell
     unsigned long long stats[TM_N];
 };
 
 #define LSDB_REJ_CAP (1 << 16)   // words per reject list of grow_region (two per warp)
 #define LSDB_PND_CAP (1 << 12)   // words of the pending-dependency list per warp
 #define SG_PND 24                // same, per lane, in small_grow
-__host__ __device__ inline size_t grow_words_per_warp(int listCap, int arenaCap) {
-    return 3 * (size_t)listCap + 64 + (size_t)arenaCap + 2 * (size_t)LSDB_REJ_CAP + LSDB_PND_CAP;
+#define LSDB_Q_WORDS (2 * 32 * LSDB_SUPER)
+__host__ __device__ inline size_t grow_words_per_warp(int listCap) {
+    return 3 * (size_t)listCap + 64 + 2 * (size_t)LSDB_REJ_CAP + LSDB_PND_CAP + LSDB_Q_WORDS;
+}
+// per CTA: NSLOTS record arenas of arenaCap words, then the per-warp work buffers
+__host__ __device__ inline size_t grow_words_per_cta(int listCap, int arenaCap, int nw) {
+    return (size_t)NSLOTS * arenaCap + (size_t)nw * grow_words_per_warp(listCap);
 }
 // dynamic shared memory of the kernel: the ban plane, then 1 KB of staging per warp
 static inline size_t grow_dyn_smem(int bmCapWords, int warpsPerCta) { return (size_t)((bmCapWords + 1) & ~1) * 4 + (size_t)warpsPerCta * 1024; }
 
 struct Rect { double x1, y1, x2, y2, wid, cX, cY, deg, dx, dy, p, prec; };
 
-struct BBox { int x0, y0, x1, y1; unsigned long long mask; };  // mask: 8x8 coarse grid cells holding accepted pixels
+struct BBox { int x0, y0, x1, y1; };
 
 #if 1  /* cycle counters are cheap (one clock64 + one smem atomic per measured call) and feed bench.py */
 #define TIC long long t0_ = clock64()
@@ -96,9 +105,8 @@ struct WarpCtx {
     const double* sinm;
     unsigned int* list;     // working point list (packed y<<16|x), listCap words
     unsigned int* scratch;  // 2*listCap+64 words: result of a frontier (non-speculative) evaluation
-    unsigned int* arena;    // arenaCap words, ring: parked speculative results of this warp
-    unsigned int* listsBase;  // this CTA's first warp buffer (to reach other warps' arenas)
-    size_t warpStride;
+    unsigned int* arenas;   // NSLOTS record arenas of arenaCap words (parked speculative results, per super-chunk)
+    unsigned int* q;        // the scout's queue of live cells of its super-chunk
     int listCap, arenaCap;
     const LsdbLsdConst* kc;
     const double* lgammaTab;
@@ -108,20 +116,19 @@ struct WarpCtx {
     int rejCap;
     unsigned int* pnd;      // pixels the current speculative evaluation skipped because a PARKED accept covers them
     int npnd;               //   (must turn out banned for the evaluation to stand), LSDB_PND_CAP words; -1 = overflow
+    int steal;              // large seeds go through the team's queue (any warp evaluates them) instead of staying with the scout
     int specChunk;          // seed-list chunk of the seed being evaluated speculatively; -1 at the frontier (parked
                             //   regions are then ignored: the state is final)
     double* stage;          // 32 x 4 doubles of shared memory: operands of the ordered sums in rect_from_region
     volatile unsigned int* bm;   // shared-memory copy of the ban plane (usedMap==1), one bit per pixel, pw words per row; NULL: use `state`
     int pw;
     double logNT, regThre;
-    int cellShift;        // coarse-grid cell = 2^cellShift pixels, grid <= 8x8
+    int cellShift;        // accept-grid cell = 2^cellShift pixels, grid <= GRID x GRID
 };
 
-__device__ __forceinline__ unsigned long long cell_bit(int x, int y, int sh) { return 1ull << (((y >> sh) << 3) | (x >> sh)); }
 // add an accepted pixel (x,y) of a growing region: bounding box + coarse-grid cell
 __device__ __forceinline__ void bbox_add(const WarpCtx& c, BBox& b, int x, int y) {
     b.x0 = min(b.x0, x); b.y0 = min(b.y0, y); b.x1 = max(b.x1, x); b.y1 = max(b.y1, y);
-    b.mask |= cell_bit(x, y, c.cellShift);
 }
 
 // noinline wrappers keep one copy of each math routine in the kernel
@@ -421,7 +428,6 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
     for (int o = 16; o > 0; o >>= 1) {
         bb.x0 = min(bb.x0, __shfl_xor_sync(FULL, bb.x0, o)); bb.y0 = min(bb.y0, __shfl_xor_sync(FULL, bb.y0, o));
         bb.x1 = max(bb.x1, __shfl_xor_sync(FULL, bb.x1, o)); bb.y1 = max(bb.y1, __shfl_xor_sync(FULL, bb.y1, o));
-        bb.mask |= __shfl_xor_sync(FULL, bb.mask, o);
     }
     STAT(c, ST_GROWS, 1); STAT(c, ST_GROWNPX, num);
     TOC(c, TM_GROW);
@@ -808,7 +814,7 @@ __device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wa
     const LsdbLsdConst* kc = c.kc;
     const int W = c.W;
     const int sx = p0 % W, sy = p0 / W;
-    bb.x0 = bb.y0 = 0x7fffffff; bb.x1 = bb.y1 = -1; bb.mask = 0ull;
+    bb.x0 = bb.y0 = 0x7fffffff; bb.x1 = bb.y1 = -1;
     used = 0;
     chk = -1;
     double regDeg = c.deg[p0];
@@ -992,19 +998,15 @@ __device__ bool any_banned(const WarpCtx& c, const unsigned int* px, int n) {
     return __any_sync(FULL, hit);
 }
 
-// coarse filter: any ACCEPT logged in [L0, logCount) whose bounding box AND coarse-cell mask overlap
-// those of the pixels this evaluation accepted?  (conservative: never misses an overlap)
-__device__ bool has_conflict(const WarpCtx& c, int L0, unsigned int bb0, unsigned int bb1, unsigned long long mask) {
-    const int L1 = c.sh->logCount;
-    if (L1 - L0 > LOG_CAP) return true;
-    const int ax0 = (int)(bb0 & 0xffff), ay0 = (int)(bb0 >> 16), ax1 = (int)(bb1 & 0xffff), ay1 = (int)(bb1 >> 16);
-    bool hit = false;
-    for (int e = L0 + c.lane; e < L1; e += 32) {
-        const unsigned int b0 = c.sh->logBox[e & (LOG_CAP - 1)][0], b1 = c.sh->logBox[e & (LOG_CAP - 1)][1];
-        const int bx0 = b0 & 0xffff, by0 = b0 >> 16, bx1 = b1 & 0xffff, by1 = b1 >> 16;
-        if (bx0 <= ax1 && bx1 >= ax0 && by0 <= ay1 && by1 >= ay0 && (c.sh->logMask[e & (LOG_CAP - 1)] & mask)) hit = true;
-    }
-    return __any_sync(FULL, hit);
+// Has a region been accepted, since `L0` regions had been accepted, anywhere near the box [b0,b1]?  Conservative
+// (never misses an overlap): decided per cell of the coarse accept grid.
+__device__ __forceinline__ bool grid_hit(const WarpCtx& c, unsigned int b0, unsigned int b1, int L0) {
+    const int sh = c.cellShift;
+    const int cx0 = px_of(b0) >> sh, cy0 = py_of(b0) >> sh, cx1 = px_of(b1) >> sh, cy1 = py_of(b1) >> sh;
+    for (int cy = cy0; cy <= cy1; cy++)
+        for (int cx = cx0; cx <= cx1; cx++)
+            if (*(volatile unsigned int*)&c.sh->grid[cy * GRID + cx] > (unsigned int)L0) return true;
+    return false;
 }
 
 // commit the result record at `recp`, at the frontier (:242-271)
@@ -1023,23 +1025,16 @@ __device__ void commit_region(WarpCtx& c, const unsigned int* recp, int* labels,
         return;
     }
     const int idx = sh->nSeg;
-    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
-    unsigned long long mask = 0ull;
     for (int k = c.lane; k < nCommit; k += 32) {
         const unsigned int v = px[k];
         const size_t p = (size_t)py_of(v) * W + px_of(v);
         atomicOr(&c.state[p], LSDB_ST_BAN);
         ban_set(c, px_of(v), py_of(v));
         labels[p] += idx + 1;  // regIdx += curMap*(regCnt+1), :261 (int32 here, u8 there)
-        x0 = min(x0, px_of(v)); y0 = min(y0, py_of(v)); x1 = max(x1, px_of(v)); y1 = max(y1, py_of(v));
-        mask |= cell_bit(px_of(v), py_of(v), c.cellShift);
+        atomicMax(&sh->grid[(py_of(v) >> c.cellShift) * GRID + (px_of(v) >> c.cellShift)], (unsigned int)idx + 1u);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        x0 = min(x0, __shfl_xor_sync(FULL, x0, o)); y0 = min(y0, __shfl_xor_sync(FULL, y0, o));
-        x1 = max(x1, __shfl_xor_sync(FULL, x1, o)); y1 = max(y1, __shfl_xor_sync(FULL, y1, o));
-        mask |= __shfl_xor_sync(FULL, mask, o);
-    }
+    __syncwarp();
+    __threadfence_block();
     if (c.lane == 0) {
         if (idx < maxSeg) {
             const double* hd = reinterpret_cast<const double*>(recp);
@@ -1056,12 +1051,6 @@ __device__ void commit_region(WarpCtx& c, const unsigned int* recp, int* labels,
         } else {
             sh->abortFlag = LSDB_ERR_CAPACITY;
         }
-        const int L = sh->logCount;
-        sh->logBox[L & (LOG_CAP - 1)][0] = pack_xy(x0, y0);
-        sh->logBox[L & (LOG_CAP - 1)][1] = pack_xy(x1, y1);
-        sh->logMask[L & (LOG_CAP - 1)] = mask;
-        __threadfence_block();
-        sh->logCount = L + 1;
         sh->nSeg = idx + 1;
         atomicAdd(&sh->stats[ST_ACCEPTS], 1ull);
     }
@@ -1081,17 +1070,12 @@ struct ChunkRecs {
 };
 #define REC_BYTES_PER_CELL 48
 
-// contiguous room for `need` words in this warp's arena ring; returns the physical offset or -1 (h2 = new virtual head base)
-__device__ __forceinline__ int arena_room(const WarpCtx& c, unsigned int head, unsigned int need, unsigned int& h2, int& avail) {
-    const unsigned int cap = (unsigned int)c.arenaCap;
-    const unsigned int tail = c.sh->arenaTail[c.w];
-    unsigned int phys = head % cap;
-    unsigned int room = cap - phys;                   // contiguous words at phys
-    h2 = head;
-    if (room < need && cap - (head + room - tail) >= need) { h2 = head + room; phys = 0; room = cap; }
-    const unsigned int freeW = cap - (h2 - tail);     // words not holding parked records
-    avail = (int)min(room, freeW);
-    return avail >= (int)need ? (int)phys : -1;
+// `need` words in the record arena of super-chunk slot `slot` (warp-uniform call); -1 when the arena is full
+__device__ __forceinline__ int slot_alloc(const WarpCtx& c, int slot, int need) {
+    int off = 0;
+    if (c.lane == 0) off = (int)atomicAdd(&c.sh->slotHead[slot], (unsigned int)((need + 1) & ~1));
+    off = __shfl_sync(FULL, off, 0);
+    return off + need <= c.arenaCap ? off : -1;
 }
 
 // should speculation leave this seed alone?  used (:222), or inside a region that an earlier seed has parked
@@ -1099,20 +1083,93 @@ __device__ __forceinline__ bool seed_taken(unsigned int st, int chunk) {
     return (st & 3u) != 0 || pend_applies(st, LSDB_ST_PACC | LSDB_ST_PREJ, chunk);
 }
 
-// Speculative evaluation of the live seeds of `nSub` consecutive chunks (up to 256 cells); parks the results and flags
-// the chunks READY.
+// the map's abort flag as ONE value for the whole warp (a per-lane read of the volatile flag could split the warp)
+__device__ __forceinline__ int aborted(const WarpCtx& c) {
+    int v = 0;
+    if (c.lane == 0) v = c.sh->abortFlag;
+    return __shfl_sync(FULL, v, 0);
+}
+
+// record arena of the super-chunk that holds chunk `chunk`
+__device__ __forceinline__ int slot_of_chunk(int chunk) { return (chunk / LSDB_SUPER) & (NSLOTS - 1); }
+
+// One large seed (cell ci, pixel p), speculatively, with the whole warp: grow, rectangle, refine, NFA; the result is
+// parked in the record arena of the seed's super-chunk.  Any warp of the team may run this for any queued seed.
+__device__ void eval_large(WarpCtx& c, int p, int ci, const ChunkRecs& R) {
+    GrowShared& sh = *c.sh;
+    const int chunkJ = ci >> 5;
+    {   // one read for the whole warp: the word changes under our feet (other warps park regions)
+        int taken = 0;
+        if (c.lane == 0) taken = seed_taken(lsdb_ld_state(&c.state[p]), chunkJ);
+        if (__shfl_sync(FULL, taken, 0)) return;   // swallowed by a region parked a moment ago: stays OC_NONE
+    }
+    BBox bb; int used = 0, chk = -1, pndOff, pndN;
+    const int L1 = sh.nSeg;
+    __threadfence_block();
+    c.specChunk = chunkJ;
+    const int oc = eval_seed(c, p, c.scratch, 2 * c.listCap + 64, true, bb, used, chk, pndOff, pndN);
+    c.specChunk = -1;
+    STAT(c, ST_SPEC, 1);
+    if (oc == OC_DEFER) return;
+    const int slot = slot_of_chunk(chunkJ);
+    const int off = slot_alloc(c, slot, used);
+    if (off < 0) {   // arena full: decided at the frontier; take the marks back
+        if (oc == OC_ACCEPT || oc == OC_REJECT) unpark_pixels(c, c.scratch + c.scratch[28], (int)c.scratch[26], chunkJ);
+        return;
+    }
+    unsigned int* dst = c.arenas + (size_t)slot * c.arenaCap + off;
+    for (int k = c.lane; k < used; k += 32) dst[k] = c.scratch[k];
+    __syncwarp();
+    if (c.lane == 0) {
+        const size_t ri = (size_t)(chunkJ & (RING - 1)) * 32 + (ci & 31);
+        R.L0[ri] = L1; R.b0[ri] = pack_xy(bb.x0, bb.y0); R.b1[ri] = pack_xy(bb.x1, bb.y1); 
+        R.off[ri] = (unsigned int)off; R.chk[ri] = chk; R.chkOff[ri] = (unsigned int)off + ARENA_HDR;
+        R.pnd[ri] = pndN; R.pndOff[ri] = (unsigned int)(off + pndOff);
+        R.oc[ri] = oc;
+    }
+    __syncwarp();
+}
+
+// take one queued large seed, if any, and evaluate it; false = queue empty
+__device__ bool help_large(WarpCtx& c, const ChunkRecs& R) {
+    GrowShared& sh = *c.sh;
+    unsigned int p = 0, ci = 0;
+    int got = 0;
+    if (c.lane == 0) {
+        while (true) {
+            const unsigned int h = *(volatile unsigned int*)&sh.lqHead;
+            if (h == *(volatile unsigned int*)&sh.lqTail) break;
+            const int e = h & (LQ_CAP - 1);
+            if (sh.lqReady[e] != h + 1) break;            // reserved, not written yet
+            p = sh.lq[e][0]; ci = sh.lq[e][1];
+            if (atomicCAS(&sh.lqHead, h, h + 1) == h) { got = 1; break; }
+        }
+    }
+    got = __shfl_sync(FULL, got, 0);
+    if (!got) return false;
+    p = __shfl_sync(FULL, p, 0); ci = __shfl_sync(FULL, ci, 0);
+    eval_large(c, (int)p, (int)ci, R);
+    __threadfence();   // record visible before the super-chunk can be flagged ready
+    if (c.lane == 0) atomicSub((int*)&sh.slotPending[slot_of_chunk((int)ci >> 5)], 1);
+    __syncwarp();
+    return true;
+}
+
+// Speculative evaluation of the live seeds of `nSub` consecutive chunks (one super-chunk, up to 256 cells); parks the
+// results and flags the chunks READY.
 //   A  collect the live cells (seed order) into a queue; then, 32 queued seeds at a time:
 //   B  one seed per LANE: small_grow decides the ~97 % of seeds whose region stays below regThre ("no change"; the
 //      accepted pixels are parked for re-validation) and flags the rest as large;
-//   C  the large seeds of the group, in order, one at a time with the whole warp (grow, rectangle, refine, NFA).  Each
-//      result is parked before the next seed starts, so later seeds already see it as a pending accept / reject.
-__device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned int* cl, int nCells, const ChunkRecs& R, unsigned int& head, int T) {
+//   C  the large seeds of the group go to the team's queue, where ANY warp picks them up (this warp helps until its
+//      own are done), so that a stretch of the seed list that is rich in large regions does not serialise on one warp.
+//      Each result is parked — its pixels marked pending — before the group that follows is scouted.
+__device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned int* cl, int nCells, const ChunkRecs& R, int T) {
     GrowShared& sh = *c.sh;
     const int lane = c.lane;
     const unsigned int lt = (1u << lane) - 1u;
     long long tSpec = clock64();
-    const unsigned int head0 = head;
-    unsigned int* q = c.scratch;   // [2k] pixel index, [2k+1] (sub << 5 | lane) | large flag
+    const int slot = slot_of_chunk(chunk0);
+    unsigned int* q = c.q;   // [2k] pixel index, [2k+1] (sub << 5 | lane)
     int qn = 0;
     for (int s = 0; s < nSub; s++) {   // ---- A
         const int ci = (chunk0 + s) * LSDB_CHUNK + lane;
@@ -1128,8 +1185,7 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
         R.oc[(size_t)((chunk0 + s) & (RING - 1)) * 32 + lane] = OC_NONE;
     }
     __syncwarp();
-    BBox bb; int used = 0, chk = -1;
-    for (int base = 0; base < qn && !sh.abortFlag; base += 32) {
+    for (int base = 0; base < qn && !aborted(c); base += 32) {
         // ---- B
         const int k = base + lane;
         bool act = k < qn;
@@ -1141,7 +1197,7 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
         unsigned int pnd[SG_PND];
         int num = 0, npnd = 0;
         bool large = act;
-        const int L0 = sh.logCount;
+        const int L0 = sh.nSeg;
         __threadfence_block();
         if (act && T <= SG_CAP) {
             num = small_grow(c, myp, T, lst, myChunk, pnd, npnd);
@@ -1158,20 +1214,19 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
             if (lane >= o) incl += t;
         }
         const int tot = __shfl_sync(FULL, incl, 31);
-        unsigned int h2; int avail;
-        const int phys = tot > 0 ? arena_room(c, head, (unsigned int)tot + 2u, h2, avail) : -1;
-        if (small && phys >= 0) {
+        const int off = tot > 0 ? slot_alloc(c, slot, tot) : -1;
+        if (small && off >= 0) {
             const size_t ri = (size_t)(myChunk & (RING - 1)) * 32 + (rel & 31u);
-            BBox sb; sb.x0 = sb.y0 = 0x7fffffff; sb.x1 = sb.y1 = -1; sb.mask = 0ull;
-            unsigned int* dst = c.arena + phys + (incl - need);
+            BBox sb; sb.x0 = sb.y0 = 0x7fffffff; sb.x1 = sb.y1 = -1;
+            const int mine = off + (incl - need);
+            unsigned int* dst = c.arenas + (size_t)slot * c.arenaCap + mine;
             for (int j = 0; j < num; j++) { dst[j] = lst[j]; bbox_add(c, sb, px_of(lst[j]), py_of(lst[j])); }
             for (int j = 0; j < npnd; j++) dst[num + j] = pnd[j];
-            R.L0[ri] = L0; R.b0[ri] = pack_xy(sb.x0, sb.y0); R.b1[ri] = pack_xy(sb.x1, sb.y1); R.mask[ri] = sb.mask;
-            R.off[ri] = 0; R.chk[ri] = num; R.chkOff[ri] = (unsigned int)(phys + (incl - need));
-            R.pnd[ri] = npnd; R.pndOff[ri] = (unsigned int)(phys + (incl - need) + num);
+            R.L0[ri] = L0; R.b0[ri] = pack_xy(sb.x0, sb.y0); R.b1[ri] = pack_xy(sb.x1, sb.y1); 
+            R.off[ri] = 0; R.chk[ri] = num; R.chkOff[ri] = (unsigned int)mine;
+            R.pnd[ri] = npnd; R.pndOff[ri] = (unsigned int)(mine + num);
             R.oc[ri] = OC_NOCHANGE;
         }   // else: arena full / too many dependencies — this seed is decided at the frontier
-        if (phys >= 0) head = h2 + (unsigned int)((tot + 1) & ~1);
         const unsigned int largeMask = __ballot_sync(FULL, act && large);
         const unsigned int nSmall = __popc(__ballot_sync(FULL, small));
         int pxs = small ? num : 0;
@@ -1182,40 +1237,48 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
             atomicAdd(&sh.stats[ST_SMALL], (unsigned long long)nSmall); atomicAdd(&sh.stats[ST_GROWNPX], (unsigned long long)pxs);
         }
         // ---- C
-        unsigned int todo = largeMask;
-        while (todo && !sh.abortFlag) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int p = __shfl_sync(FULL, myp, j);
-            const unsigned int relJ = __shfl_sync(FULL, rel, j);
-            const int chunkJ = chunk0 + (int)(relJ >> 5);
-            if (seed_taken(lsdb_ld_state(&c.state[p]), chunkJ)) continue;   // swallowed by a region parked a moment ago
-            unsigned int h3; int av;
-            const int ph = arena_room(c, head, 4096u, h3, av);
-            if (ph < 0) continue;                             // arena full: this seed is decided at the frontier
-            const int L1 = sh.logCount;
-            __threadfence_block();
-            int pndOff, pndN;
-            c.specChunk = chunkJ;
-            const int oc = eval_seed(c, p, c.arena + ph, av, true, bb, used, chk, pndOff, pndN);
-            c.specChunk = -1;
-            STAT(c, ST_SPEC, 1);
-            if (oc == OC_DEFER) continue;
+        const int nL = __popc(largeMask);
+        if (nL) {
+            // reserve nL queue entries (lane 0), publish them in seed order
+            unsigned int t0 = 0;
+            int ok = 0;
             if (lane == 0) {
-                const size_t ri = (size_t)(chunkJ & (RING - 1)) * 32 + (relJ & 31u);
-                R.L0[ri] = L1; R.b0[ri] = pack_xy(bb.x0, bb.y0); R.b1[ri] = pack_xy(bb.x1, bb.y1); R.mask[ri] = bb.mask;
-                R.off[ri] = (unsigned int)ph; R.chk[ri] = chk; R.chkOff[ri] = (unsigned int)ph + ARENA_HDR;
-                R.pnd[ri] = pndN; R.pndOff[ri] = (unsigned int)(ph + pndOff);
-                R.oc[ri] = oc;
+                while (true) {
+                    const unsigned int t = *(volatile unsigned int*)&sh.lqTail;
+                    const unsigned int h = *(volatile unsigned int*)&sh.lqHead;
+                    if (!c.steal || t + nL - h > LQ_CAP) break;
+                    if (atomicCAS(&sh.lqTail, t, t + nL) == t) { t0 = t; ok = 1; atomicAdd((int*)&sh.slotPending[slot], nL); break; }
+                }
             }
-            head = h3 + (unsigned int)used;
+            ok = __shfl_sync(FULL, ok, 0); t0 = __shfl_sync(FULL, t0, 0);
+            if (ok) {
+                if (act && large) {
+                    const unsigned int seq = t0 + __popc(largeMask & lt);
+                    const int e = seq & (LQ_CAP - 1);
+                    sh.lq[e][0] = (unsigned int)myp;
+                    sh.lq[e][1] = (unsigned int)(myChunk * LSDB_CHUNK + (int)(rel & 31u));
+                    __threadfence_block();
+                    sh.lqReady[e] = seq + 1;
+                }
+                __syncwarp();
+                while (true) {
+                    int pend = 0;
+                    if (lane == 0) pend = sh.slotPending[slot] != 0 && !sh.abortFlag;
+                    if (!__shfl_sync(FULL, pend, 0)) break;
+                    if (!help_large(c, R)) __nanosleep(100);
+                }
+            } else {   // queue full: evaluate them here
+                unsigned int todo = largeMask;
+                while (todo && !aborted(c)) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int p = __shfl_sync(FULL, myp, j);
+                    const unsigned int relJ = __shfl_sync(FULL, rel, j);
+                    eval_large(c, p, (chunk0 + (int)(relJ >> 5)) * LSDB_CHUNK + (int)(relJ & 31u), R);
+                }
+            }
         }
         __syncwarp();
-    }
-    if (lane < nSub) {
-        const int slot = (chunk0 + lane) & (RING - 1);
-        sh.chunkWarp[slot] = (unsigned char)c.w;
-        sh.chunkEnd[slot] = lane == nSub - 1 ? head : head0;   // the arena space is released when the last chunk retires
     }
     if (lane == 0) atomicAdd(&sh.stats[TM_SPEC], (unsigned long long)(clock64() - tSpec));
     __threadfence();   // records + arena contents visible before the flags
@@ -1223,18 +1286,25 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
     if (lane < nSub) sh.chunkFlag[(chunk0 + lane) & (RING - 1)] = 1;
 }
 
-// does log entry e overlap the accepted-pixel bbox/mask of a parked evaluation?
-__device__ __forceinline__ bool log_hit(const GrowShared& sh, int e, unsigned int bb0, unsigned int bb1, unsigned long long mask) {
-    const unsigned int b0 = sh.logBox[e & (LOG_CAP - 1)][0], b1 = sh.logBox[e & (LOG_CAP - 1)][1];
-    const int bx0 = b0 & 0xffff, by0 = b0 >> 16, bx1 = b1 & 0xffff, by1 = b1 >> 16;
-    const int ax0 = (int)(bb0 & 0xffff), ay0 = (int)(bb0 >> 16), ax1 = (int)(bb1 & 0xffff), ay1 = (int)(bb1 >> 16);
-    return bx0 <= ax1 && bx1 >= ax0 && by0 <= ay1 && by1 >= ay0 && (sh.logMask[e & (LOG_CAP - 1)] & mask) != 0ull;
-}
-
 // retire one READY chunk at the frontier: in seed order, validate or re-evaluate, commit.
 // The common case — seed still live, parked outcome "no change", no accepted region since the evaluation
 // started anywhere near it — is decided for all 32 cells at once (one state load, one pass over the log);
 // only commits, coarse-filter hits and missing evaluations are walked serially, in order.
+// Lane-level validation of a parked "no change" result whose pixel lists are short (the lane-per-seed evaluations):
+// every pixel it accepted must still be un-banned (looked at only when a region was accepted nearby since), and every
+// pixel it skipped because of a parked accept must be banned by now.
+__device__ __forceinline__ bool lane_valid(const WarpCtx& c, const unsigned int* earena, bool hit, int nchk, unsigned int chkOff,
+                                           int npnd, unsigned int pndOff) {
+    bool ok = true;
+    if (hit) {
+        const unsigned int* px = earena + chkOff;
+        for (int j = 0; j < nchk; j++) ok = ok && !ban_at(c, px_of(px[j]), py_of(px[j]));
+    }
+    const unsigned int* pp = earena + pndOff;
+    for (int j = 0; j < npnd; j++) ok = ok && ban_at(c, px_of(pp[j]), py_of(pp[j]));
+    return ok;
+}
+
 __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int nCells, const ChunkRecs& R, int* lab, LsdbRect* rc, int maxSeg) {
     GrowShared& sh = *c.sh;
     const int lane = c.lane;
@@ -1244,21 +1314,18 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
     const size_t ri = (size_t)slot * 32 + lane;
     const int recOc = R.oc[ri], recL0 = R.L0[ri], recChk = R.chk[ri];
     const unsigned int recB0 = R.b0[ri], recB1 = R.b1[ri], recOff = R.off[ri], recChkOff = R.chkOff[ri];
-    const unsigned long long recMask = R.mask[ri];
     const int recPnd = recOc != OC_NONE ? R.pnd[ri] : 0;
     const unsigned int recPndOff = R.pndOff[ri];
     bool committedParked = false;   // this lane's parked accept / reject was committed as parked
-    const int ew = sh.chunkWarp[slot];
-    const unsigned int* earena = c.listsBase + (size_t)ew * c.warpStride + c.listCap + (2 * (size_t)c.listCap + 64);
+    const unsigned int* earena = c.arenas + (size_t)slot_of_chunk(chunk) * c.arenaCap;
     bool live = myp >= 0 && (lsdb_ld_state(&c.state[myp]) & 3u) == 0;   // :222
-    int logSeen = sh.logCount;
-    bool hit = false;
-    if (live && recOc != OC_NONE) {
-        if (logSeen - recL0 > LOG_CAP) hit = true;
-        else for (int e = recL0; e < logSeen && !hit; e++) hit = log_hit(sh, e, recB0, recB1, recMask);
-    }
+    // short "no change" records are validated by their own lane, in parallel; commits, long records, failed and
+    // missing evaluations are walked serially, in seed order
+    const bool laneCheck = recOc == OC_NOCHANGE && recChk >= 0 && recChk + recPnd <= 64;
+    bool laneOK = false;
+    if (live && laneCheck) laneOK = lane_valid(c, earena, grid_hit(c, recB0, recB1, recL0), recChk, recChkOff, recPnd, recPndOff);
     unsigned int liveAtTurn = __ballot_sync(FULL, live);
-    unsigned int work = __ballot_sync(FULL, live && !(recOc == OC_NOCHANGE && !hit && recPnd == 0));
+    unsigned int work = __ballot_sync(FULL, live && !(laneCheck && laneOK));
     BBox bb; int used = 0, chk = -1;
     while (work) {
         const int k = __ffs(work) - 1;
@@ -1266,10 +1333,11 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
         const int p = __shfl_sync(FULL, myp, k);
         const int oc = __shfl_sync(FULL, recOc, k);
         const unsigned int* recp = earena + __shfl_sync(FULL, recOff, k);
-        bool valid = oc != OC_NONE;
-        if (valid && __shfl_sync(FULL, (int)hit, k)) {   // coarse filter hit: look at the accepted pixels themselves
+        bool valid = oc != OC_NONE && !__shfl_sync(FULL, (int)laneCheck, k);   // a lane-checked record that got here has failed
+        if (valid) {
             const int nchk = __shfl_sync(FULL, recChk, k);
-            valid = nchk >= 0 && !any_banned(c, earena + __shfl_sync(FULL, recChkOff, k), nchk);
+            const bool hit = grid_hit(c, __shfl_sync(FULL, recB0, k), __shfl_sync(FULL, recB1, k), __shfl_sync(FULL, recL0, k));
+            if (hit) valid = nchk >= 0 && !any_banned(c, earena + __shfl_sync(FULL, recChkOff, k), nchk);
         }
         if (valid) {   // every pixel the evaluation took for banned because of a parked accept must be banned by now
             const int npn = __shfl_sync(FULL, recPnd, k);
@@ -1289,21 +1357,18 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
             if (oc2 == OC_DEFER) { sh.abortFlag = LSDB_ERR_CAPACITY; break; }
             if (oc2 == OC_REJECT || oc2 == OC_ACCEPT) { commit_region(c, c.scratch, lab, rc, maxSeg); changed = true; }
             if (lane == 0) atomicAdd(&sh.stats[TM_RESPEC], (unsigned long long)(clock64() - t0));
-            if (sh.abortFlag) break;
+            if (aborted(c)) break;
         }
         if (changed && (work != 0 || (liveAtTurn >> (k + 1)) != 0)) {
             // usedMap changed: refresh the cells that come after k in this chunk
             __threadfence_block();
             if (lane > k && live) {
                 live = (lsdb_ld_state(&c.state[myp]) & 3u) == 0;
-                const int L1 = sh.logCount;
-                if (live && recOc != OC_NONE && !hit)
-                    for (int e = logSeen; e < L1 && !hit; e++) hit = log_hit(sh, e, recB0, recB1, recMask);
+                if (live && laneCheck) laneOK = lane_valid(c, earena, grid_hit(c, recB0, recB1, recL0), recChk, recChkOff, recPnd, recPndOff);
             }
-            logSeen = sh.logCount;
             const unsigned int later = ~((2u << k) - 1u);
             liveAtTurn = (liveAtTurn & ~later) | (__ballot_sync(FULL, live) & later);
-            work = __ballot_sync(FULL, lane > k && live && !(recOc == OC_NOCHANGE && !hit && recPnd == 0));
+            work = __ballot_sync(FULL, lane > k && live && !(laneCheck && laneOK));
         }
     }
     // parked accepts / rejects that were not committed as parked (seed dead at its turn, or evaluation invalidated):
@@ -1331,15 +1396,16 @@ __device__ void try_retire(WarpCtx& c, const unsigned int* cl, int nCells, int n
     if (!go) return;
     long long t0 = clock64();
     __threadfence_block();
-    while (!sh.abortFlag) {
-        const int f = sh.frontier;
-        if (f >= nChunks || sh.chunkFlag[f & (RING - 1)] != 1) break;
+    while (!aborted(c)) {
+        int f = 0, ready = 0;
+        if (c.lane == 0) { f = sh.frontier; ready = f < nChunks && sh.chunkFlag[f & (RING - 1)] == 1; }
+        f = __shfl_sync(FULL, f, 0);
+        if (!__shfl_sync(FULL, ready, 0)) break;
         __threadfence();
         retire_chunk(c, f, cl, nCells, R, lab, rc, maxSeg);
         __threadfence_block();
         if (c.lane == 0) {
             const int slot = f & (RING - 1);
-            sh.arenaTail[sh.chunkWarp[slot]] = sh.chunkEnd[slot];   // that warp's parked records up to here are dead
             sh.chunkFlag[slot] = 0;
             atomicAdd(&sh.stats[ST_CHUNKS], 1ull);
             __threadfence_block();
@@ -1363,7 +1429,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
                                                                    LsdbRect* __restrict__ rects, int maxSeg, unsigned int* __restrict__ lists,
                                                                    int listCap, int arenaCap, int runAhead, unsigned char* __restrict__ recBuf,
                                                                    const double* __restrict__ lgammaTab, int lgammaN, int* __restrict__ imgCounter,
-                                                                   const unsigned int* __restrict__ banBits, int bmCapWords) {
+                                                                   const unsigned int* __restrict__ banBits, int bmCapWords, int steal) {
     __shared__ GrowShared sh;
     extern __shared__ unsigned int bmShared[];   // the map's ban plane, one bit per pixel (bmCapWords words)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
@@ -1372,14 +1438,14 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
     c.kc = kc; c.lgammaTab = lgammaTab; c.lgammaN = lgammaN; c.sh = &sh;
     c.listCap = listCap; c.arenaCap = arenaCap;
     c.rejCap = LSDB_REJ_CAP;
-    c.warpStride = grow_words_per_warp(listCap, arenaCap);
-    c.listsBase = lists + (size_t)blockIdx.x * nw * c.warpStride;
-    c.list = c.listsBase + (size_t)w * c.warpStride;
+    c.arenas = lists + (size_t)blockIdx.x * grow_words_per_cta(listCap, arenaCap, nw);
+    c.list = c.arenas + (size_t)NSLOTS * arenaCap + (size_t)w * grow_words_per_warp(listCap);
     c.scratch = c.list + listCap;
-    c.arena = c.scratch + 2 * (size_t)listCap + 64;
-    c.rej[0] = c.arena + arenaCap;
+    c.rej[0] = c.scratch + 2 * (size_t)listCap + 64;
     c.rej[1] = c.rej[0] + LSDB_REJ_CAP;
     c.pnd = c.rej[1] + LSDB_REJ_CAP; c.npnd = 0; c.specChunk = -1;
+    c.q = c.pnd + LSDB_PND_CAP;
+    c.steal = steal;
     c.stage = reinterpret_cast<double*>(bmShared + ((bmCapWords + 1) & ~1)) + (size_t)w * 128;
     ChunkRecs R;
     {
@@ -1397,13 +1463,16 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
             const int img = atomicAdd(imgCounter, 1);
             sh.img = img;
             if (img < nImgs) {
-                sh.frontier = 0; sh.nextChunk = 0; sh.logCount = 0; sh.nSeg = 0; sh.abortFlag = 0; sh.retireLock = 0;
+                sh.frontier = 0; sh.nextChunk = 0; sh.nSeg = 0; sh.abortFlag = 0; sh.retireLock = 0;
                 sh.nCells = dyn[img].nCells;
                 sh.nChunks = (sh.nCells + LSDB_CHUNK - 1) / LSDB_CHUNK;
             }
         }
         if (tid < TM_N) sh.stats[tid] = 0;
-        if (tid < NW_MAX) sh.arenaTail[tid] = 0;
+        if (tid < NSLOTS) { sh.slotHead[tid] = 0; sh.slotPending[tid] = 0; }
+        for (int i = tid; i < LQ_CAP; i += blockDim.x) sh.lqReady[i] = 0;
+        for (int i = tid; i < GRID * GRID; i += blockDim.x) sh.grid[i] = 0;
+        if (tid == 0) { sh.lqHead = 0; sh.lqTail = 0; }
         for (int i = tid; i < RING; i += blockDim.x) sh.chunkFlag[i] = 0;
         __syncthreads();
         const int img = sh.img;
@@ -1414,7 +1483,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
         c.W = im.W; c.H = im.H; c.logNT = im.logNT; c.regThre = im.regThre;
         {
             int k = 0;
-            while (((max(im.W, im.H) - 1) >> k) > 7) k++;
+            while (((max(im.W, im.H) - 1) >> k) > GRID - 1) k++;
             c.cellShift = k;
         }
         c.state = state + im.nOff; c.deg = deg + im.nOff; c.mag = mag + im.nOff; c.cosm = cosm + im.nOff; c.sinm = sinm + im.nOff;
@@ -1435,22 +1504,23 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
         const unsigned int* cl = cells + im.nOff;
         LsdbRect* rc = rects + im.segOff;
         const int nCells = sh.nCells, nChunks = sh.nChunks;
-        unsigned int head = 0;      // this warp's virtual arena write offset
         unsigned int idle = 0;
 
-        while (!sh.abortFlag) {
+        while (!aborted(c)) {
             try_retire(c, cl, nCells, nChunks, R, lab, rc, maxSeg);
-            if (sh.frontier >= nChunks) break;
+            if (__shfl_sync(FULL, (int)sh.frontier, 0) >= nChunks) break;
             int chunk = -1;
             if (lane == 0) {
                 // claim a ticket only while the ring has room
                 if (sh.nextChunk < nChunks && sh.nextChunk - sh.frontier < runAhead) {
                     chunk = atomicAdd(&sh.nextChunk, LSDB_SUPER);
                     if (chunk >= nChunks) chunk = -1;
-                }
+                    else { sh.slotHead[slot_of_chunk(chunk)] = 0; sh.slotPending[slot_of_chunk(chunk)] = 0; }   // the slot's previous
+                }                                                                                              // super-chunk has retired
             }
             chunk = __shfl_sync(FULL, chunk, 0);
-            if (chunk < 0) {   // nothing to claim: wait for the frontier to move (or for work to drain)
+            if (chunk < 0) {   // nothing to claim: help with queued large seeds, else wait for the frontier to move
+                if (help_large(c, R)) { idle = 0; continue; }
                 long long tw = clock64();
                 __nanosleep(200);
                 if (lane == 0) {
@@ -1461,7 +1531,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
                 continue;
             }
             idle = 0;
-            speculate_super(c, chunk, min(LSDB_SUPER, nChunks - chunk), cl, nCells, R, head, T);
+            speculate_super(c, chunk, min(LSDB_SUPER, nChunks - chunk), cl, nCells, R, T);
         }
         __syncthreads();
         if (tid == 0) {
@@ -1488,8 +1558,8 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
                       unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
-                      int* imgCounter, const unsigned int* banBits, int bmCapWords) {
-    if (runAhead > RING - (NW_MAX + 1) * LSDB_SUPER) runAhead = RING - (NW_MAX + 1) * LSDB_SUPER;
+                      int* imgCounter, const unsigned int* banBits, int bmCapWords, int steal) {
+    if (runAhead <= 0 || runAhead > RING - (NW_MAX + 1) * LSDB_SUPER) runAhead = RING - (NW_MAX + 1) * LSDB_SUPER;
     if (runAhead < 1) runAhead = 1;
     static int attrSet = -1;
     if (attrSet < bmCapWords) {
@@ -1499,10 +1569,10 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
     if (nImgs > 0)
         lsdb_grow_kernel<<<nCtas, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta), s>>>(nImgs, imgs, dyn, kc, mag, deg, cosm, sinm, state, cells, labels, rects,
                                                                                 maxSeg, lists, listCap, arenaCap, runAhead, recBuf, lgammaTab, lgammaN,
-                                                                                imgCounter, banBits, bmCapWords);
+                                                                                imgCounter, banBits, bmCapWords, steal);
 }
 
-size_t lsdb_grow_list_words_per_warp(int listCap, int arenaCap) { return grow_words_per_warp(listCap, arenaCap); }
+size_t lsdb_grow_words_per_cta(int listCap, int arenaCap, int warpsPerCta) { return grow_words_per_cta(listCap, arenaCap, warpsPerCta); }
 size_t lsdb_grow_rec_bytes_per_cta(void) { return (size_t)RING * 32 * REC_BYTES_PER_CELL; }
 
 

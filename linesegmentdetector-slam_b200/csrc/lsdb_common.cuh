@@ -88,9 +88,9 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
                       unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
-                      int* imgCounter, const unsigned int* banBits, int bmCapWords);
+                      int* imgCounter, const unsigned int* banBits, int bmCapWords, int steal);
 size_t lsdb_grow_rec_bytes_per_cta(void);
-size_t lsdb_grow_list_words_per_warp(int listCap, int arenaCap);
+size_t lsdb_grow_words_per_cta(int listCap, int arenaCap, int warpsPerCta);
 void lsdb_launch_lgamma_table(cudaStream_t s, double* tab, int n);
 void lsdb_launch_used_plane(cudaStream_t s, const unsigned int* state, uint8_t* used, int n);
 int lsdb_grow_max_ctas(int device, int warpsPerCta, int bmCapWords);
