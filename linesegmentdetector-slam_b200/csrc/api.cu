@@ -215,10 +215,13 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         if (bmMax > bmLimit) bmMax = bmLimit;
         b->bmCapWords = maxBanWords <= bmMax ? maxBanWords : 0;
         if (getenv("LSDB_NO_SMEM_BAN")) b->bmCapWords = 0;
-        int nw = LSDB_GROW_WARPS;
-        // halve the team while that puts more maps on the device at once (shared memory or registers permitting)
-        while (nw > 4 && (long long)n > lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords) &&
-               lsdb_grow_max_ctas(ctx->device, nw / 2, b->bmCapWords) > lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords)) nw >>= 1;
+        // Team size.  All maps of a batch are resident at once whenever they fit, so the step ends with the slowest map;
+        // a bigger team shortens one map's critical path but speculates further past the commit frontier (more grown
+        // pixels thrown away) and shares the SM's L1 among more growers.  Measured on 4096^2 maps: 16 warps for a
+        // handful of maps, 8 around one map per SM, 4 for 256 maps — about 1200 grower warps on the device in total.
+        int nw = 1184 / n;
+        if (nw > LSDB_GROW_WARPS) nw = LSDB_GROW_WARPS;
+        if (nw < 4) nw = 4;
         if (getenv("LSDB_GROW_WARPS")) { int v = atoi(getenv("LSDB_GROW_WARPS")); if (v >= 1 && v <= LSDB_GROW_WARPS) nw = v; }
         b->nWarps = nw;
         b->runAhead = 0;   // chunks a map's team may speculate ahead of its commit frontier (0 = as far as the ring allows)

@@ -278,6 +278,59 @@ __device__ __forceinline__ int accept_lanes(WarpCtx& c, GrowSums& g, bool& cand,
     const double pi = c.kc->pi;
     const double pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
     int start = 0;
+    if (tauSmall && g.nrmOK && g.n2 >= 1.0) {
+        // Bulk step.  The serial rule tests candidate l against the sums as they stand after the accepts among lanes < l.
+        // Each accept adds a unit vector within tol of the current direction, so it turns the direction by at most
+        // sin(tol)/|S| and never shortens S.  With k candidates ahead of it that can still be accepted, candidate l
+        // therefore PASSES whatever happens before it if  S.u - k sin^2(tol) > cos(tol)|S|,  and FAILS whatever happens if
+        // S.u + k sin^2(tol) (1 + k cos(tol)/2) < cos(tol)|S|  (first-order bounds on cos(tol -/+ k sin(tol)/|S|), |S| >= 1;
+        // k = 0 leaves the knife-edge margin of the plain test).  All lanes below the first undecided one are settled at
+        // once — accepts appended, and summed, in lane order — and the serial loop only runs from that lane on.
+        const unsigned int lt = (1u << c.lane) - 1u;
+        const unsigned int candMask = __ballot_sync(FULL, cand);
+        if (candMask) {
+            const double s2 = (1.0 - c2) * (1.0 + 1e-9);
+            const double dot = g.cosDeg * cd + g.sinDeg * sd;
+            double k = (double)__popc(candMask & lt);
+            double tf = dot + (k * s2 + 0.5 * cTau * k * k * s2);
+            bool F = cand && (tf <= 0.0 || g.c2n2 - tf * tf > g.m2);
+            const unsigned int F0 = __ballot_sync(FULL, F);
+            k = (double)__popc(candMask & ~F0 & lt);          // candidates that certainly fail never count
+            tf = dot + (k * s2 + 0.5 * cTau * k * k * s2);
+            F = cand && (tf <= 0.0 || g.c2n2 - tf * tf > g.m2);
+            const double tp = dot - k * s2;
+            const bool P = cand && !F && tp > 0.0 && tp * tp - g.c2n2 > g.m2;
+            const unsigned int Pm = __ballot_sync(FULL, P), Fm = __ballot_sync(FULL, F);
+            const unsigned int Am = candMask & ~Pm & ~Fm;
+            const int lowA = Am ? __ffs(Am) - 1 : 32;
+            const unsigned int below = lowA < 32 ? (1u << lowA) - 1u : FULL;
+            // the same pixel may be a candidate of several points: only its first lane joins
+            const unsigned int grp = __match_any_sync(FULL, cand ? (unsigned int)p : 0x80000000u + (unsigned int)c.lane);
+            const bool join = P && ((1u << c.lane) & below) && (grp & Pm & below & lt) == 0u;
+            const unsigned int acc = __ballot_sync(FULL, join);
+            if (acc) {
+                const int na = __popc(acc);
+                if (num + na >= c.listCap - 1) return -1;
+                if (join) {
+                    atomicOr(&c.state[p], c.mybit);
+                    c.list[num + __popc(acc & lt)] = pack_xy(n, m);
+                }
+                unsigned int t = acc;
+                while (t) {   // :545-546, in scan order
+                    const int f = __ffs(t) - 1;
+                    t &= t - 1;
+                    g.cosDeg += __shfl_sync(FULL, cd, f);
+                    g.sinDeg += __shfl_sync(FULL, sd, f);
+                }
+                sums_refresh(g, c2, cTau, tauSmall);
+                haveExact = false;
+                num += na;
+                if (cand && (grp & acc)) cand = false;   // joined, or the same pixel seen from another point
+            }
+            start = lowA;
+            if (lowA == 32) return 0;   // everything decided: the remaining candidates failed the angle test
+        }
+    }
     while (true) {
         const bool active = cand && c.lane >= start;
         bool pass = false, unc = false;
