@@ -106,6 +106,8 @@ int lsdb_batch_planes(lsdb_batch* b, int i, double* mag, double* deg, uint8_t* u
 /* per-stage device time of the last lsdb_batch_run, CUDA events on the context stream */
 int lsdb_batch_stage_ms(lsdb_batch* b, float* ms /* [LSDB_NSTAGES] */);
 int lsdb_batch_stats(lsdb_batch* b, lsdb_stats* total);
+/* the same counters for map i alone */
+int lsdb_batch_map_stats(lsdb_batch* b, int i, lsdb_stats* out);
 /* number of kernel launches issued by the last lsdb_batch_run */
 int lsdb_batch_launches(const lsdb_batch* b);
 

@@ -67,6 +67,7 @@ def lib():
         L.lsdb_batch_planes.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci, vp, vp]
         L.lsdb_batch_stage_ms.argtypes = [vp, vp]
         L.lsdb_batch_stats.argtypes = [vp, C.POINTER(_Stats)]
+        L.lsdb_batch_map_stats.argtypes = [vp, ci, C.POINTER(_Stats)]
         L.lsdb_batch_launches.argtypes = [vp]
         L.lsdb_lsd.argtypes = [vp, vp, ci, ci, C.POINTER(_Params), vp, ci, vp, vp, vp]
         L.lsdb_fa_map_create.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(vp)]
@@ -197,6 +198,11 @@ class Batch:
     def stats(self):
         st = _Stats()
         self.ctx.check(lib().lsdb_batch_stats(self.h, C.byref(st)), "lsdb_batch_stats")
+        return {f: getattr(st, f) for f in STAT_FIELDS}
+
+    def map_stats(self, i):
+        st = _Stats()
+        self.ctx.check(lib().lsdb_batch_map_stats(self.h, int(i), C.byref(st)), "lsdb_batch_map_stats")
         return {f: getattr(st, f) for f in STAT_FIELDS}
 
     def launches(self):

@@ -429,6 +429,15 @@ extern "C" int lsdb_batch_stats(lsdb_batch* b, lsdb_stats* total) {
     return LSDB_OK;
 }
 
+extern "C" int lsdb_batch_map_stats(lsdb_batch* b, int i, lsdb_stats* out) {
+    if (!b || !out || i < 0 || i >= b->n) return LSDB_ERR_ARG;
+    int rc = fetch_dyn(b);
+    if (rc) return rc;
+    long long* t = (long long*)out;
+    for (int k = 0; k < 32; k++) t[k] = b->dynH[i].stat[k];
+    return LSDB_OK;
+}
+
 extern "C" int lsdb_lsd(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, const lsdb_lsd_params* prm, lsdb_line* lines,
                         int maxLines, int* nLines, uint8_t* lineIm, uint8_t* mapRemapped) {
     if (!ctx || !map || !prm || !nLines) return fail(ctx, LSDB_ERR_ARG, "lsdb_lsd: bad argument%s");

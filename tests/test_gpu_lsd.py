@@ -129,3 +129,44 @@ def test_full_size_map_vs_oracle(lsdb, ctx):
     key = bins * 2.0 ** 32 - pl["seeds"]
     assert np.all(np.diff(key) < 0)
     b.close()
+
+
+def test_scan_rasters_batched_then_associated(lsdb, ctx):
+    """BASELINE config 4 at test scale: rasterised lidar scans (myrdp::FeatureScan lineIm of data/Lidar.txt frames, golden
+    fixture) go through LSD as one ragged batch — segment tables equal to the unmodified reference's (1e-9) and the oracle's (bit-exact) — and the frames are
+    then associated against LSD(data/mapValue.txt) in one launch."""
+    g = np.load(os.path.join(GOLD, "fa_frames.npz"))
+    gm = np.load(os.path.join(GOLD, "bundled_maps.npz"))
+    nf = int(g["n_frames"])
+    rasters = []
+    for f in range(nf):
+        h, w = (int(v) for v in g[f"f{f}/scan_im_shape"])
+        rasters.append(np.unpackbits(g[f"f{f}/scan_im_bits"])[:h * w].reshape(h, w).astype(np.uint8))   # occupied = 1
+    b = lsdb.Batch(ctx, [(r.shape[1], r.shape[0]) for r in rasters])
+    b.upload(rasters); b.run()
+    got = b.download()
+    for f in range(nf):
+        want = g[f"f{f}/scan_lsd_lines"]            # unmodified reference, stock glibc
+        mine = lsdb.lines_to_array(got["lines"][f])
+        assert got["counts"][f] == len(want)
+        # contract: 1e-9 relative on segment geometry.  (glibc's sin/cos are 1 ulp off the correctly rounded value in two of
+        # the twelve frames' dx/dy; against the oracle on the shared correctly-rounded math the table is bit-exact.)
+        assert np.allclose(mine, want, rtol=1e-9, atol=0, equal_nan=True)
+        assert np.array_equal(mine, oraclebind.lsd(rasters[f], want_maps=False)["lines"], equal_nan=True)
+    b.close()
+    mc = oraclebind.map_cache(gm["mapValue/map"], float(gm["mapValue/param"][2]))
+    fm = lsdb.FaMap(ctx, mc, g["map_lines"])
+    frames = [dict(scan_lines=lsdb.lines_to_array(got["lines"][f]), pts=g[f"f{f}/pts"], lidar_pose=g[f"f{f}/lidar_pose"],
+                   last_pose=[-1.0, -1.0, 0.0]) for f in range(nf)]
+    hyp = fm.score(frames)
+    pos = 0
+    for f in range(nf):
+        oi, ov = oraclebind.fa_scores(frames[f]["scan_lines"], g["map_lines"], frames[f]["pts"], mc, frames[f]["lidar_pose"],
+                                      frames[f]["last_pose"])
+        h = hyp[pos:pos + len(oi)]; pos += len(oi)
+        assert np.array_equal(np.stack([h["i_scan"], h["i_map"], h["i_pair"]], 1).reshape(-1, 3), oi.reshape(-1, 3))
+        fin = np.isfinite(ov[:, 3]) if len(ov) else np.zeros(0, bool)
+        assert np.array_equal(np.isfinite(h["score"]), fin)
+        assert np.allclose(h["score"][fin], ov[fin, 3], rtol=1e-9, atol=0)
+    assert pos == len(hyp)
+    fm.close()

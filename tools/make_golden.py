@@ -53,6 +53,10 @@ for f in range(12):
     idx, val = refbind.ref_fa_scores(fs["lines"], map_lines, fs["pts"], mc, lidar, last)
     fa[f"f{f}/scan_lines"] = fs["lines"]; fa[f"f{f}/pts"] = fs["pts"]; fa[f"f{f}/lidar_pose"] = lidar
     fa[f"f{f}/last_pose"] = last; fa[f"f{f}/idx"] = idx; fa[f"f{f}/val"] = val
+    # the frame's scan raster (myrdp::FeatureScan lineIm, 0/255), bit-packed: the LSD-on-scan workload of BASELINE configs[3]
+    fa[f"f{f}/scan_im_bits"] = np.packbits(fs["line_im"] > 0); fa[f"f{f}/scan_im_shape"] = np.array(fs["line_im"].shape)
+    occ = (fs["line_im"] > 0).astype(np.uint8)            # mapValue convention: occupied = 1
+    fa[f"f{f}/scan_lsd_lines"] = refbind.ref_lsd(occ, want_maps=False)["lines"]
     print("frame", f * 8, "lines", len(fs["lines"]), "pts", len(fs["pts"]), "hyp", len(idx), "kept(<3)", int((val[:, 3] < 3).sum()))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fa_frames.npz"), **fa)
 for f in ("bundled_maps.npz", "fa_frames.npz"):
