@@ -226,7 +226,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         b->nWarps = nw;
         b->runAhead = 0;   // chunks a map's team may speculate ahead of its commit frontier (0 = as far as the ring allows)
         if (getenv("LSDB_RUNAHEAD")) b->runAhead = atoi(getenv("LSDB_RUNAHEAD"));
-        b->steal = 1;
+        b->steal = 0;   // measured: spreading large seeds over the team duplicates growth of neighbouring seeds; no net gain
         if (getenv("LSDB_STEAL")) b->steal = atoi(getenv("LSDB_STEAL"));
         const int maxCtas = lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords);
         b->nCtas = n < maxCtas ? n : maxCtas;
