@@ -11,6 +11,7 @@
  *                                 LSD/myFA.h:83-87, LSD/myFA.cpp:27-63 (dispatch), :186-272
  *                                 (thread_ScanToMapMatch), :274-305, :307-355, :357-396
  *   lsdb_hypothesis           <- structScore                            LSD/myFA.h:49-54
+ *   lsdb_map_cache            <- mylsd::createMapCache                  LSD/myLSD.h:131, LSD/myLSD.cpp:11-127
  *
  * There is no CPU fallback: every compute entry point fails with LSDB_ERR_NO_DEVICE / LSDB_ERR_CUDA
  * when no sm_100 device is usable.  All functions return LSDB_OK (0) or an error code; the text of
@@ -116,6 +117,12 @@ int lsdb_batch_launches(const lsdb_batch* b);
  * its caller's Mat (LSD/myLSD.cpp:135-142); line_im (nullable) = rows*cols u8. */
 int lsdb_lsd(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, const lsdb_lsd_params* params,
              lsdb_line* lines, int max_lines, int* n_lines, uint8_t* line_im, uint8_t* map_remapped);
+
+/* ---- mapCache (the lookup table of the association scoring) ---- */
+/* createMapCache (LSD/myLSD.cpp:11-127): truncated brush-fire distance map of the occupied cells (value 1) of `map`
+ * (rows*cols u8, BEFORE the LSD remap), in metres, f64, rows*cols.  max_dist = z_occ_max_dis (LSD/baseFunc.h:60, 1 m).
+ * Identical to the reference cell for cell, including its FIFO tie-breaking between sources. */
+int lsdb_map_cache(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double max_dist, double* out);
 
 /* ---- association scoring ---- */
 /* structScore (LSD/myFA.h:49-54) plus the indices that identify the hypothesis */

@@ -70,6 +70,7 @@ def lib():
         L.lsdb_batch_map_stats.argtypes = [vp, ci, C.POINTER(_Stats)]
         L.lsdb_batch_launches.argtypes = [vp]
         L.lsdb_lsd.argtypes = [vp, vp, ci, ci, C.POINTER(_Params), vp, ci, vp, vp, vp]
+        L.lsdb_map_cache.argtypes = [vp, vp, ci, ci, cd, cd, vp]
         L.lsdb_fa_map_create.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(vp)]
         L.lsdb_fa_map_destroy.argtypes = [vp]; L.lsdb_fa_map_destroy.restype = None
         L.lsdb_fa_score.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
@@ -118,6 +119,18 @@ class Context:
         self.check(lib().lsdb_lsd(self.h, _p(m), cols, rows, C.byref(prm), _p(lines), max_lines, C.byref(n), _p(im), _p(rm)),
                    "lsdb_lsd")
         return dict(n=n.value, lines=lines[:n.value].copy(), line_im=im, map_out=rm)
+
+
+def _ctx_map_cache(self, map_u8, res, max_dist=1.0):
+    """mylsd::createMapCache (LSD/myLSD.h:131) through lsdb_map_cache: rows x cols f64 metres."""
+    m = np.ascontiguousarray(map_u8, np.uint8)
+    rows, cols = m.shape
+    out = np.zeros((rows, cols), np.float64)
+    self.check(lib().lsdb_map_cache(self.h, _p(m), cols, rows, float(res), float(max_dist), _p(out)), "lsdb_map_cache")
+    return out
+
+
+Context.map_cache = _ctx_map_cache
 
 
 class Batch:

@@ -472,6 +472,19 @@ extern "C" int lsdb_lsd(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, c
     return LSDB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ mapCache
+extern "C" int lsdb_map_cache_device(int device, void* stream, const uint8_t* map, int cols, int rows, double res, double maxDist,
+                                     double* out, char* err, int errLen);
+
+extern "C" int lsdb_map_cache(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double maxDist, double* out) {
+    if (!ctx || !map || !out || cols <= 0 || rows <= 0 || cols > 65535 || rows > 65535 || !(res > 0) || !(maxDist >= 0))
+        return fail(ctx, LSDB_ERR_ARG, "lsdb_map_cache: bad argument%s");
+    char msg[256]; msg[0] = 0;
+    const int rc = lsdb_map_cache_device(ctx->device, (void*)ctx->stream, map, cols, rows, res, maxDist, out, msg, sizeof msg);
+    if (rc) ctx->err = msg;
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------ association
 struct lsdb_fa_map {
     lsdb_ctx* ctx;

@@ -1,10 +1,12 @@
-// Drop-in body for mylsd::myLineSegmentDetector (reference LSD/myLSD.h:132, LSD/myLSD.cpp:129-376).
+// Drop-in bodies for mylsd::myLineSegmentDetector (reference LSD/myLSD.h:132, LSD/myLSD.cpp:129-376) and
+// mylsd::createMapCache (LSD/myLSD.h:131, LSD/myLSD.cpp:11-127).
 //
-// Compiled against the reference's own myLSD.h (so the signature, structLSD and structLinesInfo are the
-// reference's, not copies) and linked with liblsdb200.so.  The reference's myLSD.cpp stays in the build
-// for createMapCache unless LSDB_DEVICE_MAP_CACHE is defined; its own myLineSegmentDetector is renamed
-// out of the way at compile time (-DmyLineSegmentDetector=myLineSegmentDetector_cpu on that one TU, see
-// INTEGRATION.md) or simply deleted by the maintainer.
+// Compiled against the reference's own myLSD.h (so the signatures, structLSD and structLinesInfo are the
+// reference's, not copies) and linked with liblsdb200.so.  The reference's two bodies are renamed out of
+// the way at compile time (-DmyLineSegmentDetector=myLineSegmentDetector_cpu
+// -DcreateMapCache=createMapCache_cpu on the myLSD.cpp TU) or simply deleted by the
+// maintainer; define LSDB_KEEP_CPU_MAP_CACHE here (and drop the second rename) to keep the reference's
+// createMapCache.
 //
 // Contract kept from the reference:
 //   * MapGray is a shallow, ref-counted copy, so the 1->255 / 255->0 remap (rows, cols >= 1 only) is
@@ -55,5 +57,22 @@ structLSD myLineSegmentDetector(Mat MapGray, int oriMapCol, int oriMapRow, doubl
     }
     return out;
 }
+
+#ifndef LSDB_KEEP_CPU_MAP_CACHE
+// The truncated distance map the association scores against; reads MapGray BEFORE the LSD remap (callers run it
+// first, LSD/main_on_windows.cpp:67-70).  Fresh CV_64FC1 Mat, rows x cols, metres.
+Mat createMapCache(Mat MapGray, double res) {
+    lsdb_ctx* ctx = lsdb_host::context();
+    const int rows = MapGray.rows, cols = MapGray.cols;
+    std::vector<uint8_t> in((size_t)rows * cols);
+    for (int y = 0; y < rows; y++) memcpy(&in[(size_t)y * cols], MapGray.ptr<uint8_t>(y), (size_t)cols);
+    std::vector<double> out((size_t)rows * cols);
+    const int rc = lsdb_map_cache(ctx, in.data(), cols, rows, res, z_occ_max_dis, out.data());
+    if (rc != LSDB_OK) lsdb_host::die("lsdb_map_cache", rc);
+    Mat mapCache = Mat::zeros(rows, cols, CV_64FC1);
+    for (int y = 0; y < rows; y++) memcpy(mapCache.ptr<double>(y), &out[(size_t)y * cols], sizeof(double) * (size_t)cols);
+    return mapCache;
+}
+#endif
 
 }  // namespace mylsd

@@ -67,4 +67,6 @@ def test_dropin_library_keeps_the_reference_entry_points():
     syms = subprocess.run(["nm", "-DC", "--defined-only", so], capture_output=True, text=True).stdout
     assert "mylsd::myLineSegmentDetector(cv::Mat, int, int, double, double, double, double, int)" in syms
     assert "myfa::FeatureAssociation(myfa::_structFAInput*)" in syms
+    assert "mylsd::createMapCache(cv::Mat, double)" in syms
     assert "mylsd::myLineSegmentDetector_cpu" in syms and "myfa::FeatureAssociation_cpu" in syms   # the reference bodies, renamed
+    assert "mylsd::createMapCache_cpu" in syms

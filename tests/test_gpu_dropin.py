@@ -44,7 +44,7 @@ def test_FeatureAssociation_dropin_matches_reference():
     g = np.load(os.path.join(GOLD, "fa_frames.npz"))
     gm = np.load(os.path.join(GOLD, "bundled_maps.npz"))
     res = float(gm["mapValue/param"][2])
-    mc = refbind.ref_map_cache(gm["mapValue/map"], res, variant="dropin")   # the reference's createMapCache, kept in the drop-in
+    mc = refbind.ref_map_cache(gm["mapValue/map"], res, variant="dropin")   # mylsd::createMapCache -> lsdb_map_cache (device)
     assert np.array_equal(mc, refbind.ref_map_cache(gm["mapValue/map"], res, variant="glibc"))
     rows, cols = mc.shape
     ml = np.ascontiguousarray(g["map_lines"], np.float64)

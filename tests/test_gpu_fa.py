@@ -66,3 +66,20 @@ def test_fa_edge_cases(lsdb, ctx):
             assert not fin.any()
     assert fm.score([]).shape == (0,)
     fm.close()
+
+
+def test_map_cache_device_matches_reference(lsdb, ctx):
+    """lsdb_map_cache == mylsd::createMapCache cell for cell (FIFO tie-breaking between sources included): bundled maps
+    against the oracle restatement, which tests/test_oracle.py pins to the unmodified reference."""
+    gm = np.load(os.path.join(GOLD, "bundled_maps.npz"))
+    for name in ("mapValue", "mapValue_map1"):
+        m = gm[name + "/map"]; res = float(gm[name + "/param"][2])
+        got = ctx.map_cache(m, res)
+        assert np.array_equal(got, oraclebind.map_cache(m, res)), name
+    for shape, seed, res in (((300, 200), 5, 0.05), ((97, 61), 6, 0.025), ((64, 64), 8, 0.3)):
+        m = synth.occupancy_grid(shape[0], shape[1], seed=seed)
+        assert np.array_equal(ctx.map_cache(m, res), oraclebind.map_cache(m, res))
+    blank = np.zeros((40, 50), np.uint8)                       # no source: every cell keeps z_occ_max_dis
+    assert np.all(ctx.map_cache(blank, 0.05) == 1.0)
+    full = np.ones((30, 30), np.uint8)
+    assert np.all(ctx.map_cache(full, 0.05) == 0.0)
