@@ -1,2 +1,2 @@
-for nw in 4 16; do echo "--- nw=$nw single"; LSDB_GROW_WARPS=$nw timeout 60 python tools/gpu_sweep.py child; done
-timeout 300 python tools/tail_probe.py 256 2>&1 | head -3
+timeout 400 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],1), d['stage_ms'], d['e2e']['value'], d['roofline']['frac'])"
+timeout 200 python tools/run_batch.py 5000 1 16384

@@ -8,5 +8,5 @@ import synth
 lsdb = load_package(); ctx = lsdb.Context(0)
 first, cnt = int(sys.argv[1]), int(sys.argv[2]); size = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 maps = [synth.occupancy_grid(size, size, seed=first + i) for i in range(cnt)]
-b = lsdb.Batch(ctx, [(size, size)] * cnt); b.upload(maps); b.run(); b.sync()
+b = lsdb.Batch(ctx, [(size, size)] * cnt, max_lines=65536); b.upload(maps); b.run(); b.sync()
 print("ok", b.counts().sum(), b.stage_ms())
