@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--cpu-sample-maps", type=int, default=0, help="maps for the cpu_baseline leg (0 = one per core, max 8)")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="resident batches that alternate on their own streams")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -165,7 +166,8 @@ def main():
     # two explicit streams: their handles are what the library launches on.  Two resident batches (A, B) of the same
     # maps alternate, step by step: while the last, slow maps of one step finish, the next step's maps already occupy the
     # SMs they left idle — the steady state of a caller that keeps the device fed.
-    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    NB = max(1, args.inflight)
+    streams = [torch.cuda.Stream() for _ in range(NB)]
     torch.cuda.set_stream(streams[0])
     stream = streams[0]
     ctxs = [lsdb.Context(local, st.cuda_stream) for st in streams]
@@ -192,22 +194,23 @@ def main():
     # ---------------- device-resident: inputs already in HBM
     for bt in batches:
         bt.upload(ptrs)
-    for k in range(max(args.warmup, 3)):
-        batches[k & 1].run()
+    for k in range(max(args.warmup, 3, NB)):
+        batches[k % NB].run()
     for bt in batches:
         bt.sync()
     sampler = ClockSampler(local); sampler.start()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(NB)]
     e0.record(streams[0])
-    streams[1].wait_event(e0)
+    for k in range(1, NB):
+        streams[k].wait_event(e0)
     for k in range(args.steps):
-        batches[k & 1].run()
-    for k in range(2):
+        batches[k % NB].run()
+    for k in range(NB):
         ends[k].record(streams[k])
     barrier()
-    ms_total = max(e0.elapsed_time(ends[0]), e0.elapsed_time(ends[1]))
+    ms_total = max(e0.elapsed_time(ev) for ev in ends)
     clocks = sampler.stop()
     # one step alone (nothing else on the device): per-stage times from the library's own events on its stream
     batch.run(); batch.sync()
@@ -247,8 +250,8 @@ def main():
     # Two batches on two private streams alternate (one host thread each; ctypes drops the GIL), so the H2D copy of
     # one step overlaps the kernels of the other: the steady state of a caller that streams batches through the library.
     workers = list(zip(ctxs, batches))
-    e2e_steps = max(2, args.steps + (args.steps & 1))    # an even number of steps, shared by the two workers
-    nseg_box = [0, 0]
+    e2e_steps = NB * max(1, (args.steps + NB - 1) // NB)  # a multiple of the worker count
+    nseg_box = [0] * NB
 
     def e2e_worker(w, k):
         cw, bw = workers[w]
@@ -256,11 +259,11 @@ def main():
             bw.upload(ptrs); bw.run(); out_w = bw.download()
             nseg_box[w] = int(out_w["counts"].sum())
 
-    for w in range(2):
+    for w in range(NB):
         e2e_worker(w, 1)                             # warm-up: allocations, first-touch
     barrier()
     t0 = time.time()
-    th = [threading.Thread(target=e2e_worker, args=(w, e2e_steps // 2)) for w in range(2)]
+    th = [threading.Thread(target=e2e_worker, args=(w, e2e_steps // NB)) for w in range(NB)]
     [t.start() for t in th]
     [t.join() for t in th]
     torch.cuda.synchronize()
@@ -293,14 +296,14 @@ def main():
             "config": {"workload": f"synthetic {size}x{size} occupancy grids, batch {n} per GPU (BASELINE configs[2])",
                        "maps_per_gpu": n, "global_batch": n * world, "parallelism": f"map-sharded x{world}, no collective",
                        "l2": f"inputs {n * size * size / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
-                       "pipelining": "two resident batches alternate on two streams (value and e2e alike); stage_ms / roofline are one step alone"},
+                       "pipelining": f"{NB} resident batches alternate on {NB} streams (value and e2e alike); stage_ms / roofline are one step alone"},
             "segments_per_s": float(segs.item()) / (ms_step * 1e-3), "segments_per_step": float(segs.item()),
             "ms_per_map_amortised": ms_step / n,
             "single_map_latency": lat,
             "stage_ms": last,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * size * size, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "how": "lsdb_batch_upload (pinned host -> HBM) + lsdb_batch_run + lsdb_batch_download per step; "
-                                               "two batches on two streams alternate so copies overlap kernels"},
+                                               f"{NB} batches on {NB} streams alternate so copies overlap kernels"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"kernel": "lsdb_stencil_kernel (remap+Gaussian+gradient)", "bound": "hbm", "achieved": achieved, "peak": peak,
