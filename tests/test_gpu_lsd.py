@@ -170,3 +170,27 @@ def test_scan_rasters_batched_then_associated(lsdb, ctx):
         assert np.allclose(h["score"][fin], ov[fin, 3], rtol=1e-9, atol=0)
     assert pos == len(hyp)
     fm.close()
+
+
+@pytest.mark.parametrize("env", [dict(LSDB_GROW_WARPS="1"), dict(LSDB_GROW_WARPS="3"), dict(LSDB_GROW_WARPS="8", LSDB_STEAL="1"),
+                                 dict(LSDB_GROW_WARPS="16", LSDB_RUNAHEAD="16"), dict(LSDB_NO_SMEM_BAN="1"),
+                                 dict(LSDB_SMEM_BAN_KB="200", LSDB_GROW_WARPS="16")])
+def test_result_is_independent_of_team_shape(lsdb, ctx, gold, env):
+    """The ordered-commit pipeline must give the sequential result whatever the speculation looks like: team size,
+    run-ahead window, team-wide queue for large seeds, ban plane in shared memory or not."""
+    maps = [gold["mapValue_aisle2/map"], synth.occupancy_grid(1500, 1100, seed=77), synth.occupancy_grid(900, 1300, seed=78, border_walls=True)]
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for m in maps])
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    b.upload(maps); b.run()
+    got = b.download(want_rects=True)
+    for i, m in enumerate(maps):
+        _compare_with_oracle(lsdb, b, i, m, got, check_planes=False)
+    b.close()
