@@ -245,6 +245,41 @@ def main():
     except Exception as e:  # the fixture is part of the repo; report rather than hide a failure
         lat = {"error": repr(e)}
 
+    # ---------------- association (BASELINE configs[3] shape): 10k scan frames scored against LSD(data/mapValue.txt) in ONE launch
+    fa = None
+    try:
+        import oraclebind
+        gf = np.load(os.path.join(ROOT, "tests", "golden", "fa_frames.npz"))
+        gmaps = np.load(os.path.join(ROOT, "tests", "golden", "bundled_maps.npz"))
+        mc = ctx.map_cache(gmaps["mapValue/map"], float(gmaps["mapValue/param"][2]))     # createMapCache on the device
+        base = [dict(scan_lines=gf[f"f{f}/scan_lines"], pts=gf[f"f{f}/pts"], lidar_pose=gf[f"f{f}/lidar_pose"],
+                     last_pose=[-1.0, -1.0, 0.0]) for f in range(int(gf["n_frames"]))]
+        reps = 10000 // len(base) + 1
+        frames = base * reps                                                             # 10 008 frames (the 12 reference frames of data/Lidar.txt, tiled)
+        fm = lsdb.FaMap(ctx, mc, gf["map_lines"])
+        hyp = fm.score(frames)                                                           # warm-up + sizes
+        t0 = time.time(); hyp = fm.score(frames); torch.cuda.synchronize(); dt_fa = time.time() - t0
+        k_ms = fm.last_ms()
+        pts_total = sum(len(f["pts"]) for f in frames)
+        # CPU: the reference's own NormalizedLineDirection / rotateScanIm / CalcScore, serial, on the 12 distinct frames
+        import refbind
+        t0 = time.time(); nh = 0
+        for f in base:
+            if refbind.available("glibc"):
+                idx, _ = refbind.ref_fa_scores(f["scan_lines"], gf["map_lines"], f["pts"], mc, f["lidar_pose"], f["last_pose"])
+            else:
+                idx, _ = oraclebind.fa_scores(f["scan_lines"], gf["map_lines"], f["pts"], mc, f["lidar_pose"], f["last_pose"])
+            nh += len(idx)
+        dt_cpu = time.time() - t0
+        fa = {"workload": f"{len(frames)} scan frames (12 frames of data/Lidar.txt tiled) x 41 map lines, one launch",
+              "hypotheses": int(len(hyp)), "scan_points": int(pts_total), "kernel_ms": k_ms,
+              "hypotheses_per_s_kernel": len(hyp) / (k_ms * 1e-3), "hypotheses_per_s_e2e": len(hyp) / dt_fa,
+              "cpu_reference_hypotheses_per_s": nh / dt_cpu, "cpu_kind": "reference serial (1 thread)" if refbind.available("glibc") else "port",
+              "l2_note": "mapCache 1377x428 f64 = 4.7 MB gathers are L2-resident"}
+        fm.close()
+    except Exception as e:
+        fa = {"error": repr(e)}
+
     # ---------------- end to end through the C ABI with host buffers
     # Every step copies its 256 maps from pinned host memory, runs the pipeline and reads the segment tables back.
     # Two batches on two private streams alternate (one host thread each; ctypes drops the GIL), so the H2D copy of
@@ -300,6 +335,7 @@ def main():
             "segments_per_s": float(segs.item()) / (ms_step * 1e-3), "segments_per_step": float(segs.item()),
             "ms_per_map_amortised": ms_step / n,
             "single_map_latency": lat,
+            "association": fa,
             "stage_ms": last,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * size * size, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "how": "lsdb_batch_upload (pinned host -> HBM) + lsdb_batch_run + lsdb_batch_download per step; "
