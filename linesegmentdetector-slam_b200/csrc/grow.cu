@@ -120,7 +120,10 @@ struct WarpCtx {
     int specChunk;          // seed-list chunk of the seed being evaluated speculatively; -1 at the frontier (parked
                             //   regions are then ignored: the state is final)
     double* stage;          // 32 x 4 doubles of shared memory: operands of the ordered sums in rect_from_region
-    volatile unsigned int* bm;   // shared-memory copy of the ban plane (usedMap==1), one bit per pixel, pw words per row; NULL: use `state`
+    volatile unsigned int* bm;   // the ban plane (usedMap==1), one bit per pixel, pw words per row: its shared-memory copy when the map
+                                 // fits (bmInSmem), else the global plane itself (48 MB for 256 maps of 4096^2: L2-resident, unlike the
+                                 // 1.5 GB of state words)
+    bool bmInSmem;
     int pw;
     double logNT, regThre;
     int cellShift;        // accept-grid cell = 2^cellShift pixels, grid <= GRID x GRID
@@ -435,7 +438,7 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
                 const int r3 = nb / 3;
                 m = py_of(pv) + r3 - 1; n = px_of(pv) + (nb - r3 * 3) - 1;
                 // banned? — from the shared-memory bit plane; only un-banned candidates touch global memory
-                cand = valid && m >= 0 && n >= 0 && m < H && n < W && !(c.bm && ban_at(c, n, m));
+                cand = valid && m >= 0 && n >= 0 && m < H && n < W && !(c.bmInSmem && ban_at(c, n, m));
                 banMask = LSDB_ST_BAN | c.mybit;
             }
             const size_t p = cand ? (size_t)m * W + n : 0;
@@ -1482,7 +1485,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
                                                                    LsdbRect* __restrict__ rects, int maxSeg, unsigned int* __restrict__ lists,
                                                                    int listCap, int arenaCap, int runAhead, unsigned char* __restrict__ recBuf,
                                                                    const double* __restrict__ lgammaTab, int lgammaN, int* __restrict__ imgCounter,
-                                                                   const unsigned int* __restrict__ banBits, int bmCapWords, int steal) {
+                                                                   unsigned int* banBits, int bmCapWords, int steal) {
     __shared__ GrowShared sh;
     extern __shared__ unsigned int bmShared[];   // the map's ban plane, one bit per pixel (bmCapWords words)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
@@ -1546,9 +1549,9 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
             if (words <= bmCapWords) {
                 const unsigned int* srcB = banBits + im.banOff;
                 for (int i = tid; i < words; i += blockDim.x) bmShared[i] = srcB[i];
-                c.bm = bmShared;
+                c.bm = bmShared; c.bmInSmem = true;
             } else {
-                c.bm = 0;
+                c.bm = banBits + im.banOff; c.bmInSmem = false;
             }
         }
         const int T = (int)ceil(im.regThre);   // regions below regThre pixels are dropped (:228)
@@ -1611,7 +1614,7 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
                       unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
-                      int* imgCounter, const unsigned int* banBits, int bmCapWords, int steal) {
+                      int* imgCounter, unsigned int* banBits, int bmCapWords, int steal) {
     if (runAhead <= 0 || runAhead > RING - (NW_MAX + 1) * LSDB_SUPER) runAhead = RING - (NW_MAX + 1) * LSDB_SUPER;
     if (runAhead < 1) runAhead = 1;
     static int attrSet = -1;

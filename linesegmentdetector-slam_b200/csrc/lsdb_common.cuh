@@ -88,7 +88,7 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
                       unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
-                      int* imgCounter, const unsigned int* banBits, int bmCapWords, int steal);
+                      int* imgCounter, unsigned int* banBits, int bmCapWords, int steal);
 size_t lsdb_grow_rec_bytes_per_cta(void);
 size_t lsdb_grow_words_per_cta(int listCap, int arenaCap, int warpsPerCta);
 void lsdb_launch_lgamma_table(cudaStream_t s, double* tab, int n);
