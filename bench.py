@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--cpu-sample-maps", type=int, default=0, help="maps for the cpu_baseline leg (0 = one per core, max 8)")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3, help="resident batches that alternate on their own streams")
+    ap.add_argument("--inflight", type=int, default=4, help="resident batches that alternate on their own streams")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))

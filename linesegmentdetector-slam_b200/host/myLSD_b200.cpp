@@ -25,17 +25,23 @@
 
 static_assert(sizeof(structLinesInfo) == sizeof(lsdb_line), "structLinesInfo layout (LSD/baseFunc.h:33-44)");
 
+// The older ROS flavour of the header (ROS/lsd/include/myLSD.h) declares the last argument as `double pseBin`:
+// build this file with -DLSDB_PSEBIN_T=double against that header.
+#ifndef LSDB_PSEBIN_T
+#define LSDB_PSEBIN_T int
+#endif
+
 namespace mylsd {
 
 structLSD myLineSegmentDetector(Mat MapGray, int oriMapCol, int oriMapRow, double sca, double sig, double angThre,
-                                double denThre, int pseBin) {
+                                double denThre, LSDB_PSEBIN_T pseBin) {
     lsdb_ctx* ctx = lsdb_host::context();
     const size_t npx = (size_t)oriMapCol * oriMapRow;
     std::vector<uint8_t> in(npx), remapped(npx), lineIm(npx);
     for (int y = 0; y < oriMapRow; y++) memcpy(&in[(size_t)y * oriMapCol], MapGray.ptr<uint8_t>(y), (size_t)oriMapCol);
 
     lsdb_lsd_params prm;
-    prm.sca = sca; prm.sig = sig; prm.angThre = angThre; prm.denThre = denThre; prm.pseBin = pseBin; prm._pad = 0;
+    prm.sca = sca; prm.sig = sig; prm.angThre = angThre; prm.denThre = denThre; prm.pseBin = (int)pseBin; prm._pad = 0;
     const int cap = 4096;
     std::vector<lsdb_line> lines(cap);
     int n = 0;
