@@ -194,3 +194,19 @@ def test_result_is_independent_of_team_shape(lsdb, ctx, gold, env):
     for i, m in enumerate(maps):
         _compare_with_oracle(lsdb, b, i, m, got, check_planes=False)
     b.close()
+
+
+def test_giant_map_on_one_gpu(lsdb, ctx):
+    """BASELINE config 5 shape (one 16384x16384 map, seed 5000) on a single GPU: segment table and rectangles bit-exact
+    against the oracle.  (Tiling it across GPUs is not built; this pins the single-GPU result the tiled version must keep.)"""
+    m = synth.occupancy_grid(16384, 16384, seed=5000)
+    b = lsdb.Batch(ctx, [(16384, 16384)], max_lines=65536)
+    b.upload([m]); b.run()
+    got = b.download(want_rects=True)
+    o = oraclebind.lsd(m, want_maps=False, want_line_im=False, max_lines=65536)
+    assert got["counts"][0] == o["n"] and o["n"] > 5000
+    assert np.array_equal(got["rects"][0], o["rects"], equal_nan=True)
+    assert np.array_equal(lsdb.lines_to_array(got["lines"][0]), o["lines"], equal_nan=True)
+    st = b.stats()
+    assert st["accepts"] == o["stats"]["accepts"] and st["rejects"] == o["stats"]["rejects"] and st["live_seeds"] == o["stats"]["live_seeds"]
+    b.close()
