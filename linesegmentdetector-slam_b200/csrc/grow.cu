@@ -358,6 +358,7 @@ __device__ __forceinline__ int accept_lanes(WarpCtx& c, GrowSums& g, bool& cand,
         if (__any_sync(FULL, unc)) {
             if (!haveExact) { regExact = d_atan2(g.sinDeg, g.cosDeg); haveExact = true; }
             if (unc) {  // the literal test, :540-543
+                if (tauSmall) dg = c.deg[p];   // not loaded up front on this path
                 double degDif = fabs(regExact - dg);
                 if (degDif > pi32) degDif = fabs(degDif - pi2);
                 pass = degDif < degThre;
@@ -390,7 +391,7 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
     const size_t sp = (size_t)sy * W + sx;
     const double regDeg0 = regDeg;
     GrowSums g;
-    g.sinDeg = c.sinm[sp]; g.cosDeg = c.cosm[sp];  // sin(regDeg), cos(regDeg)  (:515-516)
+    g.sinDeg = c.sinm[2 * sp]; g.cosDeg = c.cosm[2 * sp];  // sin(regDeg), cos(regDeg)  (:515-516)
     const bool tauSmall = degThre <= pi / 2.0;
     const bool tauGtPi = degThre > pi;
     const double cTau = degThre == c.kc->degThre ? c.kc->cosDegThre : (tauGtPi ? -1.0 : d_cos(degThre));
@@ -444,7 +445,7 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
             const size_t p = cand ? (size_t)m * W + n : 0;
             const unsigned int st = cand ? lsdb_ld_state(&c.state[p]) : 0u;
             double dg = 0.0, cd = 0.0, sd = 0.0;
-            if (cand) { dg = c.deg[p]; cd = c.cosm[p]; sd = c.sinm[p]; }  // issued with the state load, not after it
+            if (cand) { cd = c.cosm[2 * p]; sd = c.sinm[2 * p]; if (!tauSmall) dg = c.deg[p]; }  // issued with the state load, not after it
             cand = cand && !(st & banMask);
             if (c.specChunk >= 0) {
                 // speculation: a pixel inside a region an earlier seed has parked for acceptance counts as banned;
@@ -507,7 +508,7 @@ __device__ __noinline__ int small_grow(const WarpCtx& c, int p0, int T, unsigned
     unsigned short rej[SG_CAP];
     const int sx = p0 % W, sy = p0 / W;
     const double c2 = cTau * cTau;
-    double cosS = c.cosm[p0], sinS = c.sinm[p0];
+    double cosS = c.cosm[2 * (size_t)p0], sinS = c.sinm[2 * (size_t)p0];
     double n2 = cosS * cosS + sinS * sinS, c2n2 = c2 * n2, m2 = 4e-13 * n2;   // see grow_region: the test on the squares
     bool nrmOK = n2 > 1e-18;
     lst[0] = pack_xy(sx, sy);
@@ -531,7 +532,7 @@ __device__ __noinline__ int small_grow(const WarpCtx& c, int p0, int T, unsigned
                 if (own) continue;
                 const size_t p = (size_t)m * W + n;
                 const unsigned int st = lsdb_ld_state(&c.state[p]);
-                const double cd = c.cosm[p], sd = c.sinm[p];
+                const double cd = c.cosm[2 * p], sd = c.sinm[2 * p];
                 if (st & LSDB_ST_BAN) continue;
                 if (pend_applies(st, LSDB_ST_PACC, myChunk)) {   // parked for acceptance by an earlier seed: counts as banned,
                     bool dup = false;                            // to be confirmed when this evaluation retires
@@ -1542,7 +1543,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
             while (((max(im.W, im.H) - 1) >> k) > GRID - 1) k++;
             c.cellShift = k;
         }
-        c.state = state + im.nOff; c.deg = deg + im.nOff; c.mag = mag + im.nOff; c.cosm = cosm + im.nOff; c.sinm = sinm + im.nOff;
+        c.state = state + im.nOff; c.deg = deg + im.nOff; c.mag = mag + im.nOff; c.cosm = cosm + 2 * im.nOff; c.sinm = sinm + 2 * im.nOff;   // one interleaved (cos, sin) plane
         c.pw = im.pw;
         {   // the ban plane written by the stencil stage moves into shared memory when it fits
             const int words = im.H * im.pw;

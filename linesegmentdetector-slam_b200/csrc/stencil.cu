@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(NT) lsdb_stencil_kernel(const LsdbImg* __restr
             deg[p] = S.u.out.degT[t];
             state[p] = st;
             if (st == 0) {
-                cosm[p] = S.u.out.cosT[t];
-                sinm[p] = S.u.out.sinT[t];
+                cosm[2 * p] = S.u.out.cosT[t];   // one interleaved (cos, sin) plane: sinm == cosm + 1
+                sinm[2 * p] = S.u.out.sinT[t];
             }
         }
     }
