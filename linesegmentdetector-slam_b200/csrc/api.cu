@@ -553,7 +553,8 @@ extern "C" int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, c
     const size_t oTasks = 0, oLines = oTasks + al256(sizeof(LsdbFaTask) * nTasks), oLoff = oLines + al256(sizeof(LsdbFaLine) * nL),
                  oPts = oLoff + al256(sizeof(int) * (nFrames + 1)), oPoff = oPts + al256(16 * (size_t)nP),
                  oLid = oPoff + al256(sizeof(int) * (nFrames + 1)), oLast = oLid + al256(16 * (size_t)nFrames),
-                 oOut = oLast + al256(24 * (size_t)nFrames), total = oOut + al256(sizeof(LsdbFaHyp) * (size_t)nTasks * 4);
+                 oOut = oLast + al256(24 * (size_t)nFrames), oPose = oOut + al256(sizeof(LsdbFaHyp) * (size_t)nTasks * 4),
+                 total = oPose + al256(lsdb_fa_pose_bytes(nTasks));
     if (total > ctx->faDevCap) {
         if (ctx->faDev) cudaFree(ctx->faDev);
         if (ctx->faHost) cudaFreeHost(ctx->faHost);
@@ -575,7 +576,7 @@ extern "C" int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, c
     CK(ctx, cudaEventRecord(ctx->faEv[0], s));
     lsdb_launch_fa(s, nTasks, (LsdbFaTask*)(D + oTasks), (LsdbFaLine*)(D + oLines), (int*)(D + oLoff), (double*)(D + oPts),
                    (int*)(D + oPoff), (double*)(D + oLid), (double*)(D + oLast), m->linesD, m->cacheD, m->cols, m->rows,
-                   4.0 * lsdm_atan(1.0), (LsdbFaHyp*)(D + oOut));
+                   4.0 * lsdm_atan(1.0), (LsdbFaHyp*)(D + oOut), D + oPose);
     CK(ctx, cudaEventRecord(ctx->faEv[1], s));
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpyAsync(H + oOut, D + oOut, sizeof(LsdbFaHyp) * (size_t)nTasks * 4, cudaMemcpyDeviceToHost, s));

@@ -101,4 +101,5 @@ struct LsdbFaHyp { int frame, iScan, iMap, iPair; double x, y, ang, score; };  /
 struct LsdbFaLine { double k, b, dx, dy, x1, y1, x2, y2, len; int orient, pad; };  // == lsdb_line
 void lsdb_launch_fa(cudaStream_t s, int nTasks, const LsdbFaTask* tasks, const LsdbFaLine* scanLines, const int* scanLineOff,
                     const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
-                    const LsdbFaLine* mapLines, const double* mapCache, int cols, int rows, double pi, LsdbFaHyp* out);
+                    const LsdbFaLine* mapLines, const double* mapCache, int cols, int rows, double pi, LsdbFaHyp* out, void* poseBuf);
+size_t lsdb_fa_pose_bytes(int nTasks);
