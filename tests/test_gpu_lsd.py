@@ -210,3 +210,22 @@ def test_giant_map_on_one_gpu(lsdb, ctx):
     st = b.stats()
     assert st["accepts"] == o["stats"]["accepts"] and st["rejects"] == o["stats"]["rejects"] and st["live_seeds"] == o["stats"]["live_seeds"]
     b.close()
+
+
+def test_error_paths_fail_loudly_and_leave_the_context_usable(lsdb, ctx, gold):
+    """No silent truncation: a segment table that is too small is an LSDB_ERR_CAPACITY error, bad parameters are
+    LSDB_ERR_ARG, and the context keeps working afterwards."""
+    m = gold["mapValue/map"]
+    b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0])], max_lines=5)        # the map has 41 segments
+    b.upload([m]); b.run()
+    with pytest.raises(lsdb.LsdbError, match="CAPACITY"):
+        b.download()
+    b.close()
+    with pytest.raises(lsdb.LsdbError, match="ARG"):
+        lsdb.Batch(ctx, [(m.shape[1], m.shape[0])], pseBin=5000)
+    with pytest.raises(lsdb.LsdbError, match="ARG"):
+        lsdb.Batch(ctx, [(m.shape[1], m.shape[0])], sca=0.5)             # Gaussian half-width != 8: only sig/sca = 2 is built
+    with pytest.raises(lsdb.LsdbError, match="ARG"):
+        lsdb.Batch(ctx, [(0, 10)])
+    r = ctx.lsd(m)                                                       # still fine
+    assert r["n"] == 41
