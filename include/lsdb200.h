@@ -146,6 +146,21 @@ int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int n_frames, const lsdb_
                   const int* scan_line_off, const double* scan_pts, const int* scan_pt_off,
                   const double* lidar_pose, const double* last_pose, lsdb_hypothesis* out, int max_hyp,
                   int* n_hyp);
+/* The per-frame reduction that follows the scoring in FeatureAssociation (LSD/myFA.cpp:65-171, everything before ukf),
+ * done on the device so that only one record per frame comes back instead of every hypothesis:
+ *   n_kept  : hypotheses with score < 3 (:261); 0 = "no match, start a new chain" (:70-90)
+ *   best_*  : the lowest-score hypothesis — the pose of the first frame of a chain (:100-110)
+ *   mean_*  : the 1/score^2 weighted mean over the kept hypotheses in ascending score order (:160-171) and
+ *             mean_score = 1/sqrt(sum(w)/n_kept): the poseEstimate handed to ukf */
+typedef struct {
+    int n_hyp, n_kept;
+    double best_x, best_y, best_ang, best_score;
+    double mean_x, mean_y, mean_ang, mean_score;
+} lsdb_fa_estimate;
+/* same inputs as lsdb_fa_score; out[n_frames] */
+int lsdb_fa_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, int n_frames, const lsdb_line* scan_lines,
+                            const int* scan_line_off, const double* scan_pts, const int* scan_pt_off,
+                            const double* lidar_pose, const double* last_pose, lsdb_fa_estimate* out);
 /* device time of the last lsdb_fa_score kernel (ms) */
 float lsdb_fa_last_ms(const lsdb_ctx* ctx);
 

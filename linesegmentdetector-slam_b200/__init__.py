@@ -23,6 +23,8 @@ STAT_FIELDS = ["cells", "live_seeds", "grows", "grown_px", "small", "regrows", "
 LINE_DTYPE = np.dtype([("k", "f8"), ("b", "f8"), ("dx", "f8"), ("dy", "f8"), ("x1", "f8"), ("y1", "f8"), ("x2", "f8"),
                        ("y2", "f8"), ("len", "f8"), ("orient", "i4"), ("_pad", "i4")])
 RECT_FIELDS = ["x1", "y1", "x2", "y2", "wid", "cX", "cY", "deg", "dx", "dy", "p", "prec", "logNFA"]
+EST_DTYPE = np.dtype([("n_hyp", "i4"), ("n_kept", "i4"), ("best_x", "f8"), ("best_y", "f8"), ("best_ang", "f8"), ("best_score", "f8"),
+                      ("mean_x", "f8"), ("mean_y", "f8"), ("mean_ang", "f8"), ("mean_score", "f8")])
 HYP_DTYPE = np.dtype([("frame", "i4"), ("i_scan", "i4"), ("i_map", "i4"), ("i_pair", "i4"), ("x", "f8"), ("y", "f8"),
                       ("ang", "f8"), ("score", "f8")])
 
@@ -74,6 +76,7 @@ def lib():
         L.lsdb_fa_map_create.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(vp)]
         L.lsdb_fa_map_destroy.argtypes = [vp]; L.lsdb_fa_map_destroy.restype = None
         L.lsdb_fa_score.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+        L.lsdb_fa_estimate_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]
         L.lsdb_fa_last_ms.argtypes = [vp]; L.lsdb_fa_last_ms.restype = C.c_float
         _lib = L
     return _lib
@@ -258,8 +261,7 @@ class FaMap:
         ctx.check(lib().lsdb_fa_map_create(ctx.h, _p(mc), cols, rows, _p(ml), len(ml), C.byref(self.h)), "lsdb_fa_map_create")
         self.n_lines = len(ml)
 
-    def score(self, frames, max_hyp=None):
-        """frames: list of dicts(scan_lines=(n,10) or LINE_DTYPE, pts=(P,2), lidar_pose=(2,), last_pose=(3,))."""
+    def _marshal(self, frames):
         nf = len(frames)
         sl = [f["scan_lines"] if getattr(f["scan_lines"], "dtype", None) == LINE_DTYPE else array_to_lines(f["scan_lines"])
               for f in frames]
@@ -270,12 +272,25 @@ class FaMap:
         pts = np.ascontiguousarray(np.concatenate([np.asarray(f["pts"], np.float64).reshape(-1, 2) for f in frames])) if nf else np.zeros((0, 2))
         lid = np.ascontiguousarray(np.array([f["lidar_pose"] for f in frames], np.float64).reshape(nf, 2))
         last = np.ascontiguousarray(np.array([f["last_pose"] for f in frames], np.float64).reshape(nf, 3))
+        return nf, lines, loff, pts, poff, lid, last
+
+    def score(self, frames, max_hyp=None):
+        """frames: list of dicts(scan_lines=(n,10) or LINE_DTYPE, pts=(P,2), lidar_pose=(2,), last_pose=(3,))."""
+        nf, lines, loff, pts, poff, lid, last = self._marshal(frames)
         if max_hyp is None:
             max_hyp = max(4 * int(loff[-1]) * max(self.n_lines, 1), 4)
         out = np.zeros(max_hyp, HYP_DTYPE); n = C.c_int(0)
         self.ctx.check(lib().lsdb_fa_score(self.ctx.h, self.h, nf, _p(lines), _p(loff), _p(pts), _p(poff), _p(lid), _p(last),
                                            _p(out), max_hyp, C.byref(n)), "lsdb_fa_score")
         return out[:n.value].copy()
+
+    def estimate(self, frames):
+        """Per-frame reduction on the device (lsdb_fa_estimate_frames): one EST_DTYPE record per frame."""
+        nf, lines, loff, pts, poff, lid, last = self._marshal(frames)
+        out = np.zeros(nf, EST_DTYPE)
+        self.ctx.check(lib().lsdb_fa_estimate_frames(self.ctx.h, self.h, nf, _p(lines), _p(loff), _p(pts), _p(poff), _p(lid), _p(last),
+                                                     _p(out)), "lsdb_fa_estimate_frames")
+        return out
 
     def last_ms(self):
         return float(lib().lsdb_fa_last_ms(self.ctx.h))

@@ -9,6 +9,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <math.h>
 #include <string>
 #include <vector>
 
@@ -523,17 +525,20 @@ extern "C" float lsdb_fa_last_ms(const lsdb_ctx* ctx) { return ctx ? ctx->faMs :
 
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-extern "C" int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_line* scanLines, const int* lineOff,
-                             const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
-                             lsdb_hypothesis* out, int maxHyp, int* nHyp) {
+// scoring of n_frames frames; hypotheses (out, may be NULL) and / or the per-frame reduction (est, may be NULL)
+static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_line* scanLines, const int* lineOff,
+                  const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
+                  lsdb_hypothesis* out, int maxHyp, int* nHyp, lsdb_fa_estimate* est) {
     if (!ctx || !m || nFrames < 0 || !lineOff || !ptOff || !nHyp || (nFrames > 0 && (!lidarPose || !lastPose)))
         return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score: bad argument%s");
     static_assert(sizeof(lsdb_hypothesis) == sizeof(LsdbFaHyp), "layout");
     static_assert(sizeof(lsdb_line) == sizeof(LsdbFaLine), "layout");
+    static_assert(sizeof(lsdb_fa_estimate) == sizeof(LsdbFaEst), "layout");
     CK(ctx, cudaSetDevice(ctx->device));
     // pair filter, LSD/myFA.cpp:29-41 (ignoreScanLength = 40, scanToMapDiff = 0.35; LSD/baseFunc.h:80-82)
     std::vector<LsdbFaTask> tasks;
-    for (int f = 0; f < nFrames; f++)
+    std::vector<int> hypOff(nFrames + 1, 0);
+    for (int f = 0; f < nFrames; f++) {
         for (int is = 0; is < lineOff[f + 1] - lineOff[f]; is++) {
             const double lenS = scanLines[lineOff[f] + is].len;
             if (lenS < 40) continue;
@@ -545,16 +550,22 @@ extern "C" int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, c
                 tasks.push_back(t);
             }
         }
+        hypOff[f + 1] = (int)tasks.size() * 4;
+    }
     const int nTasks = (int)tasks.size();
     *nHyp = nTasks * 4;
-    if (nTasks == 0) return LSDB_OK;
-    if (nTasks * 4 > maxHyp) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_fa_score: %s%lld hypotheses exceed max_hyp", "", (long long)nTasks * 4);
+    if (nTasks == 0) {
+        if (est) for (int f = 0; f < nFrames; f++) { memset(&est[f], 0, sizeof est[f]); est[f].best_score = est[f].mean_score = INFINITY; }
+        return LSDB_OK;
+    }
+    if (out && nTasks * 4 > maxHyp) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_fa_score: %s%lld hypotheses exceed max_hyp", "", (long long)nTasks * 4);
     const int nL = lineOff[nFrames], nP = ptOff[nFrames];
     const size_t oTasks = 0, oLines = oTasks + al256(sizeof(LsdbFaTask) * nTasks), oLoff = oLines + al256(sizeof(LsdbFaLine) * nL),
                  oPts = oLoff + al256(sizeof(int) * (nFrames + 1)), oPoff = oPts + al256(16 * (size_t)nP),
                  oLid = oPoff + al256(sizeof(int) * (nFrames + 1)), oLast = oLid + al256(16 * (size_t)nFrames),
-                 oOut = oLast + al256(24 * (size_t)nFrames), oPose = oOut + al256(sizeof(LsdbFaHyp) * (size_t)nTasks * 4),
-                 total = oPose + al256(lsdb_fa_pose_bytes(nTasks));
+                 oHoff = oLast + al256(24 * (size_t)nFrames), oOut = oHoff + al256(sizeof(int) * (nFrames + 1)),
+                 oPose = oOut + al256(sizeof(LsdbFaHyp) * (size_t)nTasks * 4), oEst = oPose + al256(lsdb_fa_pose_bytes(nTasks)),
+                 total = oEst + al256(sizeof(LsdbFaEst) * (size_t)nFrames);
     if (total > ctx->faDevCap) {
         if (ctx->faDev) cudaFree(ctx->faDev);
         if (ctx->faHost) cudaFreeHost(ctx->faHost);
@@ -571,17 +582,53 @@ extern "C" int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, c
     memcpy(H + oPoff, ptOff, sizeof(int) * (nFrames + 1));
     memcpy(H + oLid, lidarPose, 16 * (size_t)nFrames);
     memcpy(H + oLast, lastPose, 24 * (size_t)nFrames);
+    memcpy(H + oHoff, hypOff.data(), sizeof(int) * (nFrames + 1));
     cudaStream_t s = ctx->stream;
     CK(ctx, cudaMemcpyAsync(D, H, oOut, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaEventRecord(ctx->faEv[0], s));
     lsdb_launch_fa(s, nTasks, (LsdbFaTask*)(D + oTasks), (LsdbFaLine*)(D + oLines), (int*)(D + oLoff), (double*)(D + oPts),
                    (int*)(D + oPoff), (double*)(D + oLid), (double*)(D + oLast), m->linesD, m->cacheD, m->cols, m->rows,
                    4.0 * lsdm_atan(1.0), (LsdbFaHyp*)(D + oOut), D + oPose);
+    if (est) lsdb_launch_fa_reduce(s, nFrames, (LsdbFaHyp*)(D + oOut), (int*)(D + oHoff), (LsdbFaEst*)(D + oEst));
     CK(ctx, cudaEventRecord(ctx->faEv[1], s));
     CK(ctx, cudaGetLastError());
-    CK(ctx, cudaMemcpyAsync(H + oOut, D + oOut, sizeof(LsdbFaHyp) * (size_t)nTasks * 4, cudaMemcpyDeviceToHost, s));
+    if (out) CK(ctx, cudaMemcpyAsync(H + oOut, D + oOut, sizeof(LsdbFaHyp) * (size_t)nTasks * 4, cudaMemcpyDeviceToHost, s));
+    if (est) CK(ctx, cudaMemcpyAsync(H + oEst, D + oEst, sizeof(LsdbFaEst) * (size_t)nFrames, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ctx->faMs, ctx->faEv[0], ctx->faEv[1]));
-    memcpy(out, H + oOut, sizeof(LsdbFaHyp) * (size_t)nTasks * 4);
+    if (out) memcpy(out, H + oOut, sizeof(LsdbFaHyp) * (size_t)nTasks * 4);
+    if (est) {
+        memcpy(est, H + oEst, sizeof(LsdbFaEst) * (size_t)nFrames);
+        for (int f = 0; f < nFrames; f++) {
+            if (est[f].n_kept >= 0) continue;
+            // more kept hypotheses than the device sort holds: same reduction on the host, from the device's scores
+            std::vector<LsdbFaHyp> hv((size_t)(hypOff[f + 1] - hypOff[f]));
+            CK(ctx, cudaMemcpy(hv.data(), D + oOut + sizeof(LsdbFaHyp) * (size_t)hypOff[f], sizeof(LsdbFaHyp) * hv.size(), cudaMemcpyDeviceToHost));
+            std::vector<LsdbFaHyp> kept;
+            for (size_t k = 0; k < hv.size(); k++) if (hv[k].score < 3) kept.push_back(hv[k]);
+            std::stable_sort(kept.begin(), kept.end(), [](const LsdbFaHyp& a, const LsdbFaHyp& b) { return a.score < b.score; });
+            lsdb_fa_estimate& E = est[f];
+            E.n_kept = (int)kept.size();
+            E.best_x = kept[0].x; E.best_y = kept[0].y; E.best_ang = kept[0].ang; E.best_score = kept[0].score;
+            double sx = 0, sy = 0, sa = 0, sw = 0;
+            for (size_t k = 0; k < kept.size(); k++) { const double w = 1 / (kept[k].score * kept[k].score); sx += kept[k].x * w; sy += kept[k].y * w; sa += kept[k].ang * w; sw += w; }
+            E.mean_x = sx / sw; E.mean_y = sy / sw; E.mean_ang = sa / sw; E.mean_score = 1 / sqrt(sw / E.n_kept);
+        }
+    }
     return LSDB_OK;
+}
+
+extern "C" int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_line* scanLines, const int* lineOff,
+                             const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
+                             lsdb_hypothesis* out, int maxHyp, int* nHyp) {
+    if (!out) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score: bad argument%s");
+    return fa_run(ctx, m, nFrames, scanLines, lineOff, pts, ptOff, lidarPose, lastPose, out, maxHyp, nHyp, 0);
+}
+
+extern "C" int lsdb_fa_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_line* scanLines, const int* lineOff,
+                                       const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
+                                       lsdb_fa_estimate* out) {
+    if (!out) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_estimate_frames: bad argument%s");
+    int nHyp = 0;
+    return fa_run(ctx, m, nFrames, scanLines, lineOff, pts, ptOff, lidarPose, lastPose, 0, 0, &nHyp, out);
 }

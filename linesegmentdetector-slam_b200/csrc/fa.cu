@@ -116,6 +116,76 @@ __global__ void __launch_bounds__(FA_THREADS) lsdb_fa_score_kernel(int nHyp, con
     }
 }
 
+// ------------------------------------------------------------------ per-frame reduction (LSD/myFA.cpp:65-171, the part before ukf)
+// One CTA per frame: keep the hypotheses with score < 3 (:261), order them by score (CompScore :398-402; ties by
+// (scan line, map line, pairing), i.e. a stable sort of the launch order), then the best one (first frame of a chain,
+// :100-110) and the 1/score^2 weighted mean accumulated IN THAT ORDER by one thread (:160-171) — the same operations
+// in the same order as the host tail of host/myFA_b200.cpp, so the estimate is bit-identical to it.
+#define FA_RED_THREADS 256
+#define FA_RED_CAP 2048
+__global__ void __launch_bounds__(FA_RED_THREADS) lsdb_fa_reduce_kernel(const LsdbFaHyp* __restrict__ hyp, const int* __restrict__ hypOff,
+                                                                        LsdbFaEst* __restrict__ est) {
+    __shared__ double key[FA_RED_CAP];
+    __shared__ int idx[FA_RED_CAP];
+    __shared__ int nKept;
+    const int f = blockIdx.x, a = hypOff[f], b = hypOff[f + 1];
+    if (threadIdx.x == 0) nKept = 0;
+    __syncthreads();
+    for (int h = a + threadIdx.x; h < b; h += FA_RED_THREADS) {
+        const double sc = hyp[h].score;
+        if (sc < 3) {
+            const int k = atomicAdd(&nKept, 1);
+            if (k < FA_RED_CAP) { key[k] = sc; idx[k] = h; }
+        }
+    }
+    __syncthreads();
+    const int n = nKept;
+    LsdbFaEst E;
+    E.nHyp = b - a; E.nKept = n;
+    E.bx = E.by = E.bang = 0; E.bscore = INFINITY; E.mx = E.my = E.mang = 0; E.mscore = INFINITY;
+    if (n == 0 || n > FA_RED_CAP) {
+        if (n > FA_RED_CAP) E.nKept = -n;   // too many for the shared-memory sort: the caller reduces on the host
+        if (threadIdx.x == 0) est[f] = E;
+        return;
+    }
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int k = n + threadIdx.x; k < m; k += FA_RED_THREADS) { key[k] = INFINITY; idx[k] = 0x7fffffff; }
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)          // bitonic sort on (score, launch index)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < m; t += FA_RED_THREADS) {
+                const int p = t ^ stride;
+                if (p > t) {
+                    const bool up = (t & size) == 0;
+                    const bool gt = key[t] > key[p] || (key[t] == key[p] && idx[t] > idx[p]);
+                    if (gt == up) {
+                        const double kk = key[t]; key[t] = key[p]; key[p] = kk;
+                        const int ii = idx[t]; idx[t] = idx[p]; idx[p] = ii;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        const LsdbFaHyp best = hyp[idx[0]];
+        E.bx = best.x; E.by = best.y; E.bang = best.ang; E.bscore = best.score;
+        double sumX = 0, sumY = 0, sumAng = 0, sumW = 0;
+        for (int k = 0; k < n; k++) {
+            const LsdbFaHyp h = hyp[idx[k]];
+            const double w = 1 / (h.score * h.score);
+            sumX += h.x * w; sumY += h.y * w; sumAng += h.ang * w; sumW += w;
+        }
+        E.mx = sumX / sumW; E.my = sumY / sumW; E.mang = sumAng / sumW;
+        E.mscore = 1 / sqrt(sumW / n);
+        est[f] = E;
+    }
+}
+
+void lsdb_launch_fa_reduce(cudaStream_t s, int nFrames, const LsdbFaHyp* hyp, const int* hypOff, LsdbFaEst* est) {
+    if (nFrames > 0) lsdb_fa_reduce_kernel<<<nFrames, FA_RED_THREADS, 0, s>>>(hyp, hypOff, est);
+}
+
 size_t lsdb_fa_pose_bytes(int nTasks) { return sizeof(FaPose) * (size_t)nTasks * 4; }
 
 void lsdb_launch_fa(cudaStream_t s, int nTasks, const LsdbFaTask* tasks, const LsdbFaLine* scanLines, const int* scanLineOff,

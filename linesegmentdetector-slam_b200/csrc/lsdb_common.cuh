@@ -103,3 +103,5 @@ void lsdb_launch_fa(cudaStream_t s, int nTasks, const LsdbFaTask* tasks, const L
                     const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
                     const LsdbFaLine* mapLines, const double* mapCache, int cols, int rows, double pi, LsdbFaHyp* out, void* poseBuf);
 size_t lsdb_fa_pose_bytes(int nTasks);
+struct LsdbFaEst { int nHyp, nKept; double bx, by, bang, bscore, mx, my, mang, mscore; };  // == lsdb_fa_estimate
+void lsdb_launch_fa_reduce(cudaStream_t s, int nFrames, const LsdbFaHyp* hyp, const int* hypOff, LsdbFaEst* est);

@@ -2,9 +2,10 @@
 //
 // The scoring half — the pair filter :29-41, the pthread pool dispatch :22-63 and, per task,
 // thread_ScanToMapMatch :186-272 (NormalizedLineDirection :274-305, rotateScanIm :307-355, CalcScore
-// :357-396) — runs as ONE kernel launch through lsdb_fa_score.  What the north star keeps on the host
-// stays on the host: the hidden-Markov gating / weighted mean below (this file, re-stated from :65-171)
-// and the reference's own myfa::ukf (:404-536), which is called, not re-implemented.
+// :357-396) — and the reduction that follows it (keep score < 3, order by score, best hypothesis /
+// 1/score^2 weighted mean, :65-171) run on the device through lsdb_fa_estimate_frames.  The branch logic
+// of the hidden-Markov chain (first frame / tracking / lost) stays here, and the reference's own
+// myfa::ukf (:404-536) is called, not re-implemented.
 //
 // Build: compile against the reference's myFA.h; the reference's myFA.cpp stays in the build for ukf()
 // with its FeatureAssociation renamed away (-DFeatureAssociation=FeatureAssociation_cpu on that TU, see
@@ -90,57 +91,35 @@ structFAOutput FeatureAssociation(structFAInput* FAInput) {
     for (int i = 0; i < nPts; i++) { pts[2 * i] = FAInput->scanImPoint[i].x; pts[2 * i + 1] = FAInput->scanImPoint[i].y; }
     const double lidar[2] = {FAInput->lidarPose.x, FAInput->lidarPose.y};
     const double last[3] = {FAInput->lastPose.x, FAInput->lastPose.y, FAInput->lastPose.ang};
-    const int cap = 4 * (nScan > 0 ? nScan : 1) * (nMap > 0 ? nMap : 1);
-    std::vector<lsdb_hypothesis> hyp(cap);
-    int nHyp = 0;
-    const int rc = lsdb_fa_score(ctx, m, 1, nScan ? (const lsdb_line*)&FAInput->scanLinesInfo[0] : 0, lineOff, pts.data(), ptOff,
-                                 lidar, last, hyp.data(), cap, &nHyp);
-    if (rc != LSDB_OK) lsdb_host::die("lsdb_fa_score", rc);
-
-    // keep what thread_ScanToMapMatch keeps: score < 3 (LSD/myFA.cpp:261)
-    std::vector<structScore> Score;
-    for (int i = 0; i < nHyp; i++) {
-        if (!(hyp[i].score < 3)) continue;
-        structScore s;
-        s.pos.x = hyp[i].x; s.pos.y = hyp[i].y; s.pos.ang = hyp[i].ang;
-        s.rotateScanImPoint = 0;
-        s.score = hyp[i].score;
-        Score.push_back(s);
-    }
-    if (Score.empty()) return lost_track();
-
-    // ascending by score (CompScore, :398-402); stable, so ties keep (scan, map, pairing) order
-    std::stable_sort(Score.begin(), Score.end(), [](const structScore& a, const structScore& b) { return a.score < b.score; });
+    (void)nMap;
+    // scoring AND the reduction that follows it (keep score < 3, order by score, best / weighted mean) run on the device;
+    // one record comes back
+    lsdb_fa_estimate est;
+    const int rc = lsdb_fa_estimate_frames(ctx, m, 1, nScan ? (const lsdb_line*)&FAInput->scanLinesInfo[0] : 0, lineOff, pts.data(), ptOff,
+                                           lidar, last, &est);
+    if (rc != LSDB_OK) lsdb_host::die("lsdb_fa_estimate_frames", rc);
+    if (est.n_kept == 0) return lost_track();
 
     structFAOutput out;
     if (fabs(FAInput->lastPose.x + 1) < 0.0001) {   // first frame of a chain: take the best hypothesis (:100-110)
         out.kalman_x = FAInput->kalman_x;
         out.kalman_P = FAInput->kalman_P;
-        out.kalman_x(0) = Score[0].pos.x;
-        out.kalman_x(1) = Score[0].pos.y;
-        out.kalman_x(2) = Score[0].pos.ang;
-        printf("Score:%lf\n", Score[0].score);
+        out.kalman_x(0) = est.best_x;
+        out.kalman_x(1) = est.best_y;
+        out.kalman_x(2) = est.best_ang;
+        printf("Score:%lf\n", est.best_score);
         return out;
     }
 
     // later frames: 1/score^2 weighted mean of every kept hypothesis (:160-171), then the reference's UKF
-    double sumX = 0, sumY = 0, sumAng = 0, sumW = 0;
-    const int n = (int)Score.size();
-    for (int i = 0; i < n; i++) {
-        const double w = 1 / (Score[i].score * Score[i].score);
-        sumX += Score[i].pos.x * w;
-        sumY += Score[i].pos.y * w;
-        sumAng += Score[i].pos.ang * w;
-        sumW += w;
-    }
-    structScore est;
-    est.pos.x = sumX / sumW;
-    est.pos.y = sumY / sumW;
-    est.pos.ang = sumAng / sumW;
-    est.rotateScanImPoint = 0;
-    est.score = 1 / sqrt(sumW / n);
-    printf("Score:%lf\n", est.score);
-    return ukf(FAInput, est);
+    structScore e;
+    e.pos.x = est.mean_x;
+    e.pos.y = est.mean_y;
+    e.pos.ang = est.mean_ang;
+    e.rotateScanImPoint = 0;
+    e.score = est.mean_score;
+    printf("Score:%lf\n", e.score);
+    return ukf(FAInput, e);
 }
 
 }  // namespace myfa

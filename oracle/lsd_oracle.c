@@ -5,7 +5,7 @@
  * drops the accidental O(seeds x image) work (per-grow Mat::zeros :519, per-NFA degMap scan
  * :940-945, full-image commit loops :243-248,259-265), which does not change any result.
  * libm calls go through lsd_math.h, i.e. this is "oracle (ii)" arithmetic;
- * tests/test_oracle_vs_ref.py pins it bit-for-bit to oracle/_ref/libref_lsdm.so (the
+ * tests/test_oracle.py pins it bit-for-bit to oracle/_ref/libref_lsdm.so (the
  * unmodified reference on the same arithmetic) and compares with libref_glibc.so.
  *
  * Documented deviations (all are undefined behaviour in the reference):

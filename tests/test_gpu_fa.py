@@ -83,3 +83,41 @@ def test_map_cache_device_matches_reference(lsdb, ctx):
     assert np.all(ctx.map_cache(blank, 0.05) == 1.0)
     full = np.ones((30, 30), np.uint8)
     assert np.all(ctx.map_cache(full, 0.05) == 0.0)
+
+
+def test_fa_estimate_matches_host_reduction(lsdb, ctx):
+    """lsdb_fa_estimate_frames (device reduction, LSD/myFA.cpp:65-171 minus ukf) == the same reduction done on the host
+    from lsdb_fa_score's hypotheses, bit for bit: keep score < 3, stable ascending sort, best, 1/score^2 weighted mean
+    accumulated in that order."""
+    g = np.load(os.path.join(GOLD, "fa_frames.npz"))
+    gm = np.load(os.path.join(GOLD, "bundled_maps.npz"))
+    mc = oraclebind.map_cache(gm["mapValue/map"], float(gm["mapValue/param"][2]))
+    nf = int(g["n_frames"])
+    frames = [dict(scan_lines=g[f"f{f}/scan_lines"], pts=g[f"f{f}/pts"], lidar_pose=g[f"f{f}/lidar_pose"],
+                   last_pose=[-1.0, -1.0, 0.0]) for f in range(nf)]
+    frames.append(dict(scan_lines=np.zeros((0, 10)), pts=np.zeros((0, 2)), lidar_pose=[0, 0], last_pose=[-1, -1, 0]))   # no hypotheses
+    frames.append(dict(frames[0], last_pose=[1e6, 1e6, 0.0]))                                                            # everything gated out
+    fm = lsdb.FaMap(ctx, mc, g["map_lines"])
+    hyp = fm.score(frames)
+    est = fm.estimate(frames)
+    assert len(est) == len(frames)
+    some = 0
+    for f in range(len(frames)):
+        h = hyp[hyp["frame"] == f]
+        assert est["n_hyp"][f] == len(h)
+        kept = h[h["score"] < 3]
+        assert est["n_kept"][f] == len(kept)
+        if len(kept) == 0:
+            continue
+        kept = kept[np.argsort(kept["score"], kind="stable")]
+        assert (est["best_x"][f], est["best_y"][f], est["best_ang"][f], est["best_score"][f]) == \
+            (kept["x"][0], kept["y"][0], kept["ang"][0], kept["score"][0])
+        sx = sy = sa = sw = 0.0
+        for k in range(len(kept)):                       # sequential, like the reference's loop
+            w = 1.0 / (kept["score"][k] * kept["score"][k])
+            sx += kept["x"][k] * w; sy += kept["y"][k] * w; sa += kept["ang"][k] * w; sw += w
+        assert est["mean_x"][f] == sx / sw and est["mean_y"][f] == sy / sw and est["mean_ang"][f] == sa / sw
+        assert est["mean_score"][f] == 1.0 / np.sqrt(sw / len(kept))
+        some += 1
+    assert some >= 6
+    fm.close()
