@@ -9,7 +9,7 @@
 // Occupancy grids are sparse: after the remap ~1 % of the source pixels are non-zero.  Adding a
 // zero tap is exact (v + (+0*k) = v, and every non-zero tap is positive, so no -0 can arise), so
 // the passes only touch non-zero taps:
-//   * staging builds one bit per source pixel (non-zero after the remap) next to the bytes;
+//   * staging builds one bit per source pixel (non-zero after the remap); the bytes themselves stay in global memory;
 //   * X pass: the 17-tap window of an output is a 17-bit slice of its row's bit vector; an empty
 //     slice costs one funnel shift, a non-empty one accumulates exactly its set taps in ascending
 //     tap order and flags the element in a per-column bit vector over the rows;
@@ -35,7 +35,6 @@ struct StencilSmem {
     double g[GW * GW];
     double taps[3 * 17];
     double wmax[8];
-    unsigned char src[LSDB_SRC_MAX * SRC_PITCH];
     unsigned int rowBits[LSDB_SRC_MAX * ROW_WORDS];          // bit x of row r: src[r][x] != 0
     unsigned int colBits[GW * ROW_WORDS];                    // bit r of column c: aux[r][c] != 0
     short idxX[GW * 17];
@@ -87,7 +86,7 @@ __device__ __forceinline__ unsigned int bits17(const unsigned int* v, int s) {
     return __funnelshift_r(lo, hi, s & 31) & 0x1ffffu;
 }
 
-__global__ void __launch_bounds__(NT) lsdb_stencil_kernel(const LsdbImg* __restrict__ imgs, const int* __restrict__ tileImg,
+__global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __restrict__ imgs, const int* __restrict__ tileImg,
                                                           LsdbImgDyn* __restrict__ dyn, const LsdbLsdConst* __restrict__ kc,
                                                           const uint8_t* __restrict__ src, double* __restrict__ mag,
                                                           double* __restrict__ deg, double* __restrict__ cosm,
@@ -143,6 +142,7 @@ __global__ void __launch_bounds__(NT) lsdb_stencil_kernel(const LsdbImg* __restr
             int gy = sy0 + r;
             const uint4 q = *reinterpret_cast<const uint4*>(base + (size_t)gy * im.srcPitch + ax0 + 16 * v);
             unsigned int w[4] = {q.x, q.y, q.z, q.w};
+            if ((q.x | q.y | q.z | q.w) == 0u) continue;   // free space: stays 0, nothing to flag (the common case)
             if (gy >= 1) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -152,7 +152,6 @@ __global__ void __launch_bounds__(NT) lsdb_stencil_kernel(const LsdbImg* __restr
                     w[k] = rmp;
                 }
             }
-            *reinterpret_cast<uint4*>(&S.src[r * SRC_PITCH + 16 * v]) = make_uint4(w[0], w[1], w[2], w[3]);
             const unsigned int nz = nz4(w[0]) | (nz4(w[1]) << 4) | (nz4(w[2]) << 8) | (nz4(w[3]) << 12);
             if (nz) {
                 atomicOr(&S.rowBits[r * ROW_WORDS + (v >> 1)], nz << ((v & 1) * 16));
@@ -186,13 +185,19 @@ __global__ void __launch_bounds__(NT) lsdb_stencil_kernel(const LsdbImg* __restr
                 for (int i = 0; i < 17; i++) { const int p = ix[i]; m |= ((rb[p >> 5] >> (p & 31)) & 1u) << i; }
             }
             if (m) {
-                const unsigned char* row = &S.src[r * SRC_PITCH];
+                // the few non-zero taps are re-read from global memory (L1/L2 hits: the window was just staged) and remapped
+                // on the fly; only the bit vectors live in shared memory, which buys a fourth resident CTA per SM
+                const int gy = sy0 + r;
+                const uint8_t* row = src + im.srcOff + (size_t)gy * im.srcPitch + ax0;
                 const double* ker = &S.taps[((gxs + c) % 3) * 17];
                 double v = 0.0;
                 while (m) {
                     const int i = __ffs(m) - 1;
                     m &= m - 1;
-                    v += (double)row[ix[i]] * ker[i];
+                    const int px = ix[i];
+                    unsigned int b = row[px];
+                    if (gy >= 1 && ax0 + px >= 1) b = b == 1u ? 255u : b;   // :135-142 (255 -> 0 never has its bit set)
+                    v += (double)b * ker[i];
                 }
                 S.u.aux[r * GW + c] = v;
                 atomicOr(&S.colBits[c * ROW_WORDS + (r >> 5)], 1u << (r & 31));
