@@ -347,7 +347,7 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 256 maps of 4096^2 (profiles/r1z_ncu_full_summary.txt),
                          # scaled to this launch's map count: the extra over the algorithmic bytes is the cos/sin planes of growable
                          # pixels, the u32 state word (instead of the reference's u8 usedMap) and the ban bit plane
-                         "traffic": 13.57e9 * (n * size * size) / (256 * 4096 * 4096) if size == 4096 else None,
+                         "traffic": 13.02e9 * (n * size * size) / (256 * 4096 * 4096) if size == 4096 else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": last["stencil"],
                          "share_of_step": last["stencil"] / sum(last.values())},
