@@ -1618,11 +1618,8 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
                       int* imgCounter, unsigned int* banBits, int bmCapWords, int steal) {
     if (runAhead <= 0 || runAhead > RING - (NW_MAX + 1) * LSDB_SUPER) runAhead = RING - (NW_MAX + 1) * LSDB_SUPER;
     if (runAhead < 1) runAhead = 1;
-    static int attrSet = -1;
-    if (attrSet < bmCapWords) {
-        cudaFuncSetAttribute(lsdb_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
-        attrSet = bmCapWords;
-    }
+    // per device and cheap: set on every launch (a process may drive several GPUs through several contexts)
+    cudaFuncSetAttribute(lsdb_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
     if (nImgs > 0)
         lsdb_grow_kernel<<<nCtas, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta), s>>>(nImgs, imgs, dyn, kc, mag, deg, cosm, sinm, state, cells, labels, rects,
                                                                                 maxSeg, lists, listCap, arenaCap, runAhead, recBuf, lgammaTab, lgammaN,

@@ -123,10 +123,6 @@ __global__ void __launch_bounds__(1024) lsdb_order_kernel(const LsdbImg* __restr
 void lsdb_launch_order(cudaStream_t s, int nImgs, const LsdbImg* imgs, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
                        const double* mag, unsigned short* bins, unsigned int* cells) {
     const int smem = (ORDER_WARPS * ORDER_BINS + 32) * sizeof(unsigned int);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lsdb_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr = true;
-    }
+    cudaFuncSetAttribute(lsdb_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, cheap
     if (nImgs > 0) lsdb_order_kernel<<<nImgs, 1024, smem, s>>>(imgs, dyn, kc, mag, bins, cells);
 }

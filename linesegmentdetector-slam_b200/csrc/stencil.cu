@@ -356,11 +356,7 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
                          unsigned int* state, unsigned int* banBits, double* gaussOut) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lsdb_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StencilSmem));
-        attr = true;
-    }
+    cudaFuncSetAttribute(lsdb_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StencilSmem));   // per device, cheap
     if (nTiles > 0)
         lsdb_stencil_kernel<<<nTiles, NT, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, gaussOut);
 }

@@ -229,3 +229,24 @@ def test_error_paths_fail_loudly_and_leave_the_context_usable(lsdb, ctx, gold):
         lsdb.Batch(ctx, [(0, 10)])
     r = ctx.lsd(m)                                                       # still fine
     assert r["n"] == 41
+
+
+def test_two_devices_in_one_process(lsdb, gold):
+    """One context per GPU inside one process ('one host thread/stream per GPU'): a batch split across two
+    devices by shard_range gives the same tables as the whole batch on one."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from lsdb200 import shard
+    names = NAMES[:4]
+    maps = [gold[n + "/map"] for n in names]
+    outs = []
+    for dev in range(2):
+        first, cnt = shard.shard_range(len(maps), dev, 2)
+        c = lsdb.Context(dev)
+        b = lsdb.Batch(c, [(m.shape[1], m.shape[0]) for m in maps[first:first + cnt]])
+        b.upload(maps[first:first + cnt]); b.run()
+        outs.extend(lsdb.lines_to_array(x) for x in b.download()["lines"])
+        b.close(); c.close()
+    for n, got in zip(names, outs):
+        assert np.array_equal(got, gold[n + "/lines"], equal_nan=True), n
