@@ -56,7 +56,9 @@ struct GrowShared {
     int img;
     int nChunks;
     int nCells;
-    volatile int chunkFlag[RING];            // 1 = evaluated, records parked
+    volatile int chunkFlag[RING];            // 1 = evaluated, records parked; 2 = being re-validated by an idle warp
+    volatile unsigned char chunkHeavy[RING]; // the chunk holds a parked large record (accept / reject / long no-change)
+    volatile int chunkSeen[RING];            // accept count when the chunk's heavy records were last re-validated
     // every super-chunk in flight owns one record arena (slot = super-chunk index mod NSLOTS), filled by bump allocation
     unsigned int slotHead[NSLOTS];
     volatile int slotPending[NSLOTS];        // large seeds of the super-chunk that are queued or being evaluated
@@ -1183,6 +1185,7 @@ __device__ void eval_large(WarpCtx& c, int p, int ci, const ChunkRecs& R) {
         R.off[ri] = (unsigned int)off; R.chk[ri] = chk; R.chkOff[ri] = (unsigned int)off + ARENA_HDR;
         R.pnd[ri] = pndN; R.pndOff[ri] = (unsigned int)(off + pndOff);
         R.oc[ri] = oc;
+        sh.chunkHeavy[chunkJ & (RING - 1)] = 1;
     }
     __syncwarp();
 }
@@ -1241,6 +1244,7 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
         qn += __popc(bal);
         R.oc[(size_t)((chunk0 + s) & (RING - 1)) * 32 + lane] = OC_NONE;
     }
+    if (lane < nSub) { sh.chunkHeavy[(chunk0 + lane) & (RING - 1)] = 0; sh.chunkSeen[(chunk0 + lane) & (RING - 1)] = -1; }
     __syncwarp();
     for (int base = 0; base < qn && !aborted(c); base += 32) {
         // ---- B
@@ -1441,6 +1445,64 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
     __syncwarp();
 }
 
+// Work for a warp that has nothing to claim: look just ahead of the commit frontier for a READY chunk whose parked large
+// result has ALREADY been invalidated (a pixel it accepted is banned now — that can only stay so), take its marks back
+// and evaluate the seed again, speculatively, against today's state.  Otherwise the retire walk would have to do that
+// evaluation itself, serially, when it gets there.  The chunk is locked (flag 2) meanwhile; the retire walk waits for 1.
+__device__ bool revalidate_ahead(WarpCtx& c, const unsigned int* cl, int nCells, int nChunks, const ChunkRecs& R) {
+    GrowShared& sh = *c.sh;
+    const int lane = c.lane;
+    int target = -1;
+    {   // 32 chunks after the frontier chunk, one per lane; the nearest candidate wins
+        const int f = __shfl_sync(FULL, (int)sh.frontier, 0);
+        const int t = f + 1 + lane;
+        const int slot = t & (RING - 1);
+        const bool candidate = t < nChunks && sh.chunkFlag[slot] == 1 && sh.chunkHeavy[slot] && sh.chunkSeen[slot] != sh.nSeg;
+        const unsigned int cm = __ballot_sync(FULL, candidate);
+        if (cm) {
+            const int l = __ffs(cm) - 1;
+            int ok = 0;
+            if (lane == l) ok = atomicCAS((int*)&sh.chunkFlag[slot], 1, 2) == 1;
+            ok = __shfl_sync(FULL, ok, l);
+            if (ok) target = __shfl_sync(FULL, t, l);
+        }
+    }
+    if (target < 0) return false;
+    __threadfence();
+    const int slot = target & (RING - 1);
+    const int seen = __shfl_sync(FULL, (int)sh.nSeg, 0);
+    const int ci = target * LSDB_CHUNK + lane;
+    const int myp = ci < nCells ? (int)cl[ci] : -1;
+    const size_t ri = (size_t)slot * 32 + lane;
+    const int recOc = R.oc[ri], recChk = R.chk[ri], recL0 = R.L0[ri];
+    const unsigned int recB0 = R.b0[ri], recB1 = R.b1[ri], recOff = R.off[ri], recChkOff = R.chkOff[ri];
+    const int recPnd = recOc != OC_NONE ? R.pnd[ri] : 0;
+    const unsigned int* earena = c.arenas + (size_t)slot_of_chunk(target) * c.arenaCap;
+    const bool heavy = myp >= 0 && (recOc == OC_ACCEPT || recOc == OC_REJECT || (recOc == OC_NOCHANGE && !(recChk >= 0 && recChk + recPnd <= 64)));
+    unsigned int todo = __ballot_sync(FULL, heavy && (lsdb_ld_state(&c.state[myp]) & 3u) == 0 && grid_hit(c, recB0, recB1, recL0));
+    bool did = false;
+    while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int nchk = __shfl_sync(FULL, recChk, k);
+        const bool stale = nchk < 0 || any_banned(c, earena + __shfl_sync(FULL, recChkOff, k), nchk);
+        if (!stale) continue;
+        const int oc = __shfl_sync(FULL, recOc, k);
+        if (oc == OC_ACCEPT || oc == OC_REJECT) {
+            const unsigned int* recp = earena + __shfl_sync(FULL, recOff, k);
+            unpark_pixels(c, recp + recp[28], (int)recp[26], target);
+        }
+        if (lane == 0) R.oc[(size_t)slot * 32 + k] = OC_NONE;
+        __syncwarp();
+        eval_large(c, __shfl_sync(FULL, myp, k), target * LSDB_CHUNK + k, R);
+        did = true;
+    }
+    __threadfence();
+    if (lane == 0) { sh.chunkSeen[slot] = seen; sh.chunkFlag[slot] = 1; }
+    __syncwarp();
+    return did;
+}
+
 // drain the READY prefix at the frontier if nobody else is doing it
 __device__ void try_retire(WarpCtx& c, const unsigned int* cl, int nCells, int nChunks, const ChunkRecs& R, int* lab, LsdbRect* rc, int maxSeg) {
     GrowShared& sh = *c.sh;
@@ -1455,7 +1517,8 @@ __device__ void try_retire(WarpCtx& c, const unsigned int* cl, int nCells, int n
     __threadfence_block();
     while (!aborted(c)) {
         int f = 0, ready = 0;
-        if (c.lane == 0) { f = sh.frontier; ready = f < nChunks && sh.chunkFlag[f & (RING - 1)] == 1; }
+        // take the chunk (1 -> 3) so that no idle warp starts re-validating it under our feet
+        if (c.lane == 0) { f = sh.frontier; ready = f < nChunks && atomicCAS((int*)&sh.chunkFlag[f & (RING - 1)], 1, 3) == 1; }
         f = __shfl_sync(FULL, f, 0);
         if (!__shfl_sync(FULL, ready, 0)) break;
         __threadfence();
@@ -1530,7 +1593,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
         for (int i = tid; i < LQ_CAP; i += blockDim.x) sh.lqReady[i] = 0;
         for (int i = tid; i < GRID * GRID; i += blockDim.x) sh.grid[i] = 0;
         if (tid == 0) { sh.lqHead = 0; sh.lqTail = 0; }
-        for (int i = tid; i < RING; i += blockDim.x) sh.chunkFlag[i] = 0;
+        for (int i = tid; i < RING; i += blockDim.x) { sh.chunkFlag[i] = 0; sh.chunkHeavy[i] = 0; sh.chunkSeen[i] = -1; }
         __syncthreads();
         const int img = sh.img;
         if (img >= nImgs) break;
@@ -1578,6 +1641,7 @@ __global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, co
             chunk = __shfl_sync(FULL, chunk, 0);
             if (chunk < 0) {   // nothing to claim: help with queued large seeds, else wait for the frontier to move
                 if (help_large(c, R)) { idle = 0; continue; }
+                if (revalidate_ahead(c, cl, nCells, nChunks, R)) { idle = 0; continue; }
                 long long tw = clock64();
                 __nanosleep(200);
                 if (lane == 0) {

@@ -9,7 +9,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     lsdb = load_package(); ctx = lsdb.Context(0)
     size = int(os.environ.get("SWEEP_SIZE", "4096"))
     m = synth.occupancy_grid(size, size, seed=1000)
-    b = lsdb.Batch(ctx, [(size, size)]); b.upload([m])
+    b = lsdb.Batch(ctx, [(size, size)], max_lines=65536); b.upload([m])
     for _ in range(2):
         b.run(); b.sync()
     st = b.stats(); ms = b.stage_ms()
