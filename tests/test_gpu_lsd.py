@@ -250,3 +250,20 @@ def test_two_devices_in_one_process(lsdb, gold):
         b.close(); c.close()
     for n, got in zip(names, outs):
         assert np.array_equal(got, gold[n + "/lines"], equal_nan=True), n
+
+
+@pytest.mark.parametrize("params", [dict(angThre=30.0), dict(denThre=0.55), dict(pseBin=512), dict(angThre=15.0, denThre=0.8, pseBin=256)])
+def test_non_default_parameters_vs_oracle(lsdb, ctx, gold, params):
+    """arguments 6-8 of myLineSegmentDetector (angThre, denThre, pseBin) other than the constants of LSD/baseFunc.h:64-68"""
+    maps = [gold["mapValue_aisle1/map"], synth.occupancy_grid(700, 500, seed=41)]
+    b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for m in maps], **params)
+    b.upload(maps); b.run()
+    got = b.download(want_rects=True)
+    for i, m in enumerate(maps):
+        o = oraclebind.lsd(m, **params)
+        pl = b.planes(i)
+        assert got["counts"][i] == o["n"]
+        assert np.array_equal(pl["used"], o["used"]) and np.array_equal(pl["labels"], o["labels"])
+        assert np.array_equal(got["rects"][i], o["rects"], equal_nan=True)
+        assert np.array_equal(lsdb.lines_to_array(got["lines"][i]), o["lines"], equal_nan=True)
+    b.close()
