@@ -868,7 +868,7 @@ __device__ bool park_pend(WarpCtx& c, unsigned int* body, int& aw, int cap, int&
     return true;
 }
 
-__device__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wantChk, BBox& bb, int& used, int& chk, int& pndOff, int& pndN) {
+__device__ __noinline__ int eval_seed(WarpCtx& c, int p0, unsigned int* out, int cap, bool wantChk, BBox& bb, int& used, int& chk, int& pndOff, int& pndN) {
     c.npnd = 0; pndOff = 0; pndN = 0;
     const LsdbLsdConst* kc = c.kc;
     const int W = c.W;
