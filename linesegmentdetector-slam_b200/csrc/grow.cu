@@ -8,26 +8,33 @@
 //
 // Exactness.  The reference's result depends on the order seeds are visited (usedMap evolves) and
 // on the order pixels join a region (regDeg is re-estimated after every accepted pixel).  Both are
-// kept: a warp replays one region in the reference's exact candidate order (lanes only evaluate
-// the 32 next neighbour candidates in parallel; accepts are applied one at a time), and regions
-// are RETIRED strictly in seed order:
-//   * the sorted seed list is cut into chunks of 32 cells; warps claim chunks by ticket and may run
-//     up to RING chunks ahead of the commit frontier;
-//   * a warp evaluates the live seeds of its chunk speculatively against the current state and
-//     parks, per seed, the outcome, the accepted-pixel lists and (for NFA-accepted / rejected
-//     regions) the rectangle in its arena, then flags the chunk READY;
+// kept: every region is replayed in the reference's exact candidate order, and regions are RETIRED
+// strictly in seed order:
+//   * the sorted seed list is cut into chunks of 32 cells; a warp claims a super-chunk of
+//     LSDB_SUPER chunks by ticket and may run a bounded window ahead of the commit frontier;
+//   * scouting: one seed per LANE (small_grow) decides the ~97 % of live seeds whose region stays
+//     below regThre pixels — the reference drops those without touching any state — and flags the
+//     rest as large;
+//   * large seeds: one WARP per seed (grow_region -> rect_from_region -> Refiner / RRR ->
+//     rectangle_improver).  Lanes test the next 32 neighbour candidates in parallel; candidates whose
+//     angle test is decided whatever the candidates before them do are accepted in bulk (sums still
+//     added in scan order), the rest one at a time;
+//   * every evaluation is parked in the record arena of its super-chunk: the outcome, the pixels it
+//     accepted, the pixels it skipped because an EARLIER seed's parked accept covers them, and (for
+//     NFA-accepted / rejected regions) the rectangle.  A parked accept / reject marks its pixels in
+//     the state words so that later seeds speculate as if it had already been committed;
 //   * whichever warp finds the frontier chunk READY takes the retire lock and drains the ready
-//     prefix in order.  A parked evaluation stands iff every pixel it accepted is still un-banned
-//     (bans only grow, and a candidate rejected by angle stays out whether or not it is banned
-//     later, so the evaluation then replays identically); a cheap bounding-box + coarse-grid filter
-//     against the log of regions accepted since the evaluation started short-cuts the pixel check.
-//     Otherwise the seed is simply re-evaluated at the frontier, where the state is final;
+//     prefix in order.  A parked evaluation stands iff (V1) every pixel it accepted is still
+//     un-banned — bans only grow, and a candidate rejected by angle stays out whether or not it is
+//     banned later, so the evaluation then replays identically — and (V2) every pixel it took for
+//     banned because of a parked accept is banned by now.  V1 is pre-filtered by a coarse "last
+//     accept" grid.  Otherwise the seed is re-evaluated at the frontier, where the state is final;
 //   * commits (usedMap 1 / 2, labels, rectangle record) happen only at the frontier.
-// So usedMap, labels and the segment list are exactly the sequential result.
+// So usedMap, labels and the segment list are exactly the sequential result, whatever the timing.
 //
 // One CTA (4-16 warps, chosen from the batch size) per map, CTAs pull maps from a counter.  All
 // floating-point sums the reference accumulates sequentially are accumulated sequentially here too
-// (lane-parallel loads, serial adds); counts and min/max are order-free and reduced in parallel.
+// (lane-parallel operands, serial adds); counts and min/max are order-free and reduced in parallel.
 // The stage is latency-bound (dependent gathers, serial accept chains), not bandwidth-bound.
 #include "lsdb_common.cuh"
 #include "../../include/lsdb200.h"
