@@ -44,6 +44,7 @@ struct StencilSmem {
     unsigned char stT[1024];
     unsigned char neRows[LSDB_SRC_MAX];                      // source rows of the window that hold a non-zero pixel
     int qn, qt;
+    int geo[6];
     int nNe;
     int anySrc;
 };
@@ -106,18 +107,24 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
     const double sca = kc->sca;
     const int h = kc->h;  // 8
 
-    // centres of the first / last Gaussian column and row: xc = floor(x/sca + 0.5)  (:428,:460)
-    const int xcA = lsdb_x86_d2i(floor(gxs / sca + 0.5)), xcB = lsdb_x86_d2i(floor((x1 - 1) / sca + 0.5));
-    const int ycA = lsdb_x86_d2i(floor(gys / sca + 0.5)), ycB = lsdb_x86_d2i(floor((y1 - 1) / sca + 0.5));
-    int sx0, sx1, sy0, sy1;
-    lsdb_window(xcA, xcB, h, im.cols, &sx0, &sx1);
-    lsdb_window(ycA, ycB, h, im.rows, &sy0, &sy1);
+    // centres of the first / last Gaussian column and row: xc = floor(x/sca + 0.5)  (:428,:460) and the source window —
+    // the same for every thread: one thread does the double-precision divisions, the rest read the result
+    if (tid == 0) {
+        const int xcA_ = lsdb_x86_d2i(floor(gxs / sca + 0.5)), xcB_ = lsdb_x86_d2i(floor((x1 - 1) / sca + 0.5));
+        const int ycA_ = lsdb_x86_d2i(floor(gys / sca + 0.5)), ycB_ = lsdb_x86_d2i(floor((y1 - 1) / sca + 0.5));
+        int a0, a1, b0, b1;
+        lsdb_window(xcA_, xcB_, h, im.cols, &a0, &a1);
+        lsdb_window(ycA_, ycB_, h, im.rows, &b0, &b1);
+        S.geo[0] = a0; S.geo[1] = a1; S.geo[2] = b0; S.geo[3] = b1;
+        S.geo[4] = (xcA_ - h >= 0 && xcB_ + h < im.cols) ? 1 : 0;   // taps are consecutive source pixels (no reflection at an
+        S.geo[5] = (ycA_ - h >= 0 && ycB_ + h < im.rows) ? 1 : 0;   // image border) in x / in y
+    }
+    __syncthreads();
+    const int sx0 = S.geo[0], sx1 = S.geo[1], sy0 = S.geo[2], sy1 = S.geo[3];
+    const bool contigX = S.geo[4] != 0, contigY = S.geo[5] != 0;
     const int ax0 = sx0 & ~15;                         // 16-byte aligned window start
     const int nVec = (sx1 + 1 - ax0 + 15) >> 4;        // uint4 per row
     const int nRows = sy1 - sy0 + 1;
-    // taps are consecutive source pixels (no reflection at an image border) in x / in y
-    const bool contigX = xcA - h >= 0 && xcB + h < im.cols;
-    const bool contigY = ycA - h >= 0 && ycB + h < im.rows;
 
     if (tid < 51) S.taps[tid] = kc->taps[tid];
     if (tid == 0) { S.qn = 0; S.qt = 0; S.nNe = 0; S.anySrc = 0; }
@@ -171,65 +178,75 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
             if (rb[0] | rb[1] | rb[2] | rb[3] | rb[4]) S.neRows[atomicAdd(&S.nNe, 1)] = (unsigned char)r;
         }
         __syncthreads();
-        const int nEl = S.nNe * gw;
-        for (int o = tid; o < nEl; o += NT) {
-            const int k = o / gw, c = o - k * gw;
-            const int r = S.neRows[k];
-            const unsigned int* rb = &S.rowBits[r * ROW_WORDS];
-            const short* ix = &S.idxX[c * 17];
-            unsigned int m;
-            if (contigX) m = bits17(rb, ix[0]);
-            else {
-                m = 0;
+        // element (row k of the non-empty list, column c): a warp takes a row for columns 0..31, the 33rd column of all
+        // rows is swept afterwards, one row per thread — no integer division by the (variable) tile width
+        const int nNe = S.nNe;
+        for (int pass = 0; pass < 2; pass++) {
+            const int kBeg = pass == 0 ? warp : tid, kStep = pass == 0 ? NT / 32 : NT;
+            const int c = pass == 0 ? lane : 32;
+            if (c >= gw) continue;
+            for (int k = kBeg; k < nNe; k += kStep) {
+                const int r = S.neRows[k];
+                const unsigned int* rb = &S.rowBits[r * ROW_WORDS];
+                const short* ix = &S.idxX[c * 17];
+                unsigned int m;
+                if (contigX) m = bits17(rb, ix[0]);
+                else {
+                    m = 0;
 #pragma unroll
-                for (int i = 0; i < 17; i++) { const int p = ix[i]; m |= ((rb[p >> 5] >> (p & 31)) & 1u) << i; }
-            }
-            if (m) {
-                // the few non-zero taps are re-read from global memory (L1/L2 hits: the window was just staged) and remapped
-                // on the fly; only the bit vectors live in shared memory, which buys a fourth resident CTA per SM
-                const int gy = sy0 + r;
-                const uint8_t* row = src + im.srcOff + (size_t)gy * im.srcPitch + ax0;
-                const double* ker = &S.taps[((gxs + c) % 3) * 17];
-                double v = 0.0;
-                while (m) {
-                    const int i = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int px = ix[i];
-                    unsigned int b = row[px];
-                    if (gy >= 1 && ax0 + px >= 1) b = b == 1u ? 255u : b;   // :135-142 (255 -> 0 never has its bit set)
-                    v += (double)b * ker[i];
+                    for (int i = 0; i < 17; i++) { const int p = ix[i]; m |= ((rb[p >> 5] >> (p & 31)) & 1u) << i; }
                 }
-                S.u.aux[r * GW + c] = v;
-                atomicOr(&S.colBits[c * ROW_WORDS + (r >> 5)], 1u << (r & 31));
+                if (m) {
+                    // the few non-zero taps are re-read from global memory (L1/L2 hits: the window was just staged) and remapped
+                    // on the fly; only the bit vectors live in shared memory, which buys a fourth resident CTA per SM
+                    const int gy = sy0 + r;
+                    const uint8_t* row = src + im.srcOff + (size_t)gy * im.srcPitch + ax0;
+                    const double* ker = &S.taps[((gxs + c) % 3) * 17];
+                    double v = 0.0;
+                    while (m) {
+                        const int i = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int px = ix[i];
+                        unsigned int b = row[px];
+                        if (gy >= 1 && ax0 + px >= 1) b = b == 1u ? 255u : b;   // :135-142 (255 -> 0 never has its bit set)
+                        v += (double)b * ker[i];
+                    }
+                    S.u.aux[r * GW + c] = v;
+                    atomicOr(&S.colBits[c * ROW_WORDS + (r >> 5)], 1u << (r & 31));
+                }
             }
         }
         __syncthreads();
 
         // ---- Y pass: g[r][c] = sum_i aux[idxY[r][i]][c] * ker_phase(r)[i]   (:452-482), non-zero taps only
-        for (int o = tid; o < gh * gw; o += NT) {
-            int r = o / gw, c = o - r * gw;
-            const short* iy = &S.idxY[r * 17];
-            const unsigned int* cb = &S.colBits[c * ROW_WORDS];
-            unsigned int m;
-            if (contigY) m = bits17(cb, iy[0]);
-            else {
-                m = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            const int rBeg = pass == 0 ? warp : tid, rStep = pass == 0 ? NT / 32 : NT;
+            const int c = pass == 0 ? lane : 32;
+            if (c >= gw) continue;
+            for (int r = rBeg; r < gh; r += rStep) {
+                const short* iy = &S.idxY[r * 17];
+                const unsigned int* cb = &S.colBits[c * ROW_WORDS];
+                unsigned int m;
+                if (contigY) m = bits17(cb, iy[0]);
+                else {
+                    m = 0;
 #pragma unroll
-                for (int i = 0; i < 17; i++) { const int p = iy[i]; m |= ((cb[p >> 5] >> (p & 31)) & 1u) << i; }
-            }
-            double v = 0.0;
-            if (m) {
-                const double* ker = &S.taps[((gys + r) % 3) * 17];
-                while (m) {
-                    const int i = __ffs(m) - 1;
-                    m &= m - 1;
-                    v += S.u.aux[iy[i] * GW + c] * ker[i];
+                    for (int i = 0; i < 17; i++) { const int p = iy[i]; m |= ((cb[p >> 5] >> (p & 31)) & 1u) << i; }
                 }
-            }
-            S.g[r * GW + c] = v;
-            if (gaussOut) {
-                int gx = gxs + c, gy = gys + r;
-                if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = v;
+                double v = 0.0;
+                if (m) {
+                    const double* ker = &S.taps[((gys + r) % 3) * 17];
+                    while (m) {
+                        const int i = __ffs(m) - 1;
+                        m &= m - 1;
+                        v += S.u.aux[iy[i] * GW + c] * ker[i];
+                    }
+                }
+                S.g[r * GW + c] = v;
+                if (gaussOut) {
+                    int gx = gxs + c, gy = gys + r;
+                    if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = v;
+                }
             }
         }
     } else {
