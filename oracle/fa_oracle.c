@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE — plain-C restatement of the scoring part of myfa::FeatureAssociation
  * (/root/reference/LSD/myFA.cpp:27-59 pair filter, :186-272 four pairings, :274-305
  * NormalizedLineDirection, :307-355 rotateScanIm, :357-396 CalcScore), serial and in the
- * reference's summation order.  Pinned against oracle/_ref by tests/test_oracle_vs_ref.py. */
+ * reference's summation order.  Pinned against oracle/_ref by tests/test_oracle.py. */
 #include "lsd_oracle.h"
 #include "lsd_math.h"
 #include <stdlib.h>

@@ -2,7 +2,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * use anything under oracle/.  The product (liblsdb200.so) never links or calls this.
  * Parity status: PINNED — checked bit-for-bit against the unmodified reference compiled into
- * oracle/_ref (tests/test_oracle_vs_ref.py) and against tests/golden fixtures generated from it. */
+ * oracle/_ref (tests/test_oracle.py) and against tests/golden fixtures generated from it. */
 #ifndef LSD_ORACLE_H
 #define LSD_ORACLE_H
 #include <stdint.h>
