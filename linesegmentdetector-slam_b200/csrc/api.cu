@@ -226,7 +226,9 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         // a small map has a short seed list (~ n/300 chunks): a big team then speculates over all of it at once, against
         // the initial state, and most large regions end up re-evaluated at the frontier (measured on the bundled maps:
         // 1377x428 -> 6.4 ms with 16 warps, 5.3 ms with 8)
-        const int sizeCap = maxN < 30000 ? 4 : (maxN < 600000 ? 8 : LSDB_GROW_WARPS);
+        // Teams of 8: with at most one team per SM that build may use 255 registers (no spills), and 8 such warps beat 16
+        // of the 128-register build on every size measured (4096^2: 105 vs 120 ms, 16384^2: 1.77 vs 1.98 s).
+        const int sizeCap = maxN < 30000 ? 4 : 8;
         if (nw > sizeCap) nw = sizeCap;
         if (nw < 4) nw = 4;
         if (getenv("LSDB_GROW_WARPS")) { int v = atoi(getenv("LSDB_GROW_WARPS")); if (v >= 1 && v <= LSDB_GROW_WARPS) nw = v; }

@@ -38,6 +38,7 @@
 // The stage is latency-bound (dependent gathers, serial accept chains), not bandwidth-bound.
 #include "lsdb_common.cuh"
 #include "../../include/lsdb200.h"
+#include <stdlib.h>
 
 #define NW_MAX LSDB_GROW_WARPS
 #define ARENA_HDR 32  // words: 13 doubles (rect + logNFA), nCommit, outcome
@@ -1548,7 +1549,8 @@ __device__ void try_retire(WarpCtx& c, const unsigned int* cl, int nCells, int n
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(NW_MAX * 32, 1) lsdb_grow_kernel(int nImgs, const LsdbImg* __restrict__ imgs, LsdbImgDyn* __restrict__ dyn,
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) lsdb_grow_kernel(int nImgs, const LsdbImg* __restrict__ imgs, LsdbImgDyn* __restrict__ dyn,
                                                                    const LsdbLsdConst* __restrict__ kc, const double* __restrict__ mag,
                                                                    const double* __restrict__ deg, const double* __restrict__ cosm,
                                                                    const double* __restrict__ sinm, unsigned int* __restrict__ state,
@@ -1682,6 +1684,13 @@ __global__ void lsdb_used_plane_kernel(const unsigned int* __restrict__ state, u
     }
 }
 
+// teams of up to 8 warps with at most one team per SM: nothing is gained by leaving registers unused, so that build
+// may take up to 255 of them (the common one is capped at 128 so that 16-warp teams and several teams per SM fit)
+static bool lsdb_grow_wide_regs(int nCtas, int warpsPerCta) {
+    if (getenv("LSDB_GROW_WIDE")) return atoi(getenv("LSDB_GROW_WIDE")) != 0 && warpsPerCta <= 8;
+    return warpsPerCta <= 8 && nCtas <= 148;
+}
+
 void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, const LsdbImg* imgs, LsdbImgDyn* dyn,
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
@@ -1690,11 +1699,18 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
     if (runAhead <= 0 || runAhead > RING - (NW_MAX + 1) * LSDB_SUPER) runAhead = RING - (NW_MAX + 1) * LSDB_SUPER;
     if (runAhead < 1) runAhead = 1;
     // per device and cheap: set on every launch (a process may drive several GPUs through several contexts)
-    cudaFuncSetAttribute(lsdb_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
-    if (nImgs > 0)
-        lsdb_grow_kernel<<<nCtas, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta), s>>>(nImgs, imgs, dyn, kc, mag, deg, cosm, sinm, state, cells, labels, rects,
-                                                                                maxSeg, lists, listCap, arenaCap, runAhead, recBuf, lgammaTab, lgammaN,
-                                                                                imgCounter, banBits, bmCapWords, steal);
+    const bool wide = lsdb_grow_wide_regs(nCtas, warpsPerCta);
+    if (wide) cudaFuncSetAttribute(lsdb_grow_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
+    else cudaFuncSetAttribute(lsdb_grow_kernel<NW_MAX * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
+    if (nImgs <= 0) return;
+    if (wide)
+        lsdb_grow_kernel<256><<<nCtas, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta), s>>>(
+            nImgs, imgs, dyn, kc, mag, deg, cosm, sinm, state, cells, labels, rects, maxSeg, lists, listCap, arenaCap, runAhead, recBuf,
+            lgammaTab, lgammaN, imgCounter, banBits, bmCapWords, steal);
+    else
+        lsdb_grow_kernel<NW_MAX * 32><<<nCtas, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta), s>>>(
+            nImgs, imgs, dyn, kc, mag, deg, cosm, sinm, state, cells, labels, rects, maxSeg, lists, listCap, arenaCap, runAhead, recBuf,
+            lgammaTab, lgammaN, imgCounter, banBits, bmCapWords, steal);
 }
 
 size_t lsdb_grow_words_per_cta(int listCap, int arenaCap, int warpsPerCta) { return grow_words_per_cta(listCap, arenaCap, warpsPerCta); }
@@ -1713,8 +1729,8 @@ void lsdb_launch_used_plane(cudaStream_t s, const unsigned int* state, uint8_t* 
 int lsdb_grow_max_ctas(int device, int warpsPerCta, int bmCapWords) {
     int sms = 0, per = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaFuncSetAttribute(lsdb_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lsdb_grow_kernel, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta));
+    cudaFuncSetAttribute(lsdb_grow_kernel<NW_MAX * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_dyn_smem(bmCapWords, NW_MAX));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lsdb_grow_kernel<NW_MAX * 32>, warpsPerCta * 32, grow_dyn_smem(bmCapWords, warpsPerCta));
     if (per < 1) per = 1;
     return sms * per;
 }
@@ -1724,7 +1740,7 @@ int lsdb_grow_max_bitmap_words(int device) {
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, lsdb_grow_kernel) != cudaSuccess) return 0;
+    if (cudaFuncGetAttributes(&fa, lsdb_grow_kernel<NW_MAX * 32>) != cudaSuccess) return 0;
     const long long room = (long long)optin - (long long)fa.sharedSizeBytes - 256 - NW_MAX * 1024;
     return room > 0 ? (int)(room / 4) : 0;
 }
