@@ -280,6 +280,59 @@ def main():
     except Exception as e:
         fa = {"error": repr(e)}
 
+    # ---------------- scan front-end: 10k lidar frames -> myrdp::FeatureScan on the device, then the
+    # device association reduction on its output (lidar beams in, one pose estimate per frame out)
+    fs = None
+    try:
+        import oraclebind
+        import refbind
+        gl = np.load(os.path.join(ROOT, "tests", "golden", "lidar_frames.npz"))
+        mp = gl["map_param"]
+        rng_j = np.random.default_rng(2024)
+        base_fr = []
+        for f in range(int(gl["n_frames"])):
+            r_, a_ = gl[f"f{f}/ranges"], gl[f"f{f}/angles"]
+            k_ = np.isfinite(r_)
+            base_fr.append((r_[k_], a_[k_]))
+        frames_l = []
+        for i in range(10000):                                                           # seeded jitter of the bundled sweeps (configs[3])
+            r_, a_ = base_fr[i % len(base_fr)]
+            frames_l.append((r_ * (1.0 + rng_j.normal(0, 0.002, len(r_))), a_))
+        ctx.feature_scan(mp[2], mp[3], mp[4], frames_l[:64])                               # warm-up
+        info_, lines_, loff_, pts_, poff_ = ctx.feature_scan(mp[2], mp[3], mp[4], frames_l, raw=True)
+        t0 = time.time()
+        info_, lines_, loff_, pts_, poff_ = ctx.feature_scan(mp[2], mp[3], mp[4], frames_l, raw=True, capacity=(len(lines_), len(pts_)))
+        dt_fs = time.time() - t0
+        k_ms = ctx.feature_scan_last_ms()
+        t0 = time.time()
+        if fa and "error" not in fa:
+            gf2 = np.load(os.path.join(ROOT, "tests", "golden", "fa_frames.npz"))
+            gm2 = np.load(os.path.join(ROOT, "tests", "golden", "bundled_maps.npz"))
+            fm2 = lsdb.FaMap(ctx, ctx.map_cache(gm2["mapValue/map"], float(gm2["mapValue/param"][2])), gf2["map_lines"])
+            lid_ = np.rint(np.stack([info_["lidar_x"], info_["lidar_y"]], 1)); last_ = np.tile(np.array([-1.0, -1.0, 0.0]), (len(frames_l), 1))
+            est_ = np.zeros(len(frames_l), lsdb.EST_DTYPE)
+            t0 = time.time()
+            ctx.check(lsdb.lib().lsdb_fa_estimate_frames(ctx.h, fm2.h, len(frames_l), lines_.ctypes.data, loff_.ctypes.data, pts_.ctypes.data,
+                                                         poff_.ctypes.data, lid_.ctypes.data, last_.ctypes.data, est_.ctypes.data), "estimate")
+            dt_est = time.time() - t0
+            fm2.close()
+        else:
+            est_, dt_est = None, None
+        sample = frames_l[:2000]
+        t0 = time.time()
+        cpu_nl, _ = refbind.ref_feature_scan_many(list(mp), sample) if refbind.available("glibc") else oraclebind.feature_scan_many(list(mp), sample)
+        dt_cpu = time.time() - t0
+        assert cpu_nl == int(loff_[len(sample)]) or not refbind.available("lsdm")   # same line count as the device on the sample
+        fs = {"workload": f"{len(frames_l)} lidar sweeps (87 bundled Lidar.txt frames, seeded 0.2 % range jitter), one call",
+              "beams": int(sum(len(r_) for r_, _ in frames_l)), "lines": int(loff_[-1]), "raster_samples": int(poff_[-1]),
+              "kernel_ms_both_passes": k_ms, "frames_per_s_kernel": len(frames_l) / (k_ms * 1e-3),
+              "frames_per_s_e2e": len(frames_l) / dt_fs,
+              "estimate_e2e_s": dt_est, "frames_with_match": None if est_ is None else int((est_["n_kept"] > 0).sum()),
+              "cpu_frames_per_s": len(sample) / dt_cpu, "cpu_kind": "reference myrdp::FeatureScan, 1 thread" if refbind.available("glibc") else "port",
+              "cpu_sample": "first 2000 frames"}
+    except Exception as e:
+        fs = {"error": repr(e)}
+
     # ---------------- end to end through the C ABI with host buffers
     # Every step copies its 256 maps from pinned host memory, runs the pipeline and reads the segment tables back.
     # Two batches on two private streams alternate (one host thread each; ctypes drops the GIL), so the H2D copy of
@@ -336,6 +389,7 @@ def main():
             "ms_per_map_amortised": ms_step / n,
             "single_map_latency": lat,
             "association": fa,
+            "scan_front_end": fs,
             "stage_ms": last,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * size * size, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "how": "lsdb_batch_upload (pinned host -> HBM) + lsdb_batch_run + lsdb_batch_download per step; "

@@ -164,6 +164,37 @@ int lsdb_fa_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, int n_frames, c
 /* device time of the last lsdb_fa_score kernel (ms) */
 float lsdb_fa_last_ms(const lsdb_ctx* ctx);
 
+/* ---- scan front-end: lidar frames -> scan lines + raster samples (the inputs of the association) ---- */
+/* myrdp::FeatureScan (LSD/myRDP.h:63, LSD/myRDP.cpp:9-185: RegionSegmentation, Ramer-Douglas-Peucker split, line records,
+ * rasterisation) for n_frames frames in one call; scanPose = (0,0,0) as in the reference.  Defaults of the three
+ * parameters: rdp_leastPoint = 3, rdp_threLine = 0.08, rdp_leastDist = 0.5 (LSD/baseFunc.h:70-72). */
+typedef struct {
+    int least_point;      /* RegionPointLimitNumber: minimum index span of a cluster */
+    double thre_line;     /* split threshold (m; scaled by the range beyond 9 m); must be > 0 */
+    double least_dist_m;  /* shortest line piece kept (m) */
+} lsdb_rdp_params;
+typedef struct {
+    int n_lines, n_pts;        /* FS.len_linesInfo, FS.scanImPoint.size() */
+    int im_cols, im_rows;      /* size of FS.lineIm */
+    double lidar_x, lidar_y;   /* FS.lidarPos */
+} lsdb_scan_info;
+/* Inputs: ranges / angles concatenated per frame (finite values only — the callers drop Inf beams,
+ * LSD/main_on_windows.cpp:110-123), beam_off[n_frames+1]; every frame needs at least one beam.
+ * Outputs (host buffers):
+ *   info[n_frames]; line_off / pt_off [n_frames+1] (prefix sums of n_lines / n_pts); im_off[n_frames+1] (bytes)
+ *   lines  : records in the reference's order, frame f at lines[line_off[f]]  (lsdb_line; `orient` as FeatureScan sets it)
+ *   pts    : (x,y) pairs = FS.scanImPoint, frame f at pts[2*pt_off[f]] — exactly what lsdb_fa_score takes
+ *   line_im: optional (NULL = skip): the 0/255 rasters FS.lineIm, frame f = im_rows*im_cols bytes at line_im[im_off[f]]
+ * lines == NULL and pts == NULL is a sizing query: only info and the three offset arrays are produced.
+ * LSDB_ERR_CAPACITY (max_lines, max_pts or line_im_cap too small) still leaves info and the offsets filled. */
+int lsdb_feature_scan_frames(lsdb_ctx* ctx, double map_resol, double map_ori_x, double map_ori_y,
+                             const lsdb_rdp_params* prm, int n_frames, const double* ranges, const double* angles,
+                             const int* beam_off, lsdb_scan_info* info, lsdb_line* lines, int max_lines, int* line_off,
+                             double* pts, int max_pts, int* pt_off, uint8_t* line_im, long long line_im_cap,
+                             long long* im_off);
+/* device time of the two kernels of the last lsdb_feature_scan_frames call (ms) */
+float lsdb_feature_scan_last_ms(const lsdb_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,8 @@ LINE_DTYPE = np.dtype([("k", "f8"), ("b", "f8"), ("dx", "f8"), ("dy", "f8"), ("x
 RECT_FIELDS = ["x1", "y1", "x2", "y2", "wid", "cX", "cY", "deg", "dx", "dy", "p", "prec", "logNFA"]
 EST_DTYPE = np.dtype([("n_hyp", "i4"), ("n_kept", "i4"), ("best_x", "f8"), ("best_y", "f8"), ("best_ang", "f8"), ("best_score", "f8"),
                       ("mean_x", "f8"), ("mean_y", "f8"), ("mean_ang", "f8"), ("mean_score", "f8")])
+SCAN_INFO_DTYPE = np.dtype([("n_lines", "i4"), ("n_pts", "i4"), ("im_cols", "i4"), ("im_rows", "i4"), ("lidar_x", "f8"), ("lidar_y", "f8")])
+RDP_DEFAULTS = dict(least_point=3, thre_line=0.08, least_dist_m=0.5)  # LSD/baseFunc.h:70-72
 HYP_DTYPE = np.dtype([("frame", "i4"), ("i_scan", "i4"), ("i_map", "i4"), ("i_pair", "i4"), ("x", "f8"), ("y", "f8"),
                       ("ang", "f8"), ("score", "f8")])
 
@@ -36,6 +38,10 @@ class LsdbError(RuntimeError):
 class _Params(C.Structure):
     _fields_ = [("sca", C.c_double), ("sig", C.c_double), ("angThre", C.c_double), ("denThre", C.c_double),
                 ("pseBin", C.c_int), ("_pad", C.c_int)]
+
+
+class _RdpParams(C.Structure):
+    _fields_ = [("least_point", C.c_int), ("thre_line", C.c_double), ("least_dist_m", C.c_double)]
 
 
 class _Stats(C.Structure):
@@ -78,6 +84,9 @@ def lib():
         L.lsdb_fa_score.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
         L.lsdb_fa_estimate_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]
         L.lsdb_fa_last_ms.argtypes = [vp]; L.lsdb_fa_last_ms.restype = C.c_float
+        L.lsdb_feature_scan_frames.argtypes = [vp, cd, cd, cd, C.POINTER(_RdpParams), ci, vp, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp,
+                                               C.c_longlong, vp]
+        L.lsdb_feature_scan_last_ms.argtypes = [vp]; L.lsdb_feature_scan_last_ms.restype = C.c_float
         _lib = L
     return _lib
 
@@ -134,6 +143,46 @@ def _ctx_map_cache(self, map_u8, res, max_dist=1.0):
 
 
 Context.map_cache = _ctx_map_cache
+
+
+def _ctx_feature_scan(self, map_res, map_ori_x, map_ori_y, frames, want_rasters=False, capacity=None, raw=False, **rdp):
+    """myrdp::FeatureScan (LSD/myRDP.h:63) for a list of frames [(ranges, angles), ...] through lsdb_feature_scan_frames
+    (a sizing query, then the real call; `capacity` = (max_lines, max_pts) skips the query).  Returns one dict per frame:
+    lines (LINE_DTYPE), pts (P,2), lidar_pos (2,), size (cols, rows) and, when asked for, line_im (rows x cols u8);
+    raw=True returns the concatenated arrays (info, lines, line_off, pts, pt_off) instead."""
+    nf = len(frames)
+    boff = np.zeros(nf + 1, np.int32)
+    for i, (r, _a) in enumerate(frames):
+        boff[i + 1] = boff[i] + len(r)
+    rng = np.ascontiguousarray(np.concatenate([np.asarray(r, np.float64) for r, _ in frames])) if nf else np.zeros(0)
+    ang = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float64) for _, a in frames])) if nf else np.zeros(0)
+    d = dict(RDP_DEFAULTS); d.update(rdp)
+    prm = _RdpParams(int(d["least_point"]), float(d["thre_line"]), float(d["least_dist_m"]))
+    info = np.zeros(nf, SCAN_INFO_DTYPE)
+    loff = np.zeros(nf + 1, np.int32); poff = np.zeros(nf + 1, np.int32); ioff = np.zeros(nf + 1, np.int64)
+    args = (self.h, float(map_res), float(map_ori_x), float(map_ori_y), C.byref(prm), nf, _p(rng), _p(ang), _p(boff), _p(info))
+    if capacity is None or want_rasters:
+        self.check(lib().lsdb_feature_scan_frames(*args, None, 0, _p(loff), None, 0, _p(poff), None, 0, _p(ioff)), "lsdb_feature_scan_frames")
+        capacity = (int(loff[-1]), int(poff[-1]))
+    lines = np.empty(max(int(capacity[0]), 1), LINE_DTYPE); pts = np.empty((max(int(capacity[1]), 1), 2))
+    im = np.zeros(max(int(ioff[-1]), 1), np.uint8) if want_rasters else None
+    self.check(lib().lsdb_feature_scan_frames(*args, _p(lines), len(lines), _p(loff), _p(pts), len(pts), _p(poff), _p(im),
+                                              0 if im is None else len(im), _p(ioff)), "lsdb_feature_scan_frames")
+    if raw:
+        return info, lines[:loff[-1]], loff, pts[:poff[-1]], poff
+    out = []
+    for f in range(nf):
+        w, h = int(info[f]["im_cols"]), int(info[f]["im_rows"])
+        rec = dict(lines=lines[loff[f]:loff[f + 1]].copy(), pts=pts[poff[f]:poff[f + 1]].copy(),
+                   lidar_pos=np.array([info[f]["lidar_x"], info[f]["lidar_y"]]), size=(w, h))
+        if want_rasters:
+            rec["line_im"] = im[ioff[f]:ioff[f + 1]].reshape(max(h, 0), max(w, 0)).copy() if w > 0 and h > 0 else np.zeros((max(h, 0), max(w, 0)), np.uint8)
+        out.append(rec)
+    return out
+
+
+Context.feature_scan = _ctx_feature_scan
+Context.feature_scan_last_ms = lambda self: float(lib().lsdb_feature_scan_last_ms(self.h))
 
 
 class Batch:

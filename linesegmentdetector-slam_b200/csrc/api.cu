@@ -28,6 +28,10 @@ struct lsdb_ctx {
     // FA staging buffers (grown on demand)
     void* faDev; size_t faDevCap;
     void* faHost; size_t faHostCap;
+    // scan front-end: ragged outputs (device + pinned mirror) and the raster plane
+    void* fsOut; void* fsOutHost; size_t fsOutCap;
+    void* fsIm; size_t fsImCap;
+    float fsMs;
 };
 
 struct lsdb_batch {
@@ -80,6 +84,7 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
     if (prop.major != 10) return LSDB_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
     lsdb_ctx* c = new lsdb_ctx();
     c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0;
+    c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsIm = 0; c->fsImCap = 0; c->fsMs = 0;
     c->lgammaTab = 0; c->lgammaN = 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LSDB_ERR_NO_DEVICE; }
     if (stream) { c->stream = (cudaStream_t)stream; c->ownStream = false; }
@@ -104,6 +109,9 @@ extern "C" void lsdb_destroy(lsdb_ctx* c) {
     cudaFree(c->lgammaTab);
     if (c->faDev) cudaFree(c->faDev);
     if (c->faHost) cudaFreeHost(c->faHost);
+    if (c->fsOut) cudaFree(c->fsOut);
+    if (c->fsOutHost) cudaFreeHost(c->fsOutHost);
+    if (c->fsIm) cudaFree(c->fsIm);
     cudaEventDestroy(c->faEv[0]); cudaEventDestroy(c->faEv[1]);
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
@@ -638,4 +646,111 @@ extern "C" int lsdb_fa_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, int 
     if (!out) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_estimate_frames: bad argument%s");
     int nHyp = 0;
     return fa_run(ctx, m, nFrames, scanLines, lineOff, pts, ptOff, lidarPose, lastPose, 0, 0, &nHyp, out);
+}
+
+// ---- scan front-end ----
+extern "C" float lsdb_feature_scan_last_ms(const lsdb_ctx* ctx) { return ctx ? ctx->fsMs : 0.f; }
+
+extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX, double oriY, const lsdb_rdp_params* prm, int nFrames,
+                                        const double* ranges, const double* angles, const int* beamOff, lsdb_scan_info* info,
+                                        lsdb_line* lines, int maxLines, int* lineOff, double* pts, int maxPts, int* ptOff,
+                                        uint8_t* lineIm, long long lineImCap, long long* imOff) {
+    static_assert(sizeof(lsdb_scan_info) == sizeof(LsdbFsInfo), "layout");
+    if (!ctx) return LSDB_ERR_ARG;
+    if (!prm || nFrames < 0 || !beamOff || !info || !lineOff || !ptOff || (lineIm && !imOff) || (!lines) != (!pts) ||
+        (nFrames > 0 && (!ranges || !angles)) || !(resol > 0) || !(prm->thre_line > 0))
+        return fail(ctx, LSDB_ERR_ARG, "lsdb_feature_scan_frames: bad argument%s");
+    lineOff[0] = 0; ptOff[0] = 0;
+    if (imOff) imOff[0] = 0;
+    if (nFrames == 0) return LSDB_OK;
+    int maxBeams = 0;
+    for (int f = 0; f < nFrames; f++) {
+        const int n = beamOff[f + 1] - beamOff[f];
+        if (beamOff[0] != 0 || n < 1) return fail(ctx, LSDB_ERR_ARG, "lsdb_feature_scan_frames: frame %s%lld has no beams", "", f);
+        maxBeams = std::max(maxBeams, n);
+    }
+    const int nB = beamOff[nFrames];
+    for (int i = 0; i < nB; i++)
+        if (!std::isfinite(ranges[i]) || !std::isfinite(angles[i]))
+            return fail(ctx, LSDB_ERR_ARG, "lsdb_feature_scan_frames: beam %s%lld is not finite (drop Inf ranges first)", "", i);
+    const size_t smem = lsdb_fscan_smem(maxBeams);
+    if (smem > 200 * 1024) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: %s%lld beams in one frame exceed the shared-memory layout", "", maxBeams);
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t oR = 0, oA = oR + al256(8 * (size_t)nB), oB = oA + al256(8 * (size_t)nB), oInfo = oB + al256(4 * (size_t)(nFrames + 1)),
+                 oLoff = oInfo + al256(sizeof(LsdbFsInfo) * (size_t)nFrames), oPoff = oLoff + al256(4 * (size_t)(nFrames + 1)),
+                 oIoff = oPoff + al256(4 * (size_t)(nFrames + 1)), total = oIoff + al256(8 * (size_t)(nFrames + 1));
+    if (total > ctx->faDevCap) {
+        if (ctx->faDev) cudaFree(ctx->faDev);
+        if (ctx->faHost) cudaFreeHost(ctx->faHost);
+        ctx->faDev = 0; ctx->faHost = 0; ctx->faDevCap = 0;
+        CK(ctx, cudaMalloc(&ctx->faDev, total + total / 4));
+        CK(ctx, cudaMallocHost(&ctx->faHost, total + total / 4));
+        ctx->faDevCap = ctx->faHostCap = total + total / 4;
+    }
+    char* H = (char*)ctx->faHost; char* D = (char*)ctx->faDev;
+    memcpy(H + oR, ranges, 8 * (size_t)nB);
+    memcpy(H + oA, angles, 8 * (size_t)nB);
+    memcpy(H + oB, beamOff, 4 * (size_t)(nFrames + 1));
+    cudaStream_t s = ctx->stream;
+    const double pi = 4.0 * lsdm_atan(1.0);
+    CK(ctx, cudaMemcpyAsync(D, H, oInfo, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaEventRecord(ctx->faEv[0], s));
+    CK(ctx, (cudaError_t)lsdb_launch_fscan(s, 0, nFrames, maxBeams, (double*)(D + oR), (double*)(D + oA), (int*)(D + oB), resol, oriX, oriY,
+                                           prm->least_point, prm->thre_line, prm->least_dist_m, pi, (LsdbFsInfo*)(D + oInfo), 0, 0, 0, 0, 0, 0));
+    CK(ctx, cudaEventRecord(ctx->faEv[1], s));
+    CK(ctx, cudaMemcpyAsync(H + oInfo, D + oInfo, sizeof(LsdbFsInfo) * (size_t)nFrames, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    float ms0 = 0;
+    CK(ctx, cudaEventElapsedTime(&ms0, ctx->faEv[0], ctx->faEv[1]));
+    ctx->fsMs = ms0;
+    memcpy(info, H + oInfo, sizeof(LsdbFsInfo) * (size_t)nFrames);
+    long long nL = 0, nP = 0, nI = 0;
+    std::vector<long long> io(nFrames + 1, 0);
+    for (int f = 0; f < nFrames; f++) {
+        if (info[f].n_lines < 0) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: frame %s%lld overflows the line-piece list", "", f);
+        nL += info[f].n_lines; nP += info[f].n_pts;
+        if (info[f].im_cols > 0 && info[f].im_rows > 0) nI += (long long)info[f].im_cols * info[f].im_rows;
+        if (nL > INT_MAX || nP > INT_MAX) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: more than 2^31 outputs at frame %s%lld", "", f);
+        lineOff[f + 1] = (int)nL; ptOff[f + 1] = (int)nP; io[f + 1] = nI;
+        if (imOff) imOff[f + 1] = nI;
+    }
+    if (!lines) return LSDB_OK;   // sizing query
+    if (nL > maxLines) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: %s%lld lines exceed max_lines", "", nL);
+    if (nP > maxPts) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: %s%lld raster samples exceed max_pts", "", nP);
+    if (lineIm && nI > lineImCap) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: rasters need %s%lld bytes", "", nI);
+    const size_t oL = 0, oP = oL + al256(sizeof(LsdbFaLine) * (size_t)nL), outTotal = oP + al256(16 * (size_t)nP);
+    if (outTotal > ctx->fsOutCap) {
+        if (ctx->fsOut) cudaFree(ctx->fsOut);
+        if (ctx->fsOutHost) cudaFreeHost(ctx->fsOutHost);
+        ctx->fsOut = 0; ctx->fsOutHost = 0; ctx->fsOutCap = 0;
+        CK(ctx, cudaMalloc(&ctx->fsOut, outTotal + outTotal / 4));
+        CK(ctx, cudaMallocHost(&ctx->fsOutHost, outTotal + outTotal / 4));
+        ctx->fsOutCap = outTotal + outTotal / 4;
+    }
+    if (lineIm && (size_t)nI > ctx->fsImCap) {
+        if (ctx->fsIm) cudaFree(ctx->fsIm);
+        ctx->fsIm = 0; ctx->fsImCap = 0;
+        CK(ctx, cudaMalloc(&ctx->fsIm, (size_t)nI + (size_t)nI / 4 + 256));
+        ctx->fsImCap = (size_t)nI + (size_t)nI / 4 + 256;
+    }
+    memcpy(H + oLoff, lineOff, 4 * (size_t)(nFrames + 1));
+    memcpy(H + oPoff, ptOff, 4 * (size_t)(nFrames + 1));
+    memcpy(H + oIoff, io.data(), 8 * (size_t)(nFrames + 1));
+    CK(ctx, cudaMemcpyAsync(D + oLoff, H + oLoff, total - oLoff, cudaMemcpyHostToDevice, s));
+    if (lineIm && nI > 0) CK(ctx, cudaMemsetAsync(ctx->fsIm, 0, (size_t)nI, s));
+    char* O = (char*)ctx->fsOut; char* OH = (char*)ctx->fsOutHost;
+    CK(ctx, cudaEventRecord(ctx->faEv[0], s));
+    CK(ctx, (cudaError_t)lsdb_launch_fscan(s, 1, nFrames, maxBeams, (double*)(D + oR), (double*)(D + oA), (int*)(D + oB), resol, oriX, oriY,
+                                           prm->least_point, prm->thre_line, prm->least_dist_m, pi, (LsdbFsInfo*)(D + oInfo), (int*)(D + oLoff),
+                                           (int*)(D + oPoff), (long long*)(D + oIoff), (LsdbFaLine*)(O + oL), (double*)(O + oP),
+                                           lineIm ? (uint8_t*)ctx->fsIm : 0));
+    CK(ctx, cudaEventRecord(ctx->faEv[1], s));
+    CK(ctx, cudaMemcpyAsync(OH, O, outTotal, cudaMemcpyDeviceToHost, s));
+    if (lineIm && nI > 0) CK(ctx, cudaMemcpyAsync(lineIm, ctx->fsIm, (size_t)nI, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    CK(ctx, cudaEventElapsedTime(&ms0, ctx->faEv[0], ctx->faEv[1]));
+    ctx->fsMs += ms0;
+    memcpy(lines, OH + oL, sizeof(LsdbFaLine) * (size_t)nL);
+    memcpy(pts, OH + oP, 16 * (size_t)nP);
+    return LSDB_OK;
 }

@@ -105,3 +105,11 @@ void lsdb_launch_fa(cudaStream_t s, int nTasks, const LsdbFaTask* tasks, const L
 size_t lsdb_fa_pose_bytes(int nTasks);
 struct LsdbFaEst { int nHyp, nKept; double bx, by, bang, bscore, mx, my, mang, mscore; };  // == lsdb_fa_estimate
 void lsdb_launch_fa_reduce(cudaStream_t s, int nFrames, const LsdbFaHyp* hyp, const int* hypOff, LsdbFaEst* est);
+
+// scan front-end (fscan.cu)
+struct LsdbFsInfo { int nLines, nPts, W, H; double lidarX, lidarY; };  // == lsdb_scan_info; nLines < 0: internal list overflow
+size_t lsdb_fscan_smem(int maxBeams);
+int lsdb_launch_fscan(cudaStream_t s, int pass, int nFrames, int maxBeams, const double* ranges, const double* angles, const int* beamOff,
+                      double resol, double oriX, double oriY, int leastPoint, double threLine, double leastDistM, double pi,
+                      LsdbFsInfo* info, const int* lineOff, const int* ptOff, const long long* imOff, LsdbFaLine* lines, double* pts,
+                      uint8_t* lineIm);

@@ -106,3 +106,38 @@ def fake_scan_frame(m, map_lines, seed, max_pts=1200):
         k = (b[1] - a[1]) / (b[0] - a[0]) if b[0] != a[0] else np.inf
         sl[j] = [k, 0, 0, 0, a[0], a[1], b[0], b[1], np.hypot(*(b - a)), 0]
     return dict(scan_lines=sl, pts=pts, lidar_pose=np.rint(off), last_pose=np.array([-1.0, -1.0, 0.0]))
+
+
+def lidar_frame(seed, n_beams=360, dropout=0.12, noise=0.004):
+    """A seeded synthetic lidar sweep (ranges, angles) in the format of the bundled Lidar.txt frames: the sensor sits in a
+    randomly rotated rectangular room with a few interior wall pieces; beams are cast against the walls, jittered, and a
+    fraction is dropped (the Inf beams the reference's readers discard, LSD/main_on_windows.cpp:110-123).  Angles follow
+    the bundled convention -3.12414 + i * (2*pi/n_beams)."""
+    rng = np.random.default_rng(seed)
+    ang = -3.12414 + np.arange(n_beams) * (2 * np.pi / n_beams)
+    phi = rng.uniform(0, np.pi)
+    hw, hh = rng.uniform(1.5, 9.0), rng.uniform(1.0, 5.0)
+    ox, oy = rng.uniform(-0.6, 0.6) * hw, rng.uniform(-0.6, 0.6) * hh
+    c = np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) - [ox, oy]
+    segs = [(c[i], c[(i + 1) % 4]) for i in range(4)]
+    for _ in range(int(rng.integers(0, 5))):
+        p = np.array([rng.uniform(-hw, hw) - ox, rng.uniform(-hh, hh) - oy])
+        d = rng.uniform(0.4, 2.5) * (np.array([1.0, 0.0]) if rng.random() < 0.5 else np.array([0.0, 1.0]))
+        segs.append((p, p + d))
+    R = np.array([[np.cos(phi), -np.sin(phi)], [np.sin(phi), np.cos(phi)]])
+    dx, dy = np.cos(ang), np.sin(ang)
+    best = np.full(n_beams, np.inf)
+    for a, b in segs:
+        a, b = R @ a, R @ b
+        ex, ey = b - a
+        den = dx * ey - dy * ex
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = (a[0] * ey - a[1] * ex) / den
+            u = (a[0] * dy - a[1] * dx) / den
+        hit = (np.abs(den) > 1e-12) & (t > 0.05) & (u >= 0) & (u <= 1)
+        best = np.where(hit & (t < best), t, best)
+    best = best + rng.normal(0, noise, n_beams)
+    best[rng.random(n_beams) < dropout] = np.inf
+    best[best > 16.4] = np.inf
+    keep = np.isfinite(best)
+    return best[keep].copy(), ang[keep].copy()

@@ -52,6 +52,18 @@ int lsdo_fa_scores(const double* scan_lines, int n_scan, const double* map_lines
                    const double* lidar_pose, const double* last_pose, int32_t* out_idx,
                    double* out_val, int max_rec);
 
+/* myrdp::FeatureScan restated (LSD/myRDP.cpp:9-375), one frame of finite beams.  map_param = cols rows resol oriX oriY.
+ * Same outputs as oracle/ref_harness.cpp:ref_feature_scan: lines [max_lines][10] (k b dx dy x1 y1 x2 y2 len orient),
+ * pts [max_pts][2], lidar_pos[2], im_size = cols, rows of the raster, line_im (0/255) when it fits line_im_cap.
+ * Returns the number of lines; *n_pts = number of raster samples. */
+int lsdo_feature_scan(const double* map_param, const double* range, const double* angle, int n,
+                      int leastPoint, double threLine, double leastDistM, double* lines, int max_lines,
+                      double* pts, int max_pts, int* n_pts, double* lidar_pos, int* im_size,
+                      uint8_t* line_im, int line_im_cap);
+
+long long lsdo_feature_scan_many(const double* map_param, const double* range, const double* angle, const int* beam_off,
+                                 int n_frames, long long* n_pts_total);
+
 #ifdef __cplusplus
 }
 #endif

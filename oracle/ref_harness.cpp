@@ -249,7 +249,7 @@ int ref_feature_scan(const double* map_param, const double* ranges, const double
         const structLinesInfo& L = FS.linesInfo[i];
         double* o = lines + 10 * i;
         o[0] = L.k; o[1] = L.b; o[2] = L.dx; o[3] = L.dy; o[4] = L.x1; o[5] = L.y1;
-        o[6] = L.x2; o[7] = L.y2; o[8] = L.len; o[9] = 0;  // orient is not set by FeatureScan
+        o[6] = L.x2; o[7] = L.y2; o[8] = L.len; o[9] = L.orient;
     }
     int np = (int)FS.scanImPoint.size();
     if (n_pts) *n_pts = np;
@@ -259,6 +259,27 @@ int ref_feature_scan(const double* map_param, const double* ranges, const double
     if (line_im && (size_t)FS.lineIm.rows * FS.lineIm.cols <= (size_t)line_im_cap) copy_mat(FS.lineIm, line_im);
     int nl = FS.len_linesInfo;
     free(FS.linesInfo);
+    return nl;
+}
+
+// FeatureScan over many frames with nothing copied out (the CPU timing leg of bench.py): returns the total line count,
+// *n_pts_total = total raster samples.
+long long ref_feature_scan_many(const double* map_param, const double* ranges, const double* angles, const int* beam_off,
+                                int n_frames, long long* n_pts_total) {
+    structMapParam mp;
+    mp.oriMapCol = (int)map_param[0]; mp.oriMapRow = (int)map_param[1];
+    mp.mapResol = map_param[2]; mp.mapOriX = map_param[3]; mp.mapOriY = map_param[4];
+    long long nl = 0, np = 0;
+    std::vector<myrdp::structLidarPointPolar> lp;
+    for (int f = 0; f < n_frames; f++) {
+        const int n = beam_off[f + 1] - beam_off[f];
+        lp.resize(n > 0 ? n : 1);
+        for (int i = 0; i < n; i++) { lp[i].range = ranges[beam_off[f] + i]; lp[i].angle = angles[beam_off[f] + i]; lp[i].split = false; }
+        myrdp::structFeatureScan FS = myrdp::FeatureScan(mp, lp.data(), n, rdp_leastPoint, rdp_threLine, rdp_leastDist);
+        nl += FS.len_linesInfo; np += (long long)FS.scanImPoint.size();
+        free(FS.linesInfo);
+    }
+    if (n_pts_total) *n_pts_total = np;
     return nl;
 }
 

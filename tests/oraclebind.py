@@ -39,8 +39,26 @@ def lib():
         L.lsdo_fa_scores.restype = C.c_int
         L.lsdo_fa_scores.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.lsdo_feature_scan.restype = C.c_int
+        L.lsdo_feature_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
+
+
+def feature_scan(map_param, ranges, angles, least_point=3, thre_line=0.08, least_dist_m=0.5):
+    """myrdp::FeatureScan restated (oracle/rdp_oracle.c); same dict as refbind.ref_feature_scan."""
+    mp = np.asarray(map_param, np.float64)
+    r = np.ascontiguousarray(ranges, np.float64); a = np.ascontiguousarray(angles, np.float64)
+    lines = np.zeros((max(2 * len(r) + 2, 1), 10)); pts = np.zeros((400000, 2)); npts = C.c_int(0)
+    lidar = np.zeros(2); imsz = np.zeros(2, np.int32)
+    cap = 4096 * 4096
+    im = np.zeros(cap, np.uint8)
+    n = lib().lsdo_feature_scan(_p(mp), _p(r), _p(a), len(r), least_point, thre_line, least_dist_m, _p(lines), len(lines), _p(pts),
+                                len(pts), C.byref(npts), _p(lidar), _p(imsz), _p(im), cap)
+    w, h = int(imsz[0]), int(imsz[1])
+    return dict(lines=lines[:n].copy(), pts=pts[:npts.value].copy(), lidar_pos=lidar, size=(w, h),
+                line_im=im[:max(w, 0) * max(h, 0)].reshape(max(h, 0), max(w, 0)).copy())
 
 
 def _p(a):
@@ -100,3 +118,17 @@ def fa_scores(scan_lines, map_lines, pts, mc, lidar_pose, last_pose):
     n = lib().lsdo_fa_scores(_p(sl), len(sl), _p(ml), len(ml), _p(pt), len(pt), _p(mc), cols, rows, _p(lp), _p(la),
                              _p(idx), _p(val), cap)
     return idx[:n].copy(), val[:n].copy()
+
+
+def feature_scan_many(map_param, frames):
+    mp = np.asarray(map_param, np.float64)
+    boff = np.zeros(len(frames) + 1, np.int32)
+    boff[1:] = np.cumsum([len(r) for r, _ in frames])
+    r = np.ascontiguousarray(np.concatenate([f[0] for f in frames]), np.float64)
+    a = np.ascontiguousarray(np.concatenate([f[1] for f in frames]), np.float64)
+    L = lib()
+    L.lsdo_feature_scan_many.restype = C.c_longlong
+    L.lsdo_feature_scan_many.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    npts = C.c_longlong(0)
+    nl = L.lsdo_feature_scan_many(_p(mp), _p(r), _p(a), _p(boff), len(frames), C.byref(npts))
+    return int(nl), int(npts.value)

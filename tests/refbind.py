@@ -40,6 +40,7 @@ def lib(variant="glibc"):
     L.ref_feature_association.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ref_feature_scan.restype = C.c_int
+    L.ref_feature_scan_many.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
     L.ref_feature_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     _libs[variant] = L
@@ -110,3 +111,17 @@ def ref_feature_scan(map_param, ranges, angles, variant="glibc"):
     w, h = int(imsz[0]), int(imsz[1])
     return dict(lines=lines[:n].copy(), pts=pts[:npts.value].copy(), lidar_pos=lidar, size=(w, h),
                 line_im=im[:w * h].reshape(h, w).copy())
+
+
+def ref_feature_scan_many(map_param, frames, variant="glibc"):
+    """myrdp::FeatureScan over a list of (ranges, angles) frames inside one native call; returns (lines, samples)."""
+    mp = np.asarray(map_param, np.float64)
+    boff = np.zeros(len(frames) + 1, np.int32)
+    boff[1:] = np.cumsum([len(r) for r, _ in frames])
+    r = np.ascontiguousarray(np.concatenate([f[0] for f in frames]), np.float64)
+    a = np.ascontiguousarray(np.concatenate([f[1] for f in frames]), np.float64)
+    L = lib(variant)
+    L.ref_feature_scan_many.restype = C.c_longlong
+    npts = C.c_longlong(0)
+    nl = L.ref_feature_scan_many(_p(mp), _p(r), _p(a), _p(boff), len(frames), C.byref(npts))
+    return int(nl), int(npts.value)

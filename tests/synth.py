@@ -8,3 +8,4 @@ _m = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_m)
 occupancy_grid = _m.occupancy_grid
 fake_scan_frame = _m.fake_scan_frame
+lidar_frame = _m.lidar_frame

@@ -1,0 +1,131 @@
+"""Parity of the CUDA scan front-end (lsdb_feature_scan_frames = myrdp::FeatureScan, LSD/myRDP.cpp:9-185) with the
+reference's golden outputs and the oracle: everything bit-exact (NaN == NaN for the intercept of vertical pieces)."""
+import os
+
+import numpy as np
+import pytest
+
+import oraclebind
+import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MP = [1377, 428, 0.05, -41.4, -9.8]
+
+
+def _lines10(rec):
+    return np.stack([rec[k].astype(np.float64) for k in ("k", "b", "dx", "dy", "x1", "y1", "x2", "y2", "len", "orient")], 1)
+
+
+def _check(got, want, tag):
+    assert tuple(got["size"]) == tuple(want["size"]), tag
+    assert np.array_equal(_lines10(got["lines"]), want["lines"], equal_nan=True), tag
+    assert np.array_equal(got["pts"], np.asarray(want["pts"], np.float64)), tag
+    assert np.array_equal(got["lidar_pos"], want["lidar_pos"]), tag
+    if "line_im" in got and "line_im" in want:
+        assert np.array_equal(got["line_im"], want["line_im"]), tag
+
+
+def _finite(r, a):
+    keep = np.isfinite(r)
+    return r[keep], a[keep]
+
+
+def test_golden_lidar_frames_one_batch(lsdb, ctx):
+    """87 frames of the bundled Lidar.txt files in ONE call against the reference's own FeatureScan output"""
+    g = np.load(os.path.join(GOLD, "lidar_frames.npz"))
+    nf = int(g["n_frames"])
+    mp = g["map_param"]
+    frames = [_finite(g[f"f{f}/ranges"], g[f"f{f}/angles"]) for f in range(nf)]
+    out = ctx.feature_scan(mp[2], mp[3], mp[4], frames, want_rasters=True)
+    assert len(out) == nf
+    for f in range(nf):
+        want = dict(lines=g[f"f{f}/lines"], pts=g[f"f{f}/pts"], lidar_pos=g[f"f{f}/lidar_pos"], size=g[f"f{f}/size"])
+        _check(out[f], want, f)
+        im = np.zeros(out[f]["line_im"].shape, np.uint8)               # FS.lineIm = 255 exactly at scanImPoint
+        im[g[f"f{f}/pts"][:, 1], g[f"f{f}/pts"][:, 0]] = 255
+        assert np.array_equal(out[f]["line_im"], im), f
+    # the golden association fixture starts from the same frames: its scan lines / points are reproduced too
+    ga = np.load(os.path.join(GOLD, "fa_frames.npz"))
+    for f in range(int(ga["n_frames"])):
+        assert np.array_equal(_lines10(out[f]["lines"]), ga[f"f{f}/scan_lines"], equal_nan=True)
+        assert np.array_equal(out[f]["pts"], ga[f"f{f}/pts"])
+
+
+@pytest.mark.parametrize("n_beams", [360, 720, 97])
+def test_synthetic_frames_vs_oracle(lsdb, ctx, n_beams):
+    frames = [synth.lidar_frame(4000 + s, n_beams=n_beams) for s in range(64)]
+    frames = [f for f in frames if len(f[0])]
+    out = ctx.feature_scan(MP[2], MP[3], MP[4], frames, want_rasters=True)
+    nl = 0
+    for f, (r, a) in enumerate(frames):
+        _check(out[f], oraclebind.feature_scan(MP, r, a), (n_beams, f))
+        nl += len(out[f]["lines"])
+    assert nl > len(frames)
+
+
+def test_ragged_and_tiny_frames(lsdb, ctx):
+    """frames of 1, 2, 3, 5 beams next to full sweeps; a sweep whose last beam joins the first (cluster 0 wraps)"""
+    rng = np.random.default_rng(7)
+    full = synth.lidar_frame(11)
+    frames = [(np.array([2.0]), np.array([0.1])), (np.array([2.0, 2.01]), np.array([0.1, 0.12])), full,
+              (np.array([1.0, 1.0, 1.0]), np.array([0.0, 0.01, 0.02])),
+              (rng.uniform(0.5, 3, 5), np.sort(rng.uniform(-3, 3, 5))), synth.lidar_frame(12, dropout=0.0),
+              (np.full(360, 3.0), -3.12414 + np.arange(360) * 0.0174532)]            # a circle: one cluster, never broken
+    out = ctx.feature_scan(MP[2], MP[3], MP[4], frames, want_rasters=True)
+    for f, (r, a) in enumerate(frames):
+        _check(out[f], oraclebind.feature_scan(MP, r, a), f)
+
+
+def test_non_default_parameters(lsdb, ctx):
+    frames = [synth.lidar_frame(900 + s) for s in range(16)]
+    for prm in (dict(least_point=1, thre_line=0.03, least_dist_m=0.2), dict(least_point=8, thre_line=0.2, least_dist_m=1.0),
+                dict(least_point=3, thre_line=0.08, least_dist_m=0.0)):
+        out = ctx.feature_scan(0.03, -20.0, -7.5, frames, want_rasters=True, **prm)
+        for f, (r, a) in enumerate(frames):
+            _check(out[f], oraclebind.feature_scan([0, 0, 0.03, -20.0, -7.5], r, a, **prm), (prm, f))
+
+
+def test_error_paths(lsdb, ctx):
+    r, a = synth.lidar_frame(1)
+    with pytest.raises(lsdb.LsdbError, match="ARG"):
+        ctx.feature_scan(MP[2], MP[3], MP[4], [(r, a), (np.zeros(0), np.zeros(0))])        # a frame without beams
+    r2 = r.copy(); r2[3] = np.inf
+    with pytest.raises(lsdb.LsdbError, match="not finite"):
+        ctx.feature_scan(MP[2], MP[3], MP[4], [(r2, a)])
+    with pytest.raises(lsdb.LsdbError, match="ARG"):
+        ctx.feature_scan(0.0, MP[3], MP[4], [(r, a)])
+    assert ctx.feature_scan(MP[2], MP[3], MP[4], []) == []
+    # capacity: the sizing query fills the offsets, the real call refuses short buffers
+    import ctypes as C
+    L = lsdb.lib()
+    boff = np.array([0, len(r)], np.int32); info = np.zeros(1, lsdb.SCAN_INFO_DTYPE)
+    loff = np.zeros(2, np.int32); poff = np.zeros(2, np.int32); ioff = np.zeros(2, np.int64)
+    prm = lsdb._RdpParams(3, 0.08, 0.5)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    args = (ctx.h, MP[2], MP[3], MP[4], C.byref(prm), 1, p(r), p(a), p(boff), p(info))
+    assert L.lsdb_feature_scan_frames(*args, None, 0, p(loff), None, 0, p(poff), None, 0, p(ioff)) == 0
+    assert loff[1] == info[0]["n_lines"] > 0 and poff[1] == info[0]["n_pts"] > 0 and ioff[1] == info[0]["im_cols"] * info[0]["im_rows"]
+    lines = np.zeros(1, lsdb.LINE_DTYPE); pts = np.zeros((int(poff[1]), 2))
+    assert L.lsdb_feature_scan_frames(*args, p(lines), 1, p(loff), p(pts), len(pts), p(poff), None, 0, p(ioff)) == 3   # LSDB_ERR_CAPACITY
+    assert b"max_lines" in L.lsdb_last_error(ctx.h)
+
+
+def test_scan_to_estimate_chain(lsdb, ctx):
+    """lidar frames -> device FeatureScan -> device scoring + reduction: the same estimates as from the reference's
+    scan lines / points of the golden association fixture"""
+    g = np.load(os.path.join(GOLD, "lidar_frames.npz"))
+    ga = np.load(os.path.join(GOLD, "fa_frames.npz"))
+    gm = np.load(os.path.join(GOLD, "bundled_maps.npz"))
+    mp = g["map_param"]
+    nf = int(ga["n_frames"])
+    out = ctx.feature_scan(mp[2], mp[3], mp[4], [_finite(g[f"f{f}/ranges"], g[f"f{f}/angles"]) for f in range(nf)])
+    mc = ctx.map_cache(gm["mapValue/map"], float(gm["mapValue/param"][2]))
+    fm = lsdb.FaMap(ctx, mc, ga["map_lines"])
+    mine = fm.estimate([dict(scan_lines=o["lines"], pts=o["pts"], lidar_pose=np.rint(o["lidar_pos"]), last_pose=ga[f"f{f}/last_pose"])
+                        for f, o in enumerate(out)])
+    ref = fm.estimate([dict(scan_lines=ga[f"f{f}/scan_lines"], pts=ga[f"f{f}/pts"], lidar_pose=ga[f"f{f}/lidar_pose"],
+                            last_pose=ga[f"f{f}/last_pose"]) for f in range(nf)])
+    assert mine.tobytes() == ref.tobytes()
+    assert int((mine["n_kept"] > 0).sum()) >= 6
+    fm.close()

@@ -59,5 +59,32 @@ for f in range(12):
     fa[f"f{f}/scan_lsd_lines"] = refbind.ref_lsd(occ, want_maps=False)["lines"]
     print("frame", f * 8, "lines", len(fs["lines"]), "pts", len(fs["pts"]), "hyp", len(idx), "kept(<3)", int((val[:, 3] < 3).sum()))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fa_frames.npz"), **fa)
-for f in ("bundled_maps.npz", "fa_frames.npz"):
+
+# scan front-end fixture: raw lidar frames (Inf beams included, as in Lidar.txt) and what the reference's
+# myrdp::FeatureScan makes of them.  Oracle (ii) build (portable math = the device's arithmetic); `glibc_same` records
+# whether the stock-glibc build gives the identical result for that frame.
+import glob  # noqa: E402
+picks = [(D + "Lidar.txt", list(range(0, 96, 8)))]
+for fn in sorted(glob.glob("/root/reference/data_2019051*/data_f*key/data*/Lidar.txt")):
+    picks.append((fn, [5, 31, 35, 119]))
+ls = {}
+k = 0
+for fn, idxs in picks:
+    raw = np.loadtxt(fn).reshape(-1, 2)
+    for i in idxs:
+        if (i + 1) * 360 > len(raw):
+            continue
+        fr = raw[i * 360:(i + 1) * 360]
+        keep = np.isfinite(fr[:, 0])
+        a = refbind.ref_feature_scan(mp, fr[keep, 0], fr[keep, 1], variant="lsdm")
+        g = refbind.ref_feature_scan(mp, fr[keep, 0], fr[keep, 1], variant="glibc")
+        same = (a["size"] == g["size"] and np.array_equal(a["lines"], g["lines"], equal_nan=True) and np.array_equal(a["pts"], g["pts"]))
+        ls[f"f{k}/ranges"] = fr[:, 0].copy(); ls[f"f{k}/angles"] = fr[:, 1].copy()
+        ls[f"f{k}/lines"] = a["lines"]; ls[f"f{k}/pts"] = a["pts"].astype(np.int32)
+        ls[f"f{k}/lidar_pos"] = a["lidar_pos"].copy(); ls[f"f{k}/size"] = np.array(a["size"]); ls[f"f{k}/glibc_same"] = np.array(same)
+        k += 1
+ls["n_frames"] = np.array(k); ls["map_param"] = np.array(mp, np.float64)
+print("lidar frames", k, "glibc-identical", sum(bool(ls[f"f{i}/glibc_same"]) for i in range(k)))
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "lidar_frames.npz"), **ls)
+for f in ("bundled_maps.npz", "fa_frames.npz", "lidar_frames.npz"):
     print(f, os.path.getsize(os.path.join(ROOT, "tests", "golden", f)) // 1024, "KiB")
