@@ -70,3 +70,5 @@ def test_dropin_library_keeps_the_reference_entry_points():
     assert "mylsd::createMapCache(cv::Mat, double)" in syms
     assert "mylsd::myLineSegmentDetector_cpu" in syms and "myfa::FeatureAssociation_cpu" in syms   # the reference bodies, renamed
     assert "mylsd::createMapCache_cpu" in syms
+    assert "myrdp::FeatureScan(_structMapParam, myrdp::_structLidarPointPolar*, int, int, double, double)" in syms
+    assert "myrdp::FeatureScan_cpu" in syms

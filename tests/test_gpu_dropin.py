@@ -1,5 +1,5 @@
-"""The C++ drop-in boundary: oracle/_ref/libref_dropin.so links the reference's OWN host code (createMapCache, myRDP,
-ukf, the harness that mirrors main_on_windows.cpp) with this repo's bodies for mylsd::myLineSegmentDetector and
+"""The C++ drop-in boundary: oracle/_ref/libref_dropin.so links the reference's OWN host code (the RDP helpers,
+ukf, the harness that mirrors main_on_windows.cpp) with this repo's bodies for mylsd::myLineSegmentDetector, createMapCache, myrdp::FeatureScan and
 myfa::FeatureAssociation (linesegmentdetector-slam_b200/host/*.cpp -> liblsdb200.so).  Same entry points, same structs:
 the outputs must match the unmodified reference (libref_glibc.so / golden fixtures)."""
 import os
@@ -94,3 +94,21 @@ def test_FeatureAssociation_dropin_matches_reference():
         assert np.allclose(kP, eP, rtol=1e-9, atol=1e-9)
         tracked += 1
     assert tracked >= 6
+
+
+@needs_dropin
+def test_FeatureScan_dropin_matches_reference():
+    """myrdp::FeatureScan through the reference's own header and structs (structFeatureScan: lineIm Mat, malloc'd
+    linesInfo, lidarPos, scanImPoint vector), body = liblsdb200"""
+    g = np.load(os.path.join(GOLD, "lidar_frames.npz"))
+    mp = list(g["map_param"])
+    for f in range(0, int(g["n_frames"]), 5):
+        r, a = g[f"f{f}/ranges"], g[f"f{f}/angles"]
+        keep = np.isfinite(r)
+        fs = refbind.ref_feature_scan(mp, r[keep], a[keep], variant="dropin")
+        assert np.array_equal(fs["lines"], g[f"f{f}/lines"], equal_nan=True)
+        assert np.array_equal(fs["pts"], g[f"f{f}/pts"].astype(np.float64))
+        assert np.array_equal(fs["lidar_pos"], g[f"f{f}/lidar_pos"]) and tuple(fs["size"]) == tuple(g[f"f{f}/size"])
+        im = np.zeros(fs["line_im"].shape, np.uint8)
+        im[g[f"f{f}/pts"][:, 1], g[f"f{f}/pts"][:, 0]] = 255
+        assert np.array_equal(fs["line_im"], im)
