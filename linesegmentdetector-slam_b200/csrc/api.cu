@@ -31,6 +31,7 @@ struct lsdb_ctx {
     // scan front-end: ragged outputs (device + pinned mirror) and the raster plane
     void* fsOut; void* fsOutHost; size_t fsOutCap;
     void* fsIm; size_t fsImCap;
+    void* fsTmp; size_t fsTmpCap;
     float fsMs;
 };
 
@@ -84,7 +85,7 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
     if (prop.major != 10) return LSDB_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
     lsdb_ctx* c = new lsdb_ctx();
     c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0;
-    c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsIm = 0; c->fsImCap = 0; c->fsMs = 0;
+    c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsIm = 0; c->fsImCap = 0; c->fsTmp = 0; c->fsTmpCap = 0; c->fsMs = 0;
     c->lgammaTab = 0; c->lgammaN = 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LSDB_ERR_NO_DEVICE; }
     if (stream) { c->stream = (cudaStream_t)stream; c->ownStream = false; }
@@ -112,6 +113,7 @@ extern "C" void lsdb_destroy(lsdb_ctx* c) {
     if (c->fsOut) cudaFree(c->fsOut);
     if (c->fsOutHost) cudaFreeHost(c->fsOutHost);
     if (c->fsIm) cudaFree(c->fsIm);
+    if (c->fsTmp) cudaFree(c->fsTmp);
     cudaEventDestroy(c->faEv[0]); cudaEventDestroy(c->faEv[1]);
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
@@ -679,6 +681,13 @@ extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX
     const size_t oR = 0, oA = oR + al256(8 * (size_t)nB), oB = oA + al256(8 * (size_t)nB), oInfo = oB + al256(4 * (size_t)(nFrames + 1)),
                  oLoff = oInfo + al256(sizeof(LsdbFsInfo) * (size_t)nFrames), oPoff = oLoff + al256(4 * (size_t)(nFrames + 1)),
                  oIoff = oPoff + al256(4 * (size_t)(nFrames + 1)), total = oIoff + al256(8 * (size_t)(nFrames + 1));
+    const size_t tmpBytes = sizeof(LsdbFsPiece) * ((size_t)nB + 2 * (size_t)nFrames);   // device only: kept line pieces, n + 2 per frame
+    if (tmpBytes > ctx->fsTmpCap) {
+        if (ctx->fsTmp) cudaFree(ctx->fsTmp);
+        ctx->fsTmp = 0; ctx->fsTmpCap = 0;
+        CK(ctx, cudaMalloc(&ctx->fsTmp, tmpBytes + tmpBytes / 4));
+        ctx->fsTmpCap = tmpBytes + tmpBytes / 4;
+    }
     if (total > ctx->faDevCap) {
         if (ctx->faDev) cudaFree(ctx->faDev);
         if (ctx->faHost) cudaFreeHost(ctx->faHost);
@@ -695,8 +704,9 @@ extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX
     const double pi = 4.0 * lsdm_atan(1.0);
     CK(ctx, cudaMemcpyAsync(D, H, oInfo, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaEventRecord(ctx->faEv[0], s));
-    CK(ctx, (cudaError_t)lsdb_launch_fscan(s, 0, nFrames, maxBeams, (double*)(D + oR), (double*)(D + oA), (int*)(D + oB), resol, oriX, oriY,
-                                           prm->least_point, prm->thre_line, prm->least_dist_m, pi, (LsdbFsInfo*)(D + oInfo), 0, 0, 0, 0, 0, 0));
+    CK(ctx, (cudaError_t)lsdb_launch_fscan_frames(s, nFrames, maxBeams, (double*)(D + oR), (double*)(D + oA), (int*)(D + oB), resol, oriX, oriY,
+                                                  prm->least_point, prm->thre_line, prm->least_dist_m, (LsdbFsInfo*)(D + oInfo),
+                                                  (LsdbFsPiece*)ctx->fsTmp));
     CK(ctx, cudaEventRecord(ctx->faEv[1], s));
     CK(ctx, cudaMemcpyAsync(H + oInfo, D + oInfo, sizeof(LsdbFsInfo) * (size_t)nFrames, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
@@ -740,10 +750,9 @@ extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX
     if (lineIm && nI > 0) CK(ctx, cudaMemsetAsync(ctx->fsIm, 0, (size_t)nI, s));
     char* O = (char*)ctx->fsOut; char* OH = (char*)ctx->fsOutHost;
     CK(ctx, cudaEventRecord(ctx->faEv[0], s));
-    CK(ctx, (cudaError_t)lsdb_launch_fscan(s, 1, nFrames, maxBeams, (double*)(D + oR), (double*)(D + oA), (int*)(D + oB), resol, oriX, oriY,
-                                           prm->least_point, prm->thre_line, prm->least_dist_m, pi, (LsdbFsInfo*)(D + oInfo), (int*)(D + oLoff),
-                                           (int*)(D + oPoff), (long long*)(D + oIoff), (LsdbFaLine*)(O + oL), (double*)(O + oP),
-                                           lineIm ? (uint8_t*)ctx->fsIm : 0));
+    CK(ctx, (cudaError_t)lsdb_launch_fscan_lines(s, nFrames, (int)nL, (int*)(D + oB), (LsdbFsInfo*)(D + oInfo), (LsdbFsPiece*)ctx->fsTmp,
+                                                 (int*)(D + oLoff), (int*)(D + oPoff), (long long*)(D + oIoff), pi, (LsdbFaLine*)(O + oL),
+                                                 (double*)(O + oP), lineIm ? (uint8_t*)ctx->fsIm : 0));
     CK(ctx, cudaEventRecord(ctx->faEv[1], s));
     CK(ctx, cudaMemcpyAsync(OH, O, outTotal, cudaMemcpyDeviceToHost, s));
     if (lineIm && nI > 0) CK(ctx, cudaMemcpyAsync(lineIm, ctx->fsIm, (size_t)nI, cudaMemcpyDeviceToHost, s));

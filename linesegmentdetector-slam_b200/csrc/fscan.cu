@@ -1,25 +1,30 @@
 // Scan front-end of the association path: myrdp::FeatureScan for a batch of lidar frames
 // (LSD/myRDP.cpp:9-185; RegionSegmentation :274-352, SplitMerge/SplitMergeAssistant :187-272,
-// getThresholdDeltaDist :354-375).  One CTA per frame.  The frame's beams live in shared memory; the
-// steps whose result depends on order (cluster boundaries, the list of line pieces, the order of the
-// raster samples) are kept in the reference's order, everything else is spread over the threads:
-//   beams -> metric / grid coordinates (correctly rounded cos/sin, computed once instead of three times)
-//   break flags -> clusters (one thread; <= n steps of a 1-byte read)
-//   Ramer-Douglas-Peucker per cluster: warp-wide arg-max with the reference's first-maximum rule and an
-//     explicit stack (the recursion only sets split flags, so the visiting order is free)
-//   line pieces -> ordered compaction by ballot -> one warp per line: sample count, then (second pass)
-//     records, raster samples and the 0/255 scan raster at their final offsets.
-// The kernel runs twice: COUNT fills lsdb_scan_info so that the host can lay out the ragged outputs,
-// WRITE recomputes the frame (a few microseconds) and stores them.  -fmad=false like the rest of the library.
+// getThresholdDeltaDist :354-375).  Two kernels:
+//   lsdb_fscan_frames_kernel — one CTA per frame, the frame's beams in shared memory.  The steps whose result
+//     depends on order (cluster boundaries, the list of line pieces) keep the reference's order, everything else
+//     is spread over the threads:
+//       beams -> metric coordinates (correctly rounded cos/sin, computed once instead of three times)
+//       break flags -> clusters (one thread; <= n steps of a 1-byte read)
+//       Ramer-Douglas-Peucker, one warp per cluster: warp-wide arg-max with the reference's first-maximum rule and
+//         an explicit stack (the recursion only sets split flags, so the visiting order is free).  The distance is a
+//         numerator over a per-call constant; division by a positive constant is monotone, so the maximum quotient
+//         is the quotient of the maximum numerator and only numerators within 2^-48 of it can tie with it: one
+//         division per call instead of one per point, same winner.
+//       grid coordinates, raster extent, line pieces -> ordered compaction by ballot -> samples per kept line
+//     Output: lsdb_scan_info and, per kept line, its end points and the offset of its samples inside the frame.
+//   lsdb_fscan_lines_kernel — one warp per kept line of the whole batch, after the host has laid out the ragged
+//     outputs: the structLinesInfo record, the raster samples in order, the 0/255 raster.
+// -fmad=false like the rest of the library.
 #include "lsdb_common.cuh"
 #include <limits.h>
 
-#define FS_NT 128
+#define FS_NT 64
 #define FS_NW (FS_NT / 32)
+#define FS_LW 8                     // warps (= lines) per CTA of the lines kernel
 
 struct FsShared {
     double red[4][FS_NW];
-    double minX, minY, maxX, maxY;
     int nc, nSeg, nLines, nPts, overflow;
 };
 
@@ -36,9 +41,11 @@ __device__ __forceinline__ double fs_delta_thre(double r) {  // LSD/myRDP.cpp:35
     return 1.1;
 }
 
+// shared memory of one frame: coordinates 2 x f64, clusters 2 x i32, one RDP stack per warp (the first doubles as
+// the line-piece list afterwards) 2 x i32 each, samples per line i32, break + split flags 2 x u8
 size_t lsdb_fscan_smem(int maxBeams) {
     const size_t cap = (size_t)maxBeams + 1;
-    return sizeof(FsShared) + 8 * 4 * cap + 4 * (2 * (cap + 1) + 2 * (cap + 2) + 2 * (2 * cap + 2) + (2 * cap + 2)) + 2 * cap + 16;
+    return sizeof(FsShared) + 8 * 2 * cap + 4 * (2 * (cap + 1) + FS_NW * 2 * (cap + 2) + (cap + 2)) + 2 * cap + 16;
 }
 
 // geometry of one kept line piece (grid coordinates relative to the frame's minimum), LSD/myRDP.cpp:75-131
@@ -46,16 +53,16 @@ struct FsLine {
     double x1, y1, x2, y2, k;
     int xLow, yLow, cnt, alongX;
 };
-__device__ __forceinline__ FsLine fs_line(double ax, double ay, double bx, double by, double minX, double minY) {
+__device__ __forceinline__ FsLine fs_line(double x1, double y1, double x2, double y2) {
     FsLine L;
-    L.x1 = ax - minX; L.y1 = ay - minY; L.x2 = bx - minX; L.y2 = by - minY;
-    L.k = (L.y2 - L.y1) / (L.x2 - L.x1);
-    const int xLow = lsdb_x86_d2i(floor(L.x1 > L.x2 ? L.x2 : L.x1)), xHigh = lsdb_x86_d2i(ceil(L.x1 > L.x2 ? L.x1 : L.x2));
-    const int yLow = lsdb_x86_d2i(floor(L.y1 > L.y2 ? L.y2 : L.y1)), yHigh = lsdb_x86_d2i(ceil(L.y1 > L.y2 ? L.y1 : L.y2));
+    L.x1 = x1; L.y1 = y1; L.x2 = x2; L.y2 = y2;
+    L.k = (y2 - y1) / (x2 - x1);
+    const int xLow = lsdb_x86_d2i(floor(x1 > x2 ? x2 : x1)), xHigh = lsdb_x86_d2i(ceil(x1 > x2 ? x1 : x2));
+    const int yLow = lsdb_x86_d2i(floor(y1 > y2 ? y2 : y1)), yHigh = lsdb_x86_d2i(ceil(y1 > y2 ? y1 : y2));
     const int xl = xHigh - xLow + 1, yl = yHigh - yLow + 1;
     L.xLow = xLow; L.yLow = yLow;
     L.cnt = xl > yl ? xl : yl;                               // emission loop bound, :132-153
-    L.alongX = fabs(L.x2 - L.x1) > fabs(L.y2 - L.y1);        // which axis is walked, :104
+    L.alongX = fabs(x2 - x1) > fabs(y2 - y1);                // which axis is walked, :104
     return L;
 }
 // sample m of a line: true when it is stored (inside the raster and off row/column 0), :107-139
@@ -65,65 +72,37 @@ __device__ __forceinline__ bool fs_sample(const FsLine& L, int m, int W, int H, 
     return !(xx < 0 || xx >= W || yy < 0 || yy >= H) && xx != 0 && yy != 0;
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(FS_NT) lsdb_fscan_kernel(
+__global__ void __launch_bounds__(FS_NT, 12) lsdb_fscan_frames_kernel(
     int maxBeams, const double* __restrict__ ranges, const double* __restrict__ angles, const int* __restrict__ beamOff,
-    double resol, double oriX, double oriY, int leastPoint, double threLine, double leastDistM, double pi,
-    LsdbFsInfo* __restrict__ info, const int* __restrict__ lineOff, const int* __restrict__ ptOff,
-    const long long* __restrict__ imOff, LsdbFaLine* __restrict__ lines, double* __restrict__ pts, uint8_t* __restrict__ lineIm) {
+    double resol, double oriX, double oriY, int leastPoint, double threLine, double leastDistM,
+    LsdbFsInfo* __restrict__ info, LsdbFsPiece* __restrict__ pieces) {
     extern __shared__ __align__(16) unsigned char fsRaw[];
     FsShared& sh = *(FsShared*)fsRaw;
     const int cap = maxBeams + 1;
-    double* px = (double*)(fsRaw + sizeof(FsShared));
-    double* py = px + cap; double* gx = py + cap; double* gy = gx + cap;
-    int* cell = (int*)(gy + cap);            // 2*(cap+1): start, end beam of each cluster
-    int* stack = cell + 2 * (cap + 1);       // 2*(cap+2)
-    int* seg = stack + 2 * (cap + 2);        // 2*(2*cap+2): beam pairs of the line pieces, compacted in place
-    int* cnt = seg + 2 * (2 * cap + 2);      // 2*cap+2: samples per kept line, then their exclusive prefix
-    uint8_t* brk = (uint8_t*)(cnt + 2 * cap + 2);
+    double* px = (double*)(fsRaw + sizeof(FsShared));   // metric x, later grid x
+    double* py = px + cap;
+    int* cell = (int*)(py + cap);            // 2*(cap+1): start, end beam of each cluster
+    int* stacks = cell + 2 * (cap + 1);      // FS_NW x 2*(cap+2)
+    int* seg = stacks;                       // beam pairs of the line pieces (after RDP), compacted in place
+    int* cnt = stacks + FS_NW * 2 * (cap + 2);   // cap+2: samples per kept line, then their exclusive prefix
+    uint8_t* brk = (uint8_t*)(cnt + cap + 2);
     uint8_t* split = brk + cap;
-    const int segCap = 2 * cap + 2;
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = beamOff[f + 1] - beamOff[f];
     const double* R = ranges + beamOff[f];
     const double* A = angles + beamOff[f];
     const double pose0 = 0.0, pose1 = 0.0, pose2 = 0.0;      // scanPose, :11
+    const int segCap = n + 2;                                // disjoint clusters give at most n + 1 pieces
 
-    // ---- beams -> coordinates (:21-34, :196-201, :289-293) and the raster extent ----
-    double mnX = INFINITY, mnY = INFINITY, mxX = 0, mxY = 0;
+    // ---- beams -> metric coordinates (:196-201, :289-293) ----
     for (int i = tid; i < n; i += FS_NT) {
         const double r = R[i], a = A[i] + pose2;
-        const double x = r * lsdm_cos(a) + pose0, y = r * lsdm_sin(a) + pose1;
-        px[i] = x; py[i] = y;
-        const double X = floor((x - oriX) / resol), Y = floor((y - oriY) / resol);
-        gx[i] = X; gy[i] = Y;
-        if (X < mnX) mnX = X;
-        if (X > mxX) mxX = X;
-        if (Y < mnY) mnY = Y;
-        if (Y > mxY) mxY = Y;
+        px[i] = r * lsdm_cos(a) + pose0; py[i] = r * lsdm_sin(a) + pose1;
         split[i] = 0;
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        double t;
-        t = __shfl_xor_sync(0xffffffffu, mnX, o); if (t < mnX) mnX = t;
-        t = __shfl_xor_sync(0xffffffffu, mxX, o); if (t > mxX) mxX = t;
-        t = __shfl_xor_sync(0xffffffffu, mnY, o); if (t < mnY) mnY = t;
-        t = __shfl_xor_sync(0xffffffffu, mxY, o); if (t > mxY) mxY = t;
-    }
-    if (lane == 0) { sh.red[0][warp] = mnX; sh.red[1][warp] = mxX; sh.red[2][warp] = mnY; sh.red[3][warp] = mxY; }
+    if (tid == 0) sh.overflow = 0;
     __syncthreads();
-    if (tid == 0) {
-        double a = sh.red[0][0], b = sh.red[1][0], c = sh.red[2][0], d = sh.red[3][0];
-        for (int w = 1; w < FS_NW; w++) {
-            if (sh.red[0][w] < a) a = sh.red[0][w];
-            if (sh.red[1][w] > b) b = sh.red[1][w];
-            if (sh.red[2][w] < c) c = sh.red[2][w];
-            if (sh.red[3][w] > d) d = sh.red[3][w];
-        }
-        sh.minX = a; sh.maxX = b; sh.minY = c; sh.maxY = d; sh.overflow = 0;
-    }
     // ---- break flags (:304-337): 1 = gap after beam i, 2 = last beam joins the first ----
     for (int i = tid; i < n; i += FS_NT) {
         const int j = i == n - 1 ? 0 : i + 1;
@@ -148,14 +127,13 @@ __global__ void __launch_bounds__(FS_NT) lsdb_fscan_kernel(
     }
     __syncthreads();
     const int nc = sh.nc;
-    const double minX = sh.minX, minY = sh.minY;
 
-    if (warp == 0) {
-        // ---- Ramer-Douglas-Peucker (:218-272) ----
-        for (int c = 0; c < nc; c++) {
-            int sp = 0;
+    // ---- Ramer-Douglas-Peucker (:218-272), clusters dealt to the warps ----
+    {
+        int* stack = stacks + warp * 2 * (cap + 2);
+        for (int c = warp; c < nc; c += FS_NW) {
             if (lane == 0) { stack[0] = cell[2 * c]; stack[1] = cell[2 * c + 1]; }
-            sp = 2;
+            int sp = 2;
             __syncwarp();
             while (sp) {
                 const int e = stack[sp - 1], s = stack[sp - 2];
@@ -166,20 +144,28 @@ __global__ void __launch_bounds__(FS_NT) lsdb_fscan_kernel(
                 const double k = (py[e] - py[s]) / (px[e] - px[s]);
                 const double d = py[e] - k * px[e];
                 const double den = sqrt(k * k + 1);
-                double best = 0; int bestPos = INT_MAX;
+                double bestN = 0;                                   // largest numerator (NaN never wins, as in `dist > dist_max`)
                 for (int i = 1 + lane; i < len - 1; i += 32) {
                     int a = s + i; if (a >= n) a -= n;
-                    const double dist = fabs(k * px[a] - py[a] + d) / den;
-                    if (dist > best) { best = dist; bestPos = i; }
+                    const double num = fabs(k * px[a] - py[a] + d);
+                    if (num > bestN) bestN = num;
                 }
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int op = __shfl_xor_sync(0xffffffffu, bestPos, o);
-                    if (ob > best || (ob == best && op < bestPos)) { best = ob; bestPos = op; }
+                for (int o = 16; o; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, bestN, o); if (t > bestN) bestN = t; }
+                double best = 0; int iMax = 0;
+                const double q = bestN / den;                       // the maximum distance
+                if (q > 0) {
+                    const double lo = bestN < 1e-280 ? 0.0 : bestN * 0.99999999999999645;   // 1 - 2^-48
+                    int pos = INT_MAX;                              // first point whose distance equals the maximum
+                    for (int i = 1 + lane; i < len - 1; i += 32) {
+                        int a = s + i; if (a >= n) a -= n;
+                        const double num = fabs(k * px[a] - py[a] + d);
+                        if (num >= lo && num / den == q) { pos = i; break; }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, pos, o); if (t < pos) pos = t; }
+                    if (pos != INT_MAX) { best = q; iMax = s + pos; if (iMax >= n) iMax -= n; }
                 }
-                int iMax = 0;
-                if (bestPos != INT_MAX) { iMax = s + bestPos; if (iMax >= n) iMax -= n; }
                 const double rr = R[iMax];
                 const double thre = rr > 9 ? rr * threLine : threLine;
                 if (best > thre) {
@@ -192,28 +178,60 @@ __global__ void __launch_bounds__(FS_NT) lsdb_fscan_kernel(
                 __syncwarp();
             }
         }
-        __syncwarp();
-        // ---- line pieces in the reference's order (:49-74) ----
-        if (lane == 0) {
-            int ns = 0;
-            for (int c = 0; c < nc; c++) {
-                const int s = cell[2 * c], e = cell[2 * c + 1];
-                const int len = e > s ? e - s + 1 : n + e - s + 1;
-                int a = s;
-                for (int j = 0; j <= len; j++) {
-                    int b;
-                    if (j < len) { b = s + j; if (b >= n) b -= n; if (!split[b]) continue; }
-                    else b = e;
-                    if (ns < segCap) { seg[2 * ns] = a; seg[2 * ns + 1] = b; }
-                    ns++;
-                    a = b;
-                }
+    }
+    __syncthreads();
+
+    // ---- grid coordinates in place (:21-34) and the raster extent ----
+    double mnX = INFINITY, mnY = INFINITY, mxX = 0, mxY = 0;
+    for (int i = tid; i < n; i += FS_NT) {
+        const double X = floor((px[i] - oriX) / resol), Y = floor((py[i] - oriY) / resol);
+        px[i] = X; py[i] = Y;
+        if (X < mnX) mnX = X;
+        if (X > mxX) mxX = X;
+        if (Y < mnY) mnY = Y;
+        if (Y > mxY) mxY = Y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        double t;
+        t = __shfl_xor_sync(0xffffffffu, mnX, o); if (t < mnX) mnX = t;
+        t = __shfl_xor_sync(0xffffffffu, mxX, o); if (t > mxX) mxX = t;
+        t = __shfl_xor_sync(0xffffffffu, mnY, o); if (t < mnY) mnY = t;
+        t = __shfl_xor_sync(0xffffffffu, mxY, o); if (t > mxY) mxY = t;
+    }
+    if (lane == 0) { sh.red[0][warp] = mnX; sh.red[1][warp] = mxX; sh.red[2][warp] = mnY; sh.red[3][warp] = mxY; }
+    // ---- line pieces in the reference's order (:49-74); the stacks are free now ----
+    __syncthreads();
+    if (tid == 0) {
+        int ns = 0;
+        for (int c = 0; c < nc; c++) {
+            const int s = cell[2 * c], e = cell[2 * c + 1];
+            const int len = e > s ? e - s + 1 : n + e - s + 1;
+            int a = s;
+            for (int j = 0; j <= len; j++) {
+                int b;
+                if (j < len) { b = s + j; if (b >= n) b -= n; if (!split[b]) continue; }
+                else b = e;
+                if (ns < segCap) { seg[2 * ns] = a; seg[2 * ns + 1] = b; }
+                ns++;
+                a = b;
             }
-            if (ns > segCap) { sh.overflow = 1; ns = segCap; }
-            sh.nSeg = ns;
         }
-        __syncwarp();
-        // ---- keep pieces of at least lineDistThre (:80-81), order preserved ----
+        if (ns > segCap) { sh.overflow = 1; ns = segCap; }
+        sh.nSeg = ns;
+    }
+    __syncthreads();
+    double minX = sh.red[0][0], maxX = sh.red[1][0], minY = sh.red[2][0], maxY = sh.red[3][0];
+#pragma unroll
+    for (int w = 1; w < FS_NW; w++) {
+        if (sh.red[0][w] < minX) minX = sh.red[0][w];
+        if (sh.red[1][w] > maxX) maxX = sh.red[1][w];
+        if (sh.red[2][w] < minY) minY = sh.red[2][w];
+        if (sh.red[3][w] > maxY) maxY = sh.red[3][w];
+    }
+    const int W = lsdb_x86_d2i(ceil(maxX - minX)), H = lsdb_x86_d2i(ceil(maxY - minY));
+    // ---- keep pieces of at least lineDistThre (:80-81), order preserved ----
+    if (warp == 0) {
         const int nSeg = sh.nSeg;
         const double distThre = leastDistM / resol;
         int nl = 0;
@@ -222,7 +240,7 @@ __global__ void __launch_bounds__(FS_NT) lsdb_fscan_kernel(
             int a = 0, b = 0; bool keep = false;
             if (i < nSeg) {
                 a = seg[2 * i]; b = seg[2 * i + 1];
-                const double ddx = gx[a] - gx[b], ddy = gy[a] - gy[b];
+                const double ddx = px[a] - px[b], ddy = py[a] - py[b];
                 keep = sqrt(ddx * ddx + ddy * ddy) >= distThre;
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -235,12 +253,11 @@ __global__ void __launch_bounds__(FS_NT) lsdb_fscan_kernel(
     }
     __syncthreads();
     const int nLines = sh.nLines;
-    const int W = lsdb_x86_d2i(ceil(sh.maxX - minX)), H = lsdb_x86_d2i(ceil(sh.maxY - minY));
 
     // ---- samples per line ----
     for (int L = warp; L < nLines; L += FS_NW) {
         const int a = seg[2 * L], b = seg[2 * L + 1];
-        const FsLine g = fs_line(gx[a], gy[a], gx[b], gy[b], minX, minY);
+        const FsLine g = fs_line(px[a] - minX, py[a] - minY, px[b] - minX, py[b] - minY);
         int c = 0;
         for (int m0 = 0; m0 < g.cnt; m0 += 32) {
             int xx, yy;
@@ -253,70 +270,91 @@ __global__ void __launch_bounds__(FS_NT) lsdb_fscan_kernel(
     if (tid == 0) {
         int run = 0;
         for (int L = 0; L < nLines; L++) { const int c = cnt[L]; cnt[L] = run; run += c; }
-        sh.nPts = run;
+        LsdbFsInfo o;
+        o.nLines = sh.overflow ? -1 : nLines; o.nPts = run; o.W = W; o.H = H;
+        o.lidarX = floor((pose0 - oriX) / resol - minX);   // :38-40
+        o.lidarY = floor((pose1 - oriY) / resol - minY);
+        info[f] = o;
     }
     __syncthreads();
-
-    if (!WRITE) {
-        if (tid == 0) {
-            LsdbFsInfo o;
-            o.nLines = sh.overflow ? -1 : nLines; o.nPts = sh.nPts; o.W = W; o.H = H;
-            o.lidarX = floor((pose0 - oriX) / resol - minX);   // :38-40
-            o.lidarY = floor((pose1 - oriY) / resol - minY);
-            info[f] = o;
-        }
-        return;
-    }
-    // ---- records, samples and raster at their final places (:82-174) ----
-    LsdbFaLine* outL = lines + lineOff[f];
-    double* outP = pts + 2 * (size_t)ptOff[f];
-    uint8_t* im = lineIm ? lineIm + imOff[f] : 0;
-    for (int L = warp; L < nLines; L += FS_NW) {
+    LsdbFsPiece* P = pieces + beamOff[f] + 2 * f;           // room for n + 2 pieces per frame
+    for (int L = tid; L < nLines; L += FS_NT) {
         const int a = seg[2 * L], b = seg[2 * L + 1];
-        const FsLine g = fs_line(gx[a], gy[a], gx[b], gy[b], minX, minY);
-        if (lane == 0) {
-            double ang = lsdm_atan(g.k) * 180.0 / pi;      // atand, LSD/baseFunc.cpp:14-16
-            int orient = 1;
-            if (ang < 0) { ang += 180; orient = -1; }
-            LsdbFaLine o;
-            o.k = g.k;
-            o.b = (g.y1 + g.y2) / 2.0 - g.k * (g.x1 + g.x2) / 2.0;
-            o.dx = lsdm_cos(ang / 180.0 * pi); o.dy = lsdm_sin(ang / 180.0 * pi);   // cosd / sind, :6-12
-            o.x1 = g.x1; o.y1 = g.y1; o.x2 = g.x2; o.y2 = g.y2;
-            const double ey = g.y2 - g.y1, ex = g.x2 - g.x1;
-            o.len = sqrt(ey * ey + ex * ex);
-            o.orient = orient; o.pad = 0;
-            outL[L] = o;
-        }
-        int run = cnt[L];
-        for (int m0 = 0; m0 < g.cnt; m0 += 32) {
-            int xx = 0, yy = 0;
-            const bool ok = m0 + lane < g.cnt && fs_sample(g, m0 + lane, W, H, xx, yy);
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const size_t o = (size_t)(run + __popc(m & ((1u << lane) - 1)));
-                outP[2 * o] = (double)xx; outP[2 * o + 1] = (double)yy;
-                if (im) im[(size_t)yy * W + xx] = 255;
-            }
-            run += __popc(m);
-        }
+        LsdbFsPiece o;
+        o.x1 = px[a] - minX; o.y1 = py[a] - minY; o.x2 = px[b] - minX; o.y2 = py[b] - minY; o.off = cnt[L]; o.pad = 0;
+        P[L] = o;
     }
 }
 
-int lsdb_launch_fscan(cudaStream_t s, int pass, int nFrames, int maxBeams, const double* ranges, const double* angles, const int* beamOff,
-                      double resol, double oriX, double oriY, int leastPoint, double threLine, double leastDistM, double pi,
-                      LsdbFsInfo* info, const int* lineOff, const int* ptOff, const long long* imOff, LsdbFaLine* lines, double* pts,
-                      uint8_t* lineIm) {
-    const size_t smem = lsdb_fscan_smem(maxBeams);
-    cudaError_t e;
-    if (pass == 0) {
-        if ((e = cudaFuncSetAttribute(lsdb_fscan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        lsdb_fscan_kernel<false><<<nFrames, FS_NT, smem, s>>>(maxBeams, ranges, angles, beamOff, resol, oriX, oriY, leastPoint, threLine,
-                                                               leastDistM, pi, info, lineOff, ptOff, imOff, lines, pts, lineIm);
-    } else {
-        if ((e = cudaFuncSetAttribute(lsdb_fscan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
-        lsdb_fscan_kernel<true><<<nFrames, FS_NT, smem, s>>>(maxBeams, ranges, angles, beamOff, resol, oriX, oriY, leastPoint, threLine,
-                                                              leastDistM, pi, info, lineOff, ptOff, imOff, lines, pts, lineIm);
+// one warp per kept line of the batch: record (:82-103, :154-174), samples and raster (:104-153)
+__global__ void __launch_bounds__(FS_LW * 32) lsdb_fscan_lines_kernel(
+    int nFrames, int nLinesTotal, const int* __restrict__ beamOff, const LsdbFsInfo* __restrict__ info,
+    const LsdbFsPiece* __restrict__ pieces, const int* __restrict__ lineOff, const int* __restrict__ ptOff,
+    const long long* __restrict__ imOff, double pi, LsdbFaLine* __restrict__ lines, double* __restrict__ pts,
+    uint8_t* __restrict__ lineIm) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * FS_LW + (threadIdx.x >> 5);
+    if (g >= nLinesTotal) return;
+    int lo = 0, hi = nFrames;                                // frame of line g: lineOff[f] <= g < lineOff[f+1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lineOff[mid] <= g) lo = mid; else hi = mid; }
+    const int f = lo, L = g - lineOff[f];
+    const LsdbFsPiece pc = pieces[beamOff[f] + 2 * f + L];
+    const FsLine ln = fs_line(pc.x1, pc.y1, pc.x2, pc.y2);
+    const int W = info[f].W, H = info[f].H;
+    {
+        double ang = 0; int orient = 1;
+        if (lane == 0) {
+            ang = lsdm_atan(ln.k) * 180.0 / pi;            // atand, LSD/baseFunc.cpp:14-16
+            if (ang < 0) { ang += 180; orient = -1; }
+        }
+        ang = __shfl_sync(0xffffffffu, ang, 0);
+        double cs = 0;
+        if (lane < 2) cs = lsdm_sincos_eval(ang / 180.0 * pi, lane == 0);   // cosd / sind, :6-12 — one code path for both lanes
+        const double sn = __shfl_sync(0xffffffffu, cs, 1);
+        if (lane == 0) {
+            LsdbFaLine o;
+            o.k = ln.k;
+            o.b = (ln.y1 + ln.y2) / 2.0 - ln.k * (ln.x1 + ln.x2) / 2.0;
+            o.dx = cs; o.dy = sn;
+            o.x1 = ln.x1; o.y1 = ln.y1; o.x2 = ln.x2; o.y2 = ln.y2;
+            const double ey = ln.y2 - ln.y1, ex = ln.x2 - ln.x1;
+            o.len = sqrt(ey * ey + ex * ex);
+            o.orient = orient; o.pad = 0;
+            lines[g] = o;
+        }
     }
+    double* outP = pts + 2 * ((size_t)ptOff[f] + (size_t)pc.off);
+    uint8_t* im = lineIm ? lineIm + imOff[f] : 0;
+    int run = 0;
+    for (int m0 = 0; m0 < ln.cnt; m0 += 32) {
+        int xx = 0, yy = 0;
+        const bool ok = m0 + lane < ln.cnt && fs_sample(ln, m0 + lane, W, H, xx, yy);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const size_t o = (size_t)(run + __popc(m & ((1u << lane) - 1)));
+            outP[2 * o] = (double)xx; outP[2 * o + 1] = (double)yy;
+            if (im) im[(size_t)yy * W + xx] = 255;
+        }
+        run += __popc(m);
+    }
+}
+
+int lsdb_launch_fscan_frames(cudaStream_t s, int nFrames, int maxBeams, const double* ranges, const double* angles, const int* beamOff,
+                             double resol, double oriX, double oriY, int leastPoint, double threLine, double leastDistM,
+                             LsdbFsInfo* info, LsdbFsPiece* pieces) {
+    const size_t smem = lsdb_fscan_smem(maxBeams);
+    cudaError_t e = cudaFuncSetAttribute(lsdb_fscan_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    lsdb_fscan_frames_kernel<<<nFrames, FS_NT, smem, s>>>(maxBeams, ranges, angles, beamOff, resol, oriX, oriY, leastPoint, threLine,
+                                                           leastDistM, info, pieces);
+    return (int)cudaGetLastError();
+}
+
+int lsdb_launch_fscan_lines(cudaStream_t s, int nFrames, int nLinesTotal, const int* beamOff, const LsdbFsInfo* info,
+                            const LsdbFsPiece* pieces, const int* lineOff, const int* ptOff, const long long* imOff, double pi,
+                            LsdbFaLine* lines, double* pts, uint8_t* lineIm) {
+    if (nLinesTotal <= 0) return 0;
+    lsdb_fscan_lines_kernel<<<(nLinesTotal + FS_LW - 1) / FS_LW, FS_LW * 32, 0, s>>>(nFrames, nLinesTotal, beamOff, info, pieces, lineOff,
+                                                                                     ptOff, imOff, pi, lines, pts, lineIm);
     return (int)cudaGetLastError();
 }

@@ -108,8 +108,11 @@ void lsdb_launch_fa_reduce(cudaStream_t s, int nFrames, const LsdbFaHyp* hyp, co
 
 // scan front-end (fscan.cu)
 struct LsdbFsInfo { int nLines, nPts, W, H; double lidarX, lidarY; };  // == lsdb_scan_info; nLines < 0: internal list overflow
+struct LsdbFsPiece { double x1, y1, x2, y2; int off, pad; };            // a kept line piece: end points, offset of its samples in the frame
 size_t lsdb_fscan_smem(int maxBeams);
-int lsdb_launch_fscan(cudaStream_t s, int pass, int nFrames, int maxBeams, const double* ranges, const double* angles, const int* beamOff,
-                      double resol, double oriX, double oriY, int leastPoint, double threLine, double leastDistM, double pi,
-                      LsdbFsInfo* info, const int* lineOff, const int* ptOff, const long long* imOff, LsdbFaLine* lines, double* pts,
-                      uint8_t* lineIm);
+int lsdb_launch_fscan_frames(cudaStream_t s, int nFrames, int maxBeams, const double* ranges, const double* angles, const int* beamOff,
+                             double resol, double oriX, double oriY, int leastPoint, double threLine, double leastDistM,
+                             LsdbFsInfo* info, LsdbFsPiece* pieces);
+int lsdb_launch_fscan_lines(cudaStream_t s, int nFrames, int nLinesTotal, const int* beamOff, const LsdbFsInfo* info,
+                            const LsdbFsPiece* pieces, const int* lineOff, const int* ptOff, const long long* imOff, double pi,
+                            LsdbFaLine* lines, double* pts, uint8_t* lineIm);
