@@ -304,20 +304,15 @@ def main():
         info_, lines_, loff_, pts_, poff_ = ctx.feature_scan(mp[2], mp[3], mp[4], frames_l, raw=True, capacity=(len(lines_), len(pts_)))
         dt_fs = time.time() - t0
         k_ms = ctx.feature_scan_last_ms()
+        gf2 = np.load(os.path.join(ROOT, "tests", "golden", "fa_frames.npz"))
+        gm2 = np.load(os.path.join(ROOT, "tests", "golden", "bundled_maps.npz"))
+        fm2 = lsdb.FaMap(ctx, ctx.map_cache(gm2["mapValue/map"], float(gm2["mapValue/param"][2])), gf2["map_lines"])
+        fm2.scan_estimate(mp[2], mp[3], mp[4], frames_l[:64])
+        fm2.scan_estimate(mp[2], mp[3], mp[4], frames_l)                                   # warm-up: staging buffers
         t0 = time.time()
-        if fa and "error" not in fa:
-            gf2 = np.load(os.path.join(ROOT, "tests", "golden", "fa_frames.npz"))
-            gm2 = np.load(os.path.join(ROOT, "tests", "golden", "bundled_maps.npz"))
-            fm2 = lsdb.FaMap(ctx, ctx.map_cache(gm2["mapValue/map"], float(gm2["mapValue/param"][2])), gf2["map_lines"])
-            lid_ = np.rint(np.stack([info_["lidar_x"], info_["lidar_y"]], 1)); last_ = np.tile(np.array([-1.0, -1.0, 0.0]), (len(frames_l), 1))
-            est_ = np.zeros(len(frames_l), lsdb.EST_DTYPE)
-            t0 = time.time()
-            ctx.check(lsdb.lib().lsdb_fa_estimate_frames(ctx.h, fm2.h, len(frames_l), lines_.ctypes.data, loff_.ctypes.data, pts_.ctypes.data,
-                                                         poff_.ctypes.data, lid_.ctypes.data, last_.ctypes.data, est_.ctypes.data), "estimate")
-            dt_est = time.time() - t0
-            fm2.close()
-        else:
-            est_, dt_est = None, None
+        _, est_ = fm2.scan_estimate(mp[2], mp[3], mp[4], frames_l)                         # sweeps in, one estimate per frame out
+        dt_est = time.time() - t0
+        fm2.close()
         sample = frames_l[:2000]
         t0 = time.time()
         cpu_nl, _ = refbind.ref_feature_scan_many(list(mp), sample) if refbind.available("glibc") else oraclebind.feature_scan_many(list(mp), sample)
@@ -327,7 +322,8 @@ def main():
               "beams": int(sum(len(r_) for r_, _ in frames_l)), "lines": int(loff_[-1]), "raster_samples": int(poff_[-1]),
               "kernel_ms_both_passes": k_ms, "frames_per_s_kernel": len(frames_l) / (k_ms * 1e-3),
               "frames_per_s_e2e": len(frames_l) / dt_fs,
-              "estimate_e2e_s": dt_est, "frames_with_match": None if est_ is None else int((est_["n_kept"] > 0).sum()),
+              "sweeps_to_estimates_per_s_e2e": len(frames_l) / dt_est, "sweeps_to_estimates_how": "lsdb_scan_estimate_frames, host buffers in/out, incl. the Python marshalling of the sweeps",
+              "frames_with_match": int((est_["n_kept"] > 0).sum()), "hypotheses_scored": int(est_["n_hyp"].sum()),
               "cpu_frames_per_s": len(sample) / dt_cpu, "cpu_kind": "reference myrdp::FeatureScan, 1 thread" if refbind.available("glibc") else "port",
               "cpu_sample": "first 2000 frames"}
     except Exception as e:

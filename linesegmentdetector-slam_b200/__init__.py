@@ -86,6 +86,7 @@ def lib():
         L.lsdb_fa_last_ms.argtypes = [vp]; L.lsdb_fa_last_ms.restype = C.c_float
         L.lsdb_feature_scan_frames.argtypes = [vp, cd, cd, cd, C.POINTER(_RdpParams), ci, vp, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp,
                                                C.c_longlong, vp]
+        L.lsdb_scan_estimate_frames.argtypes = [vp, vp, cd, cd, cd, C.POINTER(_RdpParams), ci, vp, vp, vp, vp, vp, vp]
         L.lsdb_feature_scan_last_ms.argtypes = [vp]; L.lsdb_feature_scan_last_ms.restype = C.c_float
         _lib = L
     return _lib
@@ -340,6 +341,23 @@ class FaMap:
         self.ctx.check(lib().lsdb_fa_estimate_frames(self.ctx.h, self.h, nf, _p(lines), _p(loff), _p(pts), _p(poff), _p(lid), _p(last),
                                                      _p(out)), "lsdb_fa_estimate_frames")
         return out
+
+    def scan_estimate(self, map_res, map_ori_x, map_ori_y, sweeps, last_pose=None, **rdp):
+        """lidar sweeps [(ranges, angles), ...] -> (SCAN_INFO_DTYPE, EST_DTYPE) records per frame in one call
+        (lsdb_scan_estimate_frames: FeatureScan, scoring and reduction, raster samples device-resident)."""
+        nf = len(sweeps)
+        boff = np.zeros(nf + 1, np.int32)
+        for i, (r, _a) in enumerate(sweeps):
+            boff[i + 1] = boff[i] + len(r)
+        rng = np.ascontiguousarray(np.concatenate([np.asarray(r, np.float64) for r, _ in sweeps])) if nf else np.zeros(0)
+        ang = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float64) for _, a in sweeps])) if nf else np.zeros(0)
+        d = dict(RDP_DEFAULTS); d.update(rdp)
+        prm = _RdpParams(int(d["least_point"]), float(d["thre_line"]), float(d["least_dist_m"]))
+        last = np.tile(np.array([-1.0, -1.0, 0.0]), (nf, 1)) if last_pose is None else np.ascontiguousarray(last_pose, np.float64).reshape(nf, 3)
+        info = np.zeros(nf, SCAN_INFO_DTYPE); est = np.zeros(nf, EST_DTYPE)
+        self.ctx.check(lib().lsdb_scan_estimate_frames(self.ctx.h, self.h, float(map_res), float(map_ori_x), float(map_ori_y), C.byref(prm), nf,
+                                                       _p(rng), _p(ang), _p(boff), _p(last), _p(info), _p(est)), "lsdb_scan_estimate_frames")
+        return info, est
 
     def last_ms(self):
         return float(lib().lsdb_fa_last_ms(self.ctx.h))

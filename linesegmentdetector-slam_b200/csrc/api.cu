@@ -29,7 +29,8 @@ struct lsdb_ctx {
     void* faDev; size_t faDevCap;
     void* faHost; size_t faHostCap;
     // scan front-end: ragged outputs (device + pinned mirror) and the raster plane
-    void* fsOut; void* fsOutHost; size_t fsOutCap;
+    void* fsOut; void* fsOutHost; size_t fsOutCap, fsOutHostCap;
+    void* fsLinesDev; void* fsPtsDev;   // where the last scan call left its lines / samples on the device
     void* fsIm; size_t fsImCap;
     void* fsTmp; size_t fsTmpCap;
     float fsMs;
@@ -85,7 +86,7 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
     if (prop.major != 10) return LSDB_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
     lsdb_ctx* c = new lsdb_ctx();
     c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0;
-    c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsIm = 0; c->fsImCap = 0; c->fsTmp = 0; c->fsTmpCap = 0; c->fsMs = 0;
+    c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsOutHostCap = 0; c->fsLinesDev = 0; c->fsPtsDev = 0; c->fsIm = 0; c->fsImCap = 0; c->fsTmp = 0; c->fsTmpCap = 0; c->fsMs = 0;
     c->lgammaTab = 0; c->lgammaN = 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LSDB_ERR_NO_DEVICE; }
     if (stream) { c->stream = (cudaStream_t)stream; c->ownStream = false; }
@@ -545,7 +546,8 @@ static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 // scoring of n_frames frames; hypotheses (out, may be NULL) and / or the per-frame reduction (est, may be NULL)
 static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_line* scanLines, const int* lineOff,
                   const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
-                  lsdb_hypothesis* out, int maxHyp, int* nHyp, lsdb_fa_estimate* est) {
+                  lsdb_hypothesis* out, int maxHyp, int* nHyp, lsdb_fa_estimate* est,
+                  const LsdbFaLine* devLines = 0, const double* devPts = 0) {   // set: lines / points are already on the device (scan front-end)
     if (!ctx || !m || nFrames < 0 || !lineOff || !ptOff || !nHyp || (nFrames > 0 && (!lidarPose || !lastPose)))
         return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score: bad argument%s");
     static_assert(sizeof(lsdb_hypothesis) == sizeof(LsdbFaHyp), "layout");
@@ -577,8 +579,8 @@ static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_l
     }
     if (out && nTasks * 4 > maxHyp) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_fa_score: %s%lld hypotheses exceed max_hyp", "", (long long)nTasks * 4);
     const int nL = lineOff[nFrames], nP = ptOff[nFrames];
-    const size_t oTasks = 0, oLines = oTasks + al256(sizeof(LsdbFaTask) * nTasks), oLoff = oLines + al256(sizeof(LsdbFaLine) * nL),
-                 oPts = oLoff + al256(sizeof(int) * (nFrames + 1)), oPoff = oPts + al256(16 * (size_t)nP),
+    const size_t oTasks = 0, oLines = oTasks + al256(sizeof(LsdbFaTask) * nTasks), oLoff = oLines + (devLines ? 0 : al256(sizeof(LsdbFaLine) * nL)),
+                 oPts = oLoff + al256(sizeof(int) * (nFrames + 1)), oPoff = oPts + (devPts ? 0 : al256(16 * (size_t)nP)),
                  oLid = oPoff + al256(sizeof(int) * (nFrames + 1)), oLast = oLid + al256(16 * (size_t)nFrames),
                  oHoff = oLast + al256(24 * (size_t)nFrames), oOut = oHoff + al256(sizeof(int) * (nFrames + 1)),
                  oPose = oOut + al256(sizeof(LsdbFaHyp) * (size_t)nTasks * 4), oEst = oPose + al256(lsdb_fa_pose_bytes(nTasks)),
@@ -593,9 +595,9 @@ static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_l
     }
     char* H = (char*)ctx->faHost; char* D = (char*)ctx->faDev;
     memcpy(H + oTasks, tasks.data(), sizeof(LsdbFaTask) * nTasks);
-    memcpy(H + oLines, scanLines, sizeof(LsdbFaLine) * nL);
+    if (!devLines) memcpy(H + oLines, scanLines, sizeof(LsdbFaLine) * nL);
     memcpy(H + oLoff, lineOff, sizeof(int) * (nFrames + 1));
-    memcpy(H + oPts, pts, 16 * (size_t)nP);
+    if (!devPts) memcpy(H + oPts, pts, 16 * (size_t)nP);
     memcpy(H + oPoff, ptOff, sizeof(int) * (nFrames + 1));
     memcpy(H + oLid, lidarPose, 16 * (size_t)nFrames);
     memcpy(H + oLast, lastPose, 24 * (size_t)nFrames);
@@ -603,7 +605,8 @@ static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_l
     cudaStream_t s = ctx->stream;
     CK(ctx, cudaMemcpyAsync(D, H, oOut, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaEventRecord(ctx->faEv[0], s));
-    lsdb_launch_fa(s, nTasks, (LsdbFaTask*)(D + oTasks), (LsdbFaLine*)(D + oLines), (int*)(D + oLoff), (double*)(D + oPts),
+    lsdb_launch_fa(s, nTasks, (LsdbFaTask*)(D + oTasks), devLines ? devLines : (LsdbFaLine*)(D + oLines), (int*)(D + oLoff),
+                   devPts ? devPts : (double*)(D + oPts),
                    (int*)(D + oPoff), (double*)(D + oLid), (double*)(D + oLast), m->linesD, m->cacheD, m->cols, m->rows,
                    4.0 * lsdm_atan(1.0), (LsdbFaHyp*)(D + oOut), D + oPose);
     if (est) lsdb_launch_fa_reduce(s, nFrames, (LsdbFaHyp*)(D + oOut), (int*)(D + oHoff), (LsdbFaEst*)(D + oEst));
@@ -653,10 +656,12 @@ extern "C" int lsdb_fa_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, int 
 // ---- scan front-end ----
 extern "C" float lsdb_feature_scan_last_ms(const lsdb_ctx* ctx) { return ctx ? ctx->fsMs : 0.f; }
 
-extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX, double oriY, const lsdb_rdp_params* prm, int nFrames,
-                                        const double* ranges, const double* angles, const int* beamOff, lsdb_scan_info* info,
-                                        lsdb_line* lines, int maxLines, int* lineOff, double* pts, int maxPts, int* ptOff,
-                                        uint8_t* lineIm, long long lineImCap, long long* imOff) {
+// keepOnDevice != NULL: the chained mode of lsdb_scan_estimate_frames — the line records come back in *keepOnDevice (the pair
+// filter of the association runs on the host), the raster samples stay in ctx->fsOut (ctx->fsLinesDev / fsPtsDev)
+static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const lsdb_rdp_params* prm, int nFrames,
+                  const double* ranges, const double* angles, const int* beamOff, lsdb_scan_info* info,
+                  lsdb_line* lines, int maxLines, int* lineOff, double* pts, int maxPts, int* ptOff,
+                  uint8_t* lineIm, long long lineImCap, long long* imOff, std::vector<lsdb_line>* keepOnDevice) {
     static_assert(sizeof(lsdb_scan_info) == sizeof(LsdbFsInfo), "layout");
     if (!ctx) return LSDB_ERR_ARG;
     if (!prm || nFrames < 0 || !beamOff || !info || !lineOff || !ptOff || (lineIm && !imOff) || (!lines) != (!pts) ||
@@ -724,18 +729,24 @@ extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX
         lineOff[f + 1] = (int)nL; ptOff[f + 1] = (int)nP; io[f + 1] = nI;
         if (imOff) imOff[f + 1] = nI;
     }
-    if (!lines) return LSDB_OK;   // sizing query
+    if (!lines && !keepOnDevice) return LSDB_OK;   // sizing query
+    if (keepOnDevice) { keepOnDevice->resize((size_t)nL); lines = keepOnDevice->data(); maxLines = (int)nL; maxPts = (int)nP; }
     if (nL > maxLines) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: %s%lld lines exceed max_lines", "", nL);
     if (nP > maxPts) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: %s%lld raster samples exceed max_pts", "", nP);
     if (lineIm && nI > lineImCap) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: rasters need %s%lld bytes", "", nI);
     const size_t oL = 0, oP = oL + al256(sizeof(LsdbFaLine) * (size_t)nL), outTotal = oP + al256(16 * (size_t)nP);
     if (outTotal > ctx->fsOutCap) {
         if (ctx->fsOut) cudaFree(ctx->fsOut);
-        if (ctx->fsOutHost) cudaFreeHost(ctx->fsOutHost);
-        ctx->fsOut = 0; ctx->fsOutHost = 0; ctx->fsOutCap = 0;
+        ctx->fsOut = 0; ctx->fsOutCap = 0;
         CK(ctx, cudaMalloc(&ctx->fsOut, outTotal + outTotal / 4));
-        CK(ctx, cudaMallocHost(&ctx->fsOutHost, outTotal + outTotal / 4));
         ctx->fsOutCap = outTotal + outTotal / 4;
+    }
+    const size_t hostBytes = keepOnDevice ? oP : outTotal;     // pinned mirror of what travels back
+    if (hostBytes > ctx->fsOutHostCap) {
+        if (ctx->fsOutHost) cudaFreeHost(ctx->fsOutHost);
+        ctx->fsOutHost = 0; ctx->fsOutHostCap = 0;
+        CK(ctx, cudaMallocHost(&ctx->fsOutHost, hostBytes + hostBytes / 4 + 256));
+        ctx->fsOutHostCap = hostBytes + hostBytes / 4 + 256;
     }
     if (lineIm && (size_t)nI > ctx->fsImCap) {
         if (ctx->fsIm) cudaFree(ctx->fsIm);
@@ -754,12 +765,44 @@ extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX
                                                  (int*)(D + oLoff), (int*)(D + oPoff), (long long*)(D + oIoff), pi, (LsdbFaLine*)(O + oL),
                                                  (double*)(O + oP), lineIm ? (uint8_t*)ctx->fsIm : 0));
     CK(ctx, cudaEventRecord(ctx->faEv[1], s));
-    CK(ctx, cudaMemcpyAsync(OH, O, outTotal, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(OH, O, hostBytes, cudaMemcpyDeviceToHost, s));
     if (lineIm && nI > 0) CK(ctx, cudaMemcpyAsync(lineIm, ctx->fsIm, (size_t)nI, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ms0, ctx->faEv[0], ctx->faEv[1]));
     ctx->fsMs += ms0;
     memcpy(lines, OH + oL, sizeof(LsdbFaLine) * (size_t)nL);
-    memcpy(pts, OH + oP, 16 * (size_t)nP);
+    if (!keepOnDevice) memcpy(pts, OH + oP, 16 * (size_t)nP);
+    ctx->fsLinesDev = O + oL; ctx->fsPtsDev = O + oP;
     return LSDB_OK;
+}
+
+extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX, double oriY, const lsdb_rdp_params* prm, int nFrames,
+                                        const double* ranges, const double* angles, const int* beamOff, lsdb_scan_info* info,
+                                        lsdb_line* lines, int maxLines, int* lineOff, double* pts, int maxPts, int* ptOff,
+                                        uint8_t* lineIm, long long lineImCap, long long* imOff) {
+    return fs_run(ctx, resol, oriX, oriY, prm, nFrames, ranges, angles, beamOff, info, lines, maxLines, lineOff, pts, maxPts, ptOff, lineIm,
+                  lineImCap, imOff, 0);
+}
+
+// lidar sweeps in, one estimate per frame out: FeatureScan -> (pair filter on the host, from the line lengths) -> scoring ->
+// reduction, with the raster samples (the bulk of the data) never leaving the device
+extern "C" int lsdb_scan_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, double resol, double oriX, double oriY,
+                                         const lsdb_rdp_params* prm, int nFrames, const double* ranges, const double* angles,
+                                         const int* beamOff, const double* lastPose, lsdb_scan_info* info, lsdb_fa_estimate* est) {
+    if (!ctx) return LSDB_ERR_ARG;
+    if (!m || !est || !info || nFrames < 0 || (nFrames > 0 && !lastPose)) return fail(ctx, LSDB_ERR_ARG, "lsdb_scan_estimate_frames: bad argument%s");
+    std::vector<int> lineOff((size_t)nFrames + 1, 0), ptOff((size_t)nFrames + 1, 0);
+    std::vector<lsdb_line> lines;
+    const int rc = fs_run(ctx, resol, oriX, oriY, prm, nFrames, ranges, angles, beamOff, info, 0, 0, lineOff.data(), 0, 0, ptOff.data(), 0, 0, 0, &lines);
+    if (rc != LSDB_OK || nFrames == 0) return rc;
+    const float fsMs = ctx->fsMs;
+    std::vector<double> lidar(2 * (size_t)nFrames);
+    for (int f = 0; f < nFrames; f++) {                       // (int)round(FS.lidarPos), LSD/main_on_windows.cpp:229-230
+        lidar[2 * (size_t)f] = (double)x86_d2i(round(info[f].lidar_x)); lidar[2 * (size_t)f + 1] = (double)x86_d2i(round(info[f].lidar_y));
+    }
+    int nHyp = 0;
+    const int rc2 = fa_run(ctx, m, nFrames, lines.data(), lineOff.data(), 0, ptOff.data(), lidar.data(), lastPose, 0, 0, &nHyp, est,
+                           (const LsdbFaLine*)ctx->fsLinesDev, (const double*)ctx->fsPtsDev);
+    ctx->fsMs = fsMs;
+    return rc2;
 }

@@ -128,4 +128,16 @@ def test_scan_to_estimate_chain(lsdb, ctx):
                             last_pose=ga[f"f{f}/last_pose"]) for f in range(nf)])
     assert mine.tobytes() == ref.tobytes()
     assert int((mine["n_kept"] > 0).sum()) >= 6
+    # the same in ONE call with the raster samples resident on the device; gated frames included
+    sweeps = [_finite(g[f"f{f}/ranges"], g[f"f{f}/angles"]) for f in range(nf)]
+    last = np.stack([ga[f"f{f}/last_pose"] for f in range(nf)])
+    info, est = fm.scan_estimate(mp[2], mp[3], mp[4], sweeps, last_pose=last)
+    assert est.tobytes() == ref.tobytes()
+    assert np.array_equal(info["n_lines"], [len(o["lines"]) for o in out]) and np.array_equal(info["n_pts"], [len(o["pts"]) for o in out])
+    # frames without any line (a circle) and a large batch
+    many = sweeps * 40 + [(np.full(360, 3.0), -3.12414 + np.arange(360) * 0.0174532)]
+    info2, est2 = fm.scan_estimate(mp[2], mp[3], mp[4], many)
+    one = fm.estimate([dict(scan_lines=o["lines"], pts=o["pts"], lidar_pose=np.rint(o["lidar_pos"]), last_pose=[-1.0, -1.0, 0.0]) for o in out])
+    assert est2[:-1].tobytes() == np.tile(one, 40).tobytes()
+    assert info2[-1]["n_lines"] == 0 and est2[-1]["n_kept"] == 0
     fm.close()
