@@ -136,8 +136,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--maps-per-gpu", type=int, default=256)
     ap.add_argument("--size", type=int, default=4096)
@@ -227,6 +227,8 @@ def main():
     # ---------------- config 1 latency: the reference's own single-map run (data/mapValue.txt, 1377x428), one map per call
     lat = None
     try:
+        if rank != 0:
+            raise RuntimeError("side measurements run on rank 0 only")
         g = np.load(os.path.join(ROOT, "tests", "golden", "bundled_maps.npz"))
         m1 = np.ascontiguousarray(g["mapValue/map"])
         b1 = lsdb.Batch(ctx, [(m1.shape[1], m1.shape[0])])
@@ -248,6 +250,8 @@ def main():
     # ---------------- association (BASELINE configs[3] shape): 10k scan frames scored against LSD(data/mapValue.txt) in ONE launch
     fa = None
     try:
+        if rank != 0:
+            raise RuntimeError("side measurements run on rank 0 only")
         import oraclebind
         gf = np.load(os.path.join(ROOT, "tests", "golden", "fa_frames.npz"))
         gmaps = np.load(os.path.join(ROOT, "tests", "golden", "bundled_maps.npz"))
@@ -284,6 +288,8 @@ def main():
     # device association reduction on its output (lidar beams in, one pose estimate per frame out)
     fs = None
     try:
+        if rank != 0:
+            raise RuntimeError("side measurements run on rank 0 only")
         import oraclebind
         import refbind
         gl = np.load(os.path.join(ROOT, "tests", "golden", "lidar_frames.npz"))

@@ -247,7 +247,8 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         b->runAhead = 0;   // chunks a map's team may speculate ahead of its commit frontier (0 = as far as the ring allows)
         if (getenv("LSDB_RUNAHEAD")) b->runAhead = atoi(getenv("LSDB_RUNAHEAD"));
         b->steal = 0;   // measured: spreading large seeds over the team duplicates growth of neighbouring seeds; no net gain
-        if (getenv("LSDB_STEAL")) b->steal = atoi(getenv("LSDB_STEAL"));
+        if (getenv("LSDB_STEAL")) b->steal = atoi(getenv("LSDB_STEAL")) & 0xff;
+        if (getenv("LSDB_SUPER_SHIFT")) b->steal |= ((atoi(getenv("LSDB_SUPER_SHIFT")) & 3) + 1) << 8;   // chunks per claim = 1 << n (default: per map)
         const int maxCtas = lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords);
         b->nCtas = n < maxCtas ? n : maxCtas;
         (void)sms;

@@ -58,6 +58,8 @@ enum { ST_CELLS = 0, ST_LIVE, ST_GROWS, ST_GROWNPX, ST_SMALL, ST_REGROWS, ST_RRR
 struct GrowShared {
     volatile int frontier;     // first chunk not yet retired
     int nextChunk;             // ticket counter
+    int runAhead;              // chunks the claims may lead the commit frontier (per map: depends on supShift)
+    int supShift;              // a claim covers 1 << supShift chunks (<= LSDB_SUPER): fewer per claim spreads a short seed list over the team
     int retireLock;
     volatile int nSeg;
     volatile int abortFlag;
@@ -1158,7 +1160,7 @@ __device__ __forceinline__ int aborted(const WarpCtx& c) {
 }
 
 // record arena of the super-chunk that holds chunk `chunk`
-__device__ __forceinline__ int slot_of_chunk(int chunk) { return (chunk / LSDB_SUPER) & (NSLOTS - 1); }
+__device__ __forceinline__ int slot_of_chunk(const GrowShared& sh, int chunk) { return (chunk >> sh.supShift) & (NSLOTS - 1); }
 
 // One large seed (cell ci, pixel p), speculatively, with the whole warp: grow, rectangle, refine, NFA; the result is
 // parked in the record arena of the seed's super-chunk.  Any warp of the team may run this for any queued seed.
@@ -1178,7 +1180,7 @@ __device__ void eval_large(WarpCtx& c, int p, int ci, const ChunkRecs& R) {
     c.specChunk = -1;
     STAT(c, ST_SPEC, 1);
     if (oc == OC_DEFER) return;
-    const int slot = slot_of_chunk(chunkJ);
+    const int slot = slot_of_chunk(sh, chunkJ);
     const int off = slot_alloc(c, slot, used);
     if (off < 0) {   // arena full: decided at the frontier; take the marks back
         if (oc == OC_ACCEPT || oc == OC_REJECT) unpark_pixels(c, c.scratch + c.scratch[28], (int)c.scratch[26], chunkJ);
@@ -1218,7 +1220,7 @@ __device__ bool help_large(WarpCtx& c, const ChunkRecs& R) {
     p = __shfl_sync(FULL, p, 0); ci = __shfl_sync(FULL, ci, 0);
     eval_large(c, (int)p, (int)ci, R);
     __threadfence();   // record visible before the super-chunk can be flagged ready
-    if (c.lane == 0) atomicSub((int*)&sh.slotPending[slot_of_chunk((int)ci >> 5)], 1);
+    if (c.lane == 0) atomicSub((int*)&sh.slotPending[slot_of_chunk(sh, (int)ci >> 5)], 1);
     __syncwarp();
     return true;
 }
@@ -1236,7 +1238,7 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
     const int lane = c.lane;
     const unsigned int lt = (1u << lane) - 1u;
     long long tSpec = clock64();
-    const int slot = slot_of_chunk(chunk0);
+    const int slot = slot_of_chunk(*c.sh, chunk0);
     unsigned int* q = c.q;   // [2k] pixel index, [2k+1] (sub << 5 | lane)
     int qn = 0;
     for (int s = 0; s < nSub; s++) {   // ---- A
@@ -1386,7 +1388,7 @@ __device__ void retire_chunk(WarpCtx& c, int chunk, const unsigned int* cl, int 
     const int recPnd = recOc != OC_NONE ? R.pnd[ri] : 0;
     const unsigned int recPndOff = R.pndOff[ri];
     bool committedParked = false;   // this lane's parked accept / reject was committed as parked
-    const unsigned int* earena = c.arenas + (size_t)slot_of_chunk(chunk) * c.arenaCap;
+    const unsigned int* earena = c.arenas + (size_t)slot_of_chunk(*c.sh, chunk) * c.arenaCap;
     bool live = myp >= 0 && (lsdb_ld_state(&c.state[myp]) & 3u) == 0;   // :222
     // short "no change" records are validated by their own lane, in parallel; commits, long records, failed and
     // missing evaluations are walked serially, in seed order
@@ -1485,7 +1487,7 @@ __device__ bool revalidate_ahead(WarpCtx& c, const unsigned int* cl, int nCells,
     const int recOc = R.oc[ri], recChk = R.chk[ri], recL0 = R.L0[ri];
     const unsigned int recB0 = R.b0[ri], recB1 = R.b1[ri], recOff = R.off[ri], recChkOff = R.chkOff[ri];
     const int recPnd = recOc != OC_NONE ? R.pnd[ri] : 0;
-    const unsigned int* earena = c.arenas + (size_t)slot_of_chunk(target) * c.arenaCap;
+    const unsigned int* earena = c.arenas + (size_t)slot_of_chunk(*c.sh, target) * c.arenaCap;
     const bool heavy = myp >= 0 && (recOc == OC_ACCEPT || recOc == OC_REJECT || (recOc == OC_NOCHANGE && !(recChk >= 0 && recChk + recPnd <= 64)));
     unsigned int todo = __ballot_sync(FULL, heavy && (lsdb_ld_state(&c.state[myp]) & 3u) == 0 && grid_hit(c, recB0, recB1, recL0));
     bool did = false;
@@ -1574,7 +1576,7 @@ __global__ void __launch_bounds__(MAXT, 1) lsdb_grow_kernel(int nImgs, const Lsd
     c.rej[1] = c.rej[0] + LSDB_REJ_CAP;
     c.pnd = c.rej[1] + LSDB_REJ_CAP; c.npnd = 0; c.specChunk = -1;
     c.q = c.pnd + LSDB_PND_CAP;
-    c.steal = steal;
+    c.steal = steal & 0xff;
     c.stage = reinterpret_cast<double*>(bmShared + ((bmCapWords + 1) & ~1)) + (size_t)w * 128;
     ChunkRecs R;
     {
@@ -1595,6 +1597,14 @@ __global__ void __launch_bounds__(MAXT, 1) lsdb_grow_kernel(int nImgs, const Lsd
                 sh.frontier = 0; sh.nextChunk = 0; sh.nSeg = 0; sh.abortFlag = 0; sh.retireLock = 0;
                 sh.nCells = dyn[img].nCells;
                 sh.nChunks = (sh.nCells + LSDB_CHUNK - 1) / LSDB_CHUNK;
+                // chunks per claim: LSDB_SUPER for long seed lists; a short list (a small map alone on the device) is cut
+                // finer so that every warp of the team gets several claims
+                int shift = 3;
+                static_assert(LSDB_SUPER == 8, "supShift starts at log2(LSDB_SUPER)");
+                if ((steal >> 8) & 15) shift = ((steal >> 8) & 15) - 1;
+                else while (shift > 0 && (sh.nChunks >> shift) < 6 * (int)(blockDim.x >> 5)) shift--;   // measured on the bundled maps
+                sh.supShift = shift;
+                sh.runAhead = min(runAhead, (NSLOTS - (int)(blockDim.x >> 5) - 1) << shift);   // a slot is not reused while its claim is in flight
             }
         }
         if (tid < TM_N) sh.stats[tid] = 0;
@@ -1641,10 +1651,10 @@ __global__ void __launch_bounds__(MAXT, 1) lsdb_grow_kernel(int nImgs, const Lsd
             int chunk = -1;
             if (lane == 0) {
                 // claim a ticket only while the ring has room
-                if (sh.nextChunk < nChunks && sh.nextChunk - sh.frontier < runAhead) {
-                    chunk = atomicAdd(&sh.nextChunk, LSDB_SUPER);
+                if (sh.nextChunk < nChunks && sh.nextChunk - sh.frontier < sh.runAhead) {
+                    chunk = atomicAdd(&sh.nextChunk, 1 << sh.supShift);
                     if (chunk >= nChunks) chunk = -1;
-                    else { sh.slotHead[slot_of_chunk(chunk)] = 0; sh.slotPending[slot_of_chunk(chunk)] = 0; }   // the slot's previous
+                    else { sh.slotHead[slot_of_chunk(sh, chunk)] = 0; sh.slotPending[slot_of_chunk(sh, chunk)] = 0; }   // the slot's previous
                 }                                                                                              // super-chunk has retired
             }
             chunk = __shfl_sync(FULL, chunk, 0);
@@ -1661,7 +1671,7 @@ __global__ void __launch_bounds__(MAXT, 1) lsdb_grow_kernel(int nImgs, const Lsd
                 continue;
             }
             idle = 0;
-            speculate_super(c, chunk, min(LSDB_SUPER, nChunks - chunk), cl, nCells, R, T);
+            speculate_super(c, chunk, min(1 << sh.supShift, nChunks - chunk), cl, nCells, R, T);
         }
         __syncthreads();
         if (tid == 0) {

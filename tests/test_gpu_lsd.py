@@ -174,7 +174,7 @@ def test_scan_rasters_batched_then_associated(lsdb, ctx):
 
 @pytest.mark.parametrize("env", [dict(LSDB_GROW_WARPS="1"), dict(LSDB_GROW_WARPS="3"), dict(LSDB_GROW_WARPS="8", LSDB_STEAL="1"),
                                  dict(LSDB_GROW_WARPS="16", LSDB_RUNAHEAD="16"), dict(LSDB_NO_SMEM_BAN="1"),
-                                 dict(LSDB_SMEM_BAN_KB="200", LSDB_GROW_WARPS="16"), dict(LSDB_GROW_WIDE="0"), dict(LSDB_GROW_WIDE="1", LSDB_GROW_WARPS="8")])
+                                 dict(LSDB_SMEM_BAN_KB="200", LSDB_GROW_WARPS="16"), dict(LSDB_GROW_WIDE="0"), dict(LSDB_GROW_WIDE="1", LSDB_GROW_WARPS="8"), dict(LSDB_SUPER_SHIFT="0"), dict(LSDB_SUPER_SHIFT="3", LSDB_GROW_WARPS="16")])
 def test_result_is_independent_of_team_shape(lsdb, ctx, gold, env):
     """The ordered-commit pipeline must give the sequential result whatever the speculation looks like: team size,
     run-ahead window, team-wide queue for large seeds, ban plane in shared memory or not."""

@@ -9,7 +9,7 @@ lsdb = load_package(); ctx = lsdb.Context(0)
 g = np.load(os.path.join(ROOT, "tests", "golden", "bundled_maps.npz"))
 for name in ("mapValue", "mapValue_aisle2", "mapValue_map1"):
     m = g[name + "/map"]
-    for env in [dict(), dict(LSDB_RUNAHEAD="16"), dict(LSDB_RUNAHEAD="32"), dict(LSDB_RUNAHEAD="64"), dict(LSDB_GROW_WARPS="8"), dict(LSDB_GROW_WARPS="8", LSDB_RUNAHEAD="32"), dict(LSDB_GROW_WARPS="4", LSDB_RUNAHEAD="32"), dict(LSDB_NO_SMEM_BAN="1")]:
+    for env in [dict(), dict(LSDB_SUPER_SHIFT="3"), dict(LSDB_SUPER_SHIFT="2"), dict(LSDB_SUPER_SHIFT="1"), dict(LSDB_SUPER_SHIFT="0"), dict(LSDB_SUPER_SHIFT="1", LSDB_GROW_WARPS="16"), dict(LSDB_SUPER_SHIFT="0", LSDB_GROW_WARPS="16")]:
         os.environ.update(env)
         b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0])]); b.upload([m])
         for k in list(env): os.environ.pop(k)
