@@ -194,8 +194,8 @@ int lsdb_feature_scan_frames(lsdb_ctx* ctx, double map_resol, double map_ori_x, 
                              long long* im_off);
 /* The whole scan side of one localisation step for n_frames sweeps: FeatureScan, then the scoring and reduction of
  * lsdb_fa_estimate_frames against map `m`, with lidar_pose = (int)round(FS.lidarPos) as LSD/main_on_windows.cpp:229-230
- * builds it.  Same results as lsdb_feature_scan_frames followed by lsdb_fa_estimate_frames, but the raster samples never
- * leave the device (only the line records come back for the length filter of LSD/myFA.cpp:29-41).
+ * builds it.  Same results as lsdb_feature_scan_frames followed by lsdb_fa_estimate_frames, but scan lines and raster samples
+ * never leave the device (the length filter of LSD/myFA.cpp:29-41 runs there as well).
  *   last_pose [n_frames][3], info [n_frames] out, est [n_frames] out. */
 int lsdb_scan_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, double map_resol, double map_ori_x, double map_ori_y,
                               const lsdb_rdp_params* prm, int n_frames, const double* ranges, const double* angles,

@@ -28,6 +28,7 @@ struct lsdb_ctx {
     // FA staging buffers (grown on demand)
     void* faDev; size_t faDevCap;
     void* faHost; size_t faHostCap;
+    void* faAux; void* faAuxHost; size_t faAuxCap;   // small staging of the device-resident association path
     // scan front-end: ragged outputs (device + pinned mirror) and the raster plane
     void* fsOut; void* fsOutHost; size_t fsOutCap, fsOutHostCap;
     void* fsLinesDev; void* fsPtsDev;   // where the last scan call left its lines / samples on the device
@@ -85,7 +86,7 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LSDB_ERR_NO_DEVICE;
     if (prop.major != 10) return LSDB_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
     lsdb_ctx* c = new lsdb_ctx();
-    c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0;
+    c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0; c->faAux = 0; c->faAuxHost = 0; c->faAuxCap = 0;
     c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsOutHostCap = 0; c->fsLinesDev = 0; c->fsPtsDev = 0; c->fsIm = 0; c->fsImCap = 0; c->fsTmp = 0; c->fsTmpCap = 0; c->fsMs = 0;
     c->lgammaTab = 0; c->lgammaN = 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LSDB_ERR_NO_DEVICE; }
@@ -111,6 +112,8 @@ extern "C" void lsdb_destroy(lsdb_ctx* c) {
     cudaFree(c->lgammaTab);
     if (c->faDev) cudaFree(c->faDev);
     if (c->faHost) cudaFreeHost(c->faHost);
+    if (c->faAux) cudaFree(c->faAux);
+    if (c->faAuxHost) cudaFreeHost(c->faAuxHost);
     if (c->fsOut) cudaFree(c->fsOut);
     if (c->fsOutHost) cudaFreeHost(c->fsOutHost);
     if (c->fsIm) cudaFree(c->fsIm);
@@ -544,6 +547,18 @@ extern "C" float lsdb_fa_last_ms(const lsdb_ctx* ctx) { return ctx ? ctx->faMs :
 
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// the reduction of LSD/myFA.cpp:65-171 on the host, for frames that keep more hypotheses than the device sort holds
+static void host_reduce(const std::vector<LsdbFaHyp>& hv, lsdb_fa_estimate& E) {
+    std::vector<LsdbFaHyp> kept;
+    for (size_t k = 0; k < hv.size(); k++) if (hv[k].score < 3) kept.push_back(hv[k]);
+    std::stable_sort(kept.begin(), kept.end(), [](const LsdbFaHyp& a, const LsdbFaHyp& b) { return a.score < b.score; });
+    E.n_kept = (int)kept.size();
+    E.best_x = kept[0].x; E.best_y = kept[0].y; E.best_ang = kept[0].ang; E.best_score = kept[0].score;
+    double sx = 0, sy = 0, sa = 0, sw = 0;
+    for (size_t k = 0; k < kept.size(); k++) { const double w = 1 / (kept[k].score * kept[k].score); sx += kept[k].x * w; sy += kept[k].y * w; sa += kept[k].ang * w; sw += w; }
+    E.mean_x = sx / sw; E.mean_y = sy / sw; E.mean_ang = sa / sw; E.mean_score = 1 / sqrt(sw / E.n_kept);
+}
+
 // scoring of n_frames frames; hypotheses (out, may be NULL) and / or the per-frame reduction (est, may be NULL)
 static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_line* scanLines, const int* lineOff,
                   const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose,
@@ -586,10 +601,10 @@ static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_l
                  oHoff = oLast + al256(24 * (size_t)nFrames), oOut = oHoff + al256(sizeof(int) * (nFrames + 1)),
                  oPose = oOut + al256(sizeof(LsdbFaHyp) * (size_t)nTasks * 4), oEst = oPose + al256(lsdb_fa_pose_bytes(nTasks)),
                  total = oEst + al256(sizeof(LsdbFaEst) * (size_t)nFrames);
-    if (total > ctx->faDevCap) {
+    if (total > ctx->faDevCap || total > ctx->faHostCap) {   // the device-resident path grows the device side alone
         if (ctx->faDev) cudaFree(ctx->faDev);
         if (ctx->faHost) cudaFreeHost(ctx->faHost);
-        ctx->faDev = 0; ctx->faHost = 0; ctx->faDevCap = 0;
+        ctx->faDev = 0; ctx->faHost = 0; ctx->faDevCap = 0; ctx->faHostCap = 0;
         CK(ctx, cudaMalloc(&ctx->faDev, total + total / 4));
         CK(ctx, cudaMallocHost(&ctx->faHost, total + total / 4));
         ctx->faDevCap = ctx->faHostCap = total + total / 4;
@@ -625,15 +640,7 @@ static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_l
             // more kept hypotheses than the device sort holds: same reduction on the host, from the device's scores
             std::vector<LsdbFaHyp> hv((size_t)(hypOff[f + 1] - hypOff[f]));
             CK(ctx, cudaMemcpy(hv.data(), D + oOut + sizeof(LsdbFaHyp) * (size_t)hypOff[f], sizeof(LsdbFaHyp) * hv.size(), cudaMemcpyDeviceToHost));
-            std::vector<LsdbFaHyp> kept;
-            for (size_t k = 0; k < hv.size(); k++) if (hv[k].score < 3) kept.push_back(hv[k]);
-            std::stable_sort(kept.begin(), kept.end(), [](const LsdbFaHyp& a, const LsdbFaHyp& b) { return a.score < b.score; });
-            lsdb_fa_estimate& E = est[f];
-            E.n_kept = (int)kept.size();
-            E.best_x = kept[0].x; E.best_y = kept[0].y; E.best_ang = kept[0].ang; E.best_score = kept[0].score;
-            double sx = 0, sy = 0, sa = 0, sw = 0;
-            for (size_t k = 0; k < kept.size(); k++) { const double w = 1 / (kept[k].score * kept[k].score); sx += kept[k].x * w; sy += kept[k].y * w; sa += kept[k].ang * w; sw += w; }
-            E.mean_x = sx / sw; E.mean_y = sy / sw; E.mean_ang = sa / sw; E.mean_score = 1 / sqrt(sw / E.n_kept);
+            host_reduce(hv, est[f]);
         }
     }
     return LSDB_OK;
@@ -654,15 +661,87 @@ extern "C" int lsdb_fa_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, int 
     return fa_run(ctx, m, nFrames, scanLines, lineOff, pts, ptOff, lidarPose, lastPose, 0, 0, &nHyp, out);
 }
 
+// The same reduction for scan lines / raster samples that are already on the device (output of the scan front-end): the pair
+// filter runs there too (count, prefix sum, write), so only the offsets, lidar / last poses go up and the estimates come back.
+static int fa_run_dev(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const int* lineOff, const int* ptOff, const double* lidarPose,
+                      const double* lastPose, lsdb_fa_estimate* est, const LsdbFaLine* devLines, const double* devPts) {
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int nL = lineOff[nFrames];
+    cudaStream_t s = ctx->stream;
+    // small staging (sizes known up front): offsets, poses, the pair-filter scratch, hypothesis offsets, estimates
+    const size_t oLoff = 0, oPoff = oLoff + al256(4 * (size_t)(nFrames + 1)), oLid = oPoff + al256(4 * (size_t)(nFrames + 1)),
+                 oLast = oLid + al256(16 * (size_t)nFrames), oScr = oLast + al256(24 * (size_t)nFrames),
+                 oHoff = oScr + al256(4 * lsdb_fa_pairs_scratch_ints(nL)), oEst = oHoff + al256(4 * (size_t)(nFrames + 1)),
+                 auxTotal = oEst + al256(sizeof(LsdbFaEst) * (size_t)nFrames);
+    if (auxTotal > ctx->faAuxCap) {
+        if (ctx->faAux) cudaFree(ctx->faAux);
+        if (ctx->faAuxHost) cudaFreeHost(ctx->faAuxHost);
+        ctx->faAux = 0; ctx->faAuxHost = 0; ctx->faAuxCap = 0;
+        CK(ctx, cudaMalloc(&ctx->faAux, auxTotal + auxTotal / 4));
+        CK(ctx, cudaMallocHost(&ctx->faAuxHost, auxTotal + auxTotal / 4));
+        ctx->faAuxCap = auxTotal + auxTotal / 4;
+    }
+    char* A = (char*)ctx->faAux; char* AH = (char*)ctx->faAuxHost;
+    memcpy(AH + oLoff, lineOff, 4 * (size_t)(nFrames + 1));
+    memcpy(AH + oPoff, ptOff, 4 * (size_t)(nFrames + 1));
+    memcpy(AH + oLid, lidarPose, 16 * (size_t)nFrames);
+    memcpy(AH + oLast, lastPose, 24 * (size_t)nFrames);
+    CK(ctx, cudaMemcpyAsync(A, AH, oScr, cudaMemcpyHostToDevice, s));
+    int nTasks = 0;
+    if (nL > 0) {
+        int* scr = (int*)(A + oScr);
+        lsdb_launch_fa_pairs_count(s, nL, devLines, m->linesD, m->nLines, scr);
+        CK(ctx, cudaMemcpyAsync(&nTasks, scr + nL, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaStreamSynchronize(s));
+    }
+    if (nTasks == 0) {
+        for (int f = 0; f < nFrames; f++) { memset(&est[f], 0, sizeof est[f]); est[f].best_score = est[f].mean_score = INFINITY; }
+        return LSDB_OK;
+    }
+    if ((long long)nTasks * 4 > INT_MAX) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_scan_estimate_frames: %s%lld tasks exceed 2^31 hypotheses", "", nTasks);
+    // large staging (needs the task count): tasks, hypotheses, pose scratch
+    const size_t oTasks = 0, oOut = oTasks + al256(sizeof(LsdbFaTask) * (size_t)nTasks), oPose = oOut + al256(sizeof(LsdbFaHyp) * (size_t)nTasks * 4),
+                 total = oPose + al256(lsdb_fa_pose_bytes(nTasks));
+    if (total > ctx->faDevCap) {
+        if (ctx->faDev) cudaFree(ctx->faDev);
+        if (ctx->faHost) cudaFreeHost(ctx->faHost);
+        ctx->faDev = 0; ctx->faHost = 0; ctx->faDevCap = 0; ctx->faHostCap = 0;   // nothing is staged through the host mirror here
+        CK(ctx, cudaMalloc(&ctx->faDev, total + total / 4));
+        ctx->faDevCap = total + total / 4;
+    }
+    char* D = (char*)ctx->faDev;
+    CK(ctx, cudaEventRecord(ctx->faEv[0], s));
+    lsdb_launch_fa_pairs_write(s, nL, nFrames, devLines, (int*)(A + oLoff), m->linesD, m->nLines, (int*)(A + oScr), (LsdbFaTask*)(D + oTasks),
+                               (int*)(A + oHoff));
+    lsdb_launch_fa(s, nTasks, (LsdbFaTask*)(D + oTasks), devLines, (int*)(A + oLoff), devPts, (int*)(A + oPoff), (double*)(A + oLid),
+                   (double*)(A + oLast), m->linesD, m->cacheD, m->cols, m->rows, 4.0 * lsdm_atan(1.0), (LsdbFaHyp*)(D + oOut), D + oPose);
+    lsdb_launch_fa_reduce(s, nFrames, (LsdbFaHyp*)(D + oOut), (int*)(A + oHoff), (LsdbFaEst*)(A + oEst));
+    CK(ctx, cudaEventRecord(ctx->faEv[1], s));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(AH + oHoff, A + oHoff, auxTotal - oHoff, cudaMemcpyDeviceToHost, s));   // hypothesis offsets + estimates
+    CK(ctx, cudaStreamSynchronize(s));
+    CK(ctx, cudaEventElapsedTime(&ctx->faMs, ctx->faEv[0], ctx->faEv[1]));
+    memcpy(est, AH + oEst, sizeof(LsdbFaEst) * (size_t)nFrames);
+    const int* hypOff = (const int*)(AH + oHoff);
+    for (int f = 0; f < nFrames; f++) {
+        if (est[f].n_kept >= 0) continue;
+        // more kept hypotheses than the device sort holds: same reduction on the host, from the device's scores
+        std::vector<LsdbFaHyp> hv((size_t)(hypOff[f + 1] - hypOff[f]));
+        CK(ctx, cudaMemcpy(hv.data(), D + oOut + sizeof(LsdbFaHyp) * (size_t)hypOff[f], sizeof(LsdbFaHyp) * hv.size(), cudaMemcpyDeviceToHost));
+        host_reduce(hv, est[f]);
+    }
+    return LSDB_OK;
+}
+
 // ---- scan front-end ----
 extern "C" float lsdb_feature_scan_last_ms(const lsdb_ctx* ctx) { return ctx ? ctx->fsMs : 0.f; }
 
-// keepOnDevice != NULL: the chained mode of lsdb_scan_estimate_frames — the line records come back in *keepOnDevice (the pair
-// filter of the association runs on the host), the raster samples stay in ctx->fsOut (ctx->fsLinesDev / fsPtsDev)
+// keepOnDevice: the chained mode of lsdb_scan_estimate_frames — line records and raster samples stay in ctx->fsOut
+// (ctx->fsLinesDev / fsPtsDev); only info and the offsets come back
 static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const lsdb_rdp_params* prm, int nFrames,
                   const double* ranges, const double* angles, const int* beamOff, lsdb_scan_info* info,
                   lsdb_line* lines, int maxLines, int* lineOff, double* pts, int maxPts, int* ptOff,
-                  uint8_t* lineIm, long long lineImCap, long long* imOff, std::vector<lsdb_line>* keepOnDevice) {
+                  uint8_t* lineIm, long long lineImCap, long long* imOff, bool keepOnDevice) {
     static_assert(sizeof(lsdb_scan_info) == sizeof(LsdbFsInfo), "layout");
     if (!ctx) return LSDB_ERR_ARG;
     if (!prm || nFrames < 0 || !beamOff || !info || !lineOff || !ptOff || (lineIm && !imOff) || (!lines) != (!pts) ||
@@ -694,10 +773,10 @@ static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const l
         CK(ctx, cudaMalloc(&ctx->fsTmp, tmpBytes + tmpBytes / 4));
         ctx->fsTmpCap = tmpBytes + tmpBytes / 4;
     }
-    if (total > ctx->faDevCap) {
+    if (total > ctx->faDevCap || total > ctx->faHostCap) {   // the device-resident path grows the device side alone
         if (ctx->faDev) cudaFree(ctx->faDev);
         if (ctx->faHost) cudaFreeHost(ctx->faHost);
-        ctx->faDev = 0; ctx->faHost = 0; ctx->faDevCap = 0;
+        ctx->faDev = 0; ctx->faHost = 0; ctx->faDevCap = 0; ctx->faHostCap = 0;
         CK(ctx, cudaMalloc(&ctx->faDev, total + total / 4));
         CK(ctx, cudaMallocHost(&ctx->faHost, total + total / 4));
         ctx->faDevCap = ctx->faHostCap = total + total / 4;
@@ -731,7 +810,7 @@ static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const l
         if (imOff) imOff[f + 1] = nI;
     }
     if (!lines && !keepOnDevice) return LSDB_OK;   // sizing query
-    if (keepOnDevice) { keepOnDevice->resize((size_t)nL); lines = keepOnDevice->data(); maxLines = (int)nL; maxPts = (int)nP; }
+    if (keepOnDevice) { maxLines = (int)nL; maxPts = (int)nP; }
     if (nL > maxLines) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: %s%lld lines exceed max_lines", "", nL);
     if (nP > maxPts) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: %s%lld raster samples exceed max_pts", "", nP);
     if (lineIm && nI > lineImCap) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: rasters need %s%lld bytes", "", nI);
@@ -742,7 +821,7 @@ static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const l
         CK(ctx, cudaMalloc(&ctx->fsOut, outTotal + outTotal / 4));
         ctx->fsOutCap = outTotal + outTotal / 4;
     }
-    const size_t hostBytes = keepOnDevice ? oP : outTotal;     // pinned mirror of what travels back
+    const size_t hostBytes = keepOnDevice ? 0 : outTotal;      // pinned mirror of what travels back
     if (hostBytes > ctx->fsOutHostCap) {
         if (ctx->fsOutHost) cudaFreeHost(ctx->fsOutHost);
         ctx->fsOutHost = 0; ctx->fsOutHostCap = 0;
@@ -766,13 +845,12 @@ static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const l
                                                  (int*)(D + oLoff), (int*)(D + oPoff), (long long*)(D + oIoff), pi, (LsdbFaLine*)(O + oL),
                                                  (double*)(O + oP), lineIm ? (uint8_t*)ctx->fsIm : 0));
     CK(ctx, cudaEventRecord(ctx->faEv[1], s));
-    CK(ctx, cudaMemcpyAsync(OH, O, hostBytes, cudaMemcpyDeviceToHost, s));
+    if (hostBytes) CK(ctx, cudaMemcpyAsync(OH, O, hostBytes, cudaMemcpyDeviceToHost, s));
     if (lineIm && nI > 0) CK(ctx, cudaMemcpyAsync(lineIm, ctx->fsIm, (size_t)nI, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ms0, ctx->faEv[0], ctx->faEv[1]));
     ctx->fsMs += ms0;
-    memcpy(lines, OH + oL, sizeof(LsdbFaLine) * (size_t)nL);
-    if (!keepOnDevice) memcpy(pts, OH + oP, 16 * (size_t)nP);
+    if (!keepOnDevice) { memcpy(lines, OH + oL, sizeof(LsdbFaLine) * (size_t)nL); memcpy(pts, OH + oP, 16 * (size_t)nP); }
     ctx->fsLinesDev = O + oL; ctx->fsPtsDev = O + oP;
     return LSDB_OK;
 }
@@ -782,28 +860,26 @@ extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX
                                         lsdb_line* lines, int maxLines, int* lineOff, double* pts, int maxPts, int* ptOff,
                                         uint8_t* lineIm, long long lineImCap, long long* imOff) {
     return fs_run(ctx, resol, oriX, oriY, prm, nFrames, ranges, angles, beamOff, info, lines, maxLines, lineOff, pts, maxPts, ptOff, lineIm,
-                  lineImCap, imOff, 0);
+                  lineImCap, imOff, false);
 }
 
-// lidar sweeps in, one estimate per frame out: FeatureScan -> (pair filter on the host, from the line lengths) -> scoring ->
-// reduction, with the raster samples (the bulk of the data) never leaving the device
+// lidar sweeps in, one estimate per frame out: FeatureScan -> pair filter -> scoring -> reduction, all on the device; the
+// scan lines and raster samples never leave it
 extern "C" int lsdb_scan_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, double resol, double oriX, double oriY,
                                          const lsdb_rdp_params* prm, int nFrames, const double* ranges, const double* angles,
                                          const int* beamOff, const double* lastPose, lsdb_scan_info* info, lsdb_fa_estimate* est) {
     if (!ctx) return LSDB_ERR_ARG;
     if (!m || !est || !info || nFrames < 0 || (nFrames > 0 && !lastPose)) return fail(ctx, LSDB_ERR_ARG, "lsdb_scan_estimate_frames: bad argument%s");
     std::vector<int> lineOff((size_t)nFrames + 1, 0), ptOff((size_t)nFrames + 1, 0);
-    std::vector<lsdb_line> lines;
-    const int rc = fs_run(ctx, resol, oriX, oriY, prm, nFrames, ranges, angles, beamOff, info, 0, 0, lineOff.data(), 0, 0, ptOff.data(), 0, 0, 0, &lines);
+    const int rc = fs_run(ctx, resol, oriX, oriY, prm, nFrames, ranges, angles, beamOff, info, 0, 0, lineOff.data(), 0, 0, ptOff.data(), 0, 0, 0, true);
     if (rc != LSDB_OK || nFrames == 0) return rc;
     const float fsMs = ctx->fsMs;
     std::vector<double> lidar(2 * (size_t)nFrames);
     for (int f = 0; f < nFrames; f++) {                       // (int)round(FS.lidarPos), LSD/main_on_windows.cpp:229-230
         lidar[2 * (size_t)f] = (double)x86_d2i(round(info[f].lidar_x)); lidar[2 * (size_t)f + 1] = (double)x86_d2i(round(info[f].lidar_y));
     }
-    int nHyp = 0;
-    const int rc2 = fa_run(ctx, m, nFrames, lines.data(), lineOff.data(), 0, ptOff.data(), lidar.data(), lastPose, 0, 0, &nHyp, est,
-                           (const LsdbFaLine*)ctx->fsLinesDev, (const double*)ctx->fsPtsDev);
+    const int rc2 = fa_run_dev(ctx, m, nFrames, lineOff.data(), ptOff.data(), lidar.data(), lastPose, est, (const LsdbFaLine*)ctx->fsLinesDev,
+                               (const double*)ctx->fsPtsDev);
     ctx->fsMs = fsMs;
     return rc2;
 }

@@ -200,3 +200,116 @@ void lsdb_launch_fa(cudaStream_t s, int nTasks, const LsdbFaTask* tasks, const L
     lsdb_fa_score_kernel<<<(nHyp + perCta - 1) / perCta, FA_THREADS, 0, s>>>(nHyp, tasks, scanLines, scanLineOff, pts, ptOff, mapLines, mapCache,
                                                                             cols, rows, pose, out);
 }
+
+// ---- the pair filter of LSD/myFA.cpp:29-41 on the device (used when the scan lines are already there) ----
+// count: one thread per scan line; lines shorter than ignoreScanLength = 40 pair with nothing, the others with every map
+// line whose length is within scanToMapDiff = 0.35 of theirs (LSD/baseFunc.h:80-82)
+__device__ __forceinline__ bool fa_pair_ok(double lenS, double lenDiff, double lenM) { return !(lenM < lenS - lenDiff || lenM > lenS + lenDiff); }
+
+__global__ void lsdb_fa_pair_count_kernel(int nL, const LsdbFaLine* __restrict__ scanLines, const LsdbFaLine* __restrict__ mapLines, int nMap,
+                                          int* __restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nL) return;
+    const double lenS = scanLines[i].len;
+    int c = 0;
+    if (!(lenS < 40)) {
+        const double lenDiff = lenS * 0.35;
+        for (int im = 0; im < nMap; im++) c += fa_pair_ok(lenS, lenDiff, mapLines[im].len) ? 1 : 0;
+    }
+    cnt[i] = c;
+}
+
+// exclusive prefix sum of n ints in three small launches (tiles of 1024, their sums, the add-back); out[n] = total
+#define FA_SCAN_TILE 1024
+__global__ void __launch_bounds__(FA_SCAN_TILE) lsdb_scan_tiles_kernel(int n, const int* in, int* out, int* __restrict__ tileSum) {   // in may alias out
+    __shared__ int wsum[32];
+    const int i = blockIdx.x * FA_SCAN_TILE + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = i < n ? in[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    const int incl = x + (warp ? wsum[warp - 1] : 0);
+    if (i < n) out[i] = incl - v;
+    if (threadIdx.x == FA_SCAN_TILE - 1) tileSum[blockIdx.x] = incl;
+}
+__global__ void __launch_bounds__(FA_SCAN_TILE) lsdb_scan_sums_kernel(int nTiles, int* __restrict__ tileSum, int* __restrict__ total) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nTiles; base += FA_SCAN_TILE) {
+        const int i = base + threadIdx.x;
+        const int v = i < nTiles ? tileSum[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const int incl = x + (warp ? wsum[warp - 1] : 0) + carry;
+        if (i < nTiles) tileSum[i] = incl - v;      // exclusive offset of the tile
+        __syncthreads();
+        if (threadIdx.x == FA_SCAN_TILE - 1) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void lsdb_scan_add_kernel(int n, int* __restrict__ out, const int* __restrict__ tileOff, const int* __restrict__ total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += tileOff[i / FA_SCAN_TILE];
+    if (i == 0) out[n] = *total;
+}
+
+// tasks in (frame, scan line, map line) order at their offsets; hypOff[f] = 4 * tasks before frame f
+__global__ void lsdb_fa_pair_write_kernel(int nL, int nFrames, const LsdbFaLine* __restrict__ scanLines, const int* __restrict__ lineOff,
+                                          const LsdbFaLine* __restrict__ mapLines, int nMap, const int* __restrict__ taskOff,
+                                          LsdbFaTask* __restrict__ tasks, int* __restrict__ hypOff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nFrames) hypOff[i] = 4 * taskOff[lineOff[i]];
+    if (i >= nL) return;
+    const int n = taskOff[i + 1] - taskOff[i];
+    if (n == 0) return;
+    int lo = 0, hi = nFrames;                                // frame of scan line i: lineOff[f] <= i < lineOff[f+1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lineOff[mid] <= i) lo = mid; else hi = mid; }
+    const double lenS = scanLines[i].len, lenDiff = lenS * 0.35;
+    LsdbFaTask* t = tasks + taskOff[i];
+    int k = 0;
+    for (int im = 0; im < nMap; im++)
+        if (fa_pair_ok(lenS, lenDiff, mapLines[im].len)) { LsdbFaTask o = {lo, i - lineOff[lo], im, 0}; t[k++] = o; }
+}
+
+// scratch ints needed by lsdb_launch_fa_pairs_count: cnt[nL] is reused as taskOff[nL+1], then tile sums and the total
+size_t lsdb_fa_pairs_scratch_ints(int nL) { return (size_t)nL + 1 + (size_t)(nL + FA_SCAN_TILE - 1) / FA_SCAN_TILE + 2; }
+
+// phase 1: taskOff[0..nL] (exclusive prefix of the pair counts; taskOff[nL] = number of tasks)
+void lsdb_launch_fa_pairs_count(cudaStream_t s, int nL, const LsdbFaLine* scanLines, const LsdbFaLine* mapLines, int nMap, int* scratch) {
+    if (nL <= 0) return;
+    const int nTiles = (nL + FA_SCAN_TILE - 1) / FA_SCAN_TILE;
+    int* taskOff = scratch; int* tileSum = scratch + nL + 1; int* total = tileSum + nTiles;
+    lsdb_fa_pair_count_kernel<<<(nL + 255) / 256, 256, 0, s>>>(nL, scanLines, mapLines, nMap, taskOff);
+    lsdb_scan_tiles_kernel<<<nTiles, FA_SCAN_TILE, 0, s>>>(nL, taskOff, taskOff, tileSum);
+    lsdb_scan_sums_kernel<<<1, FA_SCAN_TILE, 0, s>>>(nTiles, tileSum, total);
+    lsdb_scan_add_kernel<<<(nL + 255) / 256, 256, 0, s>>>(nL, taskOff, tileSum, total);
+}
+// phase 2: the task list and the per-frame hypothesis offsets
+void lsdb_launch_fa_pairs_write(cudaStream_t s, int nL, int nFrames, const LsdbFaLine* scanLines, const int* lineOff, const LsdbFaLine* mapLines,
+                                int nMap, const int* scratch, LsdbFaTask* tasks, int* hypOff) {
+    const int n = (nL > nFrames + 1 ? nL : nFrames + 1);
+    lsdb_fa_pair_write_kernel<<<(n + 255) / 256, 256, 0, s>>>(nL, nFrames, scanLines, lineOff, mapLines, nMap, scratch, tasks, hypOff);
+}

@@ -75,6 +75,10 @@ def test_ragged_and_tiny_frames(lsdb, ctx):
     out = ctx.feature_scan(MP[2], MP[3], MP[4], frames, want_rasters=True)
     for f, (r, a) in enumerate(frames):
         _check(out[f], oraclebind.feature_scan(MP, r, a), f)
+    # a batch in which no frame yields a line: empty outputs, no launch of the lines kernel
+    none = ctx.feature_scan(MP[2], MP[3], MP[4], [frames[-1], frames[0]], want_rasters=True)
+    assert [len(o["lines"]) for o in none] == [0, 0] and [len(o["pts"]) for o in none] == [0, 0]
+    _check(none[0], oraclebind.feature_scan(MP, *frames[-1]), "circle")
 
 
 def test_non_default_parameters(lsdb, ctx):
@@ -140,4 +144,6 @@ def test_scan_to_estimate_chain(lsdb, ctx):
     one = fm.estimate([dict(scan_lines=o["lines"], pts=o["pts"], lidar_pose=np.rint(o["lidar_pos"]), last_pose=[-1.0, -1.0, 0.0]) for o in out])
     assert est2[:-1].tobytes() == np.tile(one, 40).tobytes()
     assert info2[-1]["n_lines"] == 0 and est2[-1]["n_kept"] == 0
+    info3, est3 = fm.scan_estimate(mp[2], mp[3], mp[4], [many[-1]])             # nothing to score at all
+    assert info3[0]["n_lines"] == 0 and est3[0]["n_hyp"] == 0 and est3[0]["n_kept"] == 0
     fm.close()
