@@ -319,6 +319,17 @@ def main():
         _, est_ = fm2.scan_estimate(mp[2], mp[3], mp[4], frames_l)                         # sweeps in, one estimate per frame out
         dt_est = time.time() - t0
         fm2.close()
+        # LSD on the scan rasters (configs[3]'s throughput workload): FeatureScan rasters -> occupancy convention -> one batch
+        nr = 2048
+        ras = ctx.feature_scan(mp[2], mp[3], mp[4], frames_l[:nr], want_rasters=True)
+        rmaps = [np.ascontiguousarray((o_["line_im"] > 0).astype(np.uint8)) for o_ in ras]
+        rb = lsdb.Batch(ctx, [(m_.shape[1], m_.shape[0]) for m_ in rmaps], max_lines=256)
+        rb.upload(rmaps); rb.run(); rb.sync()
+        t0 = time.time(); rb.run(); rb.sync(); dt_r = time.time() - t0
+        r_counts = rb.download()["counts"]
+        r_stage = rb.stage_ms(); rb.close()
+        raster_lsd = {"rasters": nr, "mpix": sum(m_.size for m_ in rmaps) / 1e6, "ms": dt_r * 1e3, "rasters_per_s": nr / dt_r,
+                      "mpix_per_s": sum(m_.size for m_ in rmaps) / dt_r / 1e6, "segments": int(r_counts.sum()), "stage_ms": r_stage}
         sample = frames_l[:2000]
         t0 = time.time()
         cpu_nl, _ = refbind.ref_feature_scan_many(list(mp), sample) if refbind.available("glibc") else oraclebind.feature_scan_many(list(mp), sample)
@@ -331,7 +342,7 @@ def main():
               "sweeps_to_estimates_per_s_e2e": len(frames_l) / dt_est, "sweeps_to_estimates_how": "lsdb_scan_estimate_frames, host buffers in/out, incl. the Python marshalling of the sweeps",
               "frames_with_match": int((est_["n_kept"] > 0).sum()), "hypotheses_scored": int(est_["n_hyp"].sum()),
               "cpu_frames_per_s": len(sample) / dt_cpu, "cpu_kind": "reference myrdp::FeatureScan, 1 thread" if refbind.available("glibc") else "port",
-              "cpu_sample": "first 2000 frames"}
+              "cpu_sample": "first 2000 frames", "raster_lsd": raster_lsd}
     except Exception as e:
         fs = {"error": repr(e)}
 
