@@ -247,6 +247,9 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         if (nw < 1) nw = 1;   // thousands of small maps (scan rasters): one warp each beats teams of 4 (2048 rasters: 36.6 vs 54.8 ms)
         if (getenv("LSDB_GROW_WARPS")) { int v = atoi(getenv("LSDB_GROW_WARPS")); if (v >= 1 && v <= LSDB_GROW_WARPS) nw = v; }
         b->nWarps = nw;
+        // one-warp teams = thousands of small maps: the shared-memory copy of the ban plane would cap the resident maps per SM
+        // (4096 scan rasters: 58 ms without it, 65 ms with it)
+        if (nw == 1 && !getenv("LSDB_SMEM_BAN_KB")) b->bmCapWords = 0;
         b->runAhead = 0;   // chunks a map's team may speculate ahead of its commit frontier (0 = as far as the ring allows)
         if (getenv("LSDB_RUNAHEAD")) b->runAhead = atoi(getenv("LSDB_RUNAHEAD"));
         b->steal = 0;   // measured: spreading large seeds over the team duplicates growth of neighbouring seeds; no net gain

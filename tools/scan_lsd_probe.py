@@ -20,7 +20,7 @@ sweeps = [(base[i % len(base)][0] * (1 + rng.normal(0, 0.002, len(base[i % len(b
 t = time.time(); fs = ctx.feature_scan(mp[2], mp[3], mp[4], sweeps, want_rasters=True); t_fs = time.time() - t
 maps = [np.ascontiguousarray((o["line_im"] > 0).astype(np.uint8)) for o in fs]     # mapValue convention: occupied = 1
 px = sum(m.size for m in maps)
-for env in [dict(), dict(LSDB_GROW_WARPS="1"), dict(LSDB_GROW_WARPS="2"), dict(LSDB_GROW_WARPS="4")]:
+for env in [dict(), dict(LSDB_GROW_WIDE="1"), dict(LSDB_GROW_WARPS="2", LSDB_GROW_WIDE="1"), dict(LSDB_SUPER_SHIFT="3"), dict(LSDB_NO_SMEM_BAN="1")]:
     os.environ.update(env)
     b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for m in maps], max_lines=256)
     for k in list(env): os.environ.pop(k)
