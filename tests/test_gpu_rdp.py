@@ -81,6 +81,33 @@ def test_ragged_and_tiny_frames(lsdb, ctx):
     _check(none[0], oraclebind.feature_scan(MP, *frames[-1]), "circle")
 
 
+def test_randomised_sweeps_vs_oracle(lsdb, ctx):
+    """1 500 sweeps of random length (1..1500 beams), room, noise and dropout in one ragged call; degenerate beams mixed in
+    (repeated points -> 0/0 slopes, exactly axis-aligned pieces, far returns beyond 9 m where the split threshold scales)"""
+    rng = np.random.default_rng(99)
+    frames = []
+    for s in range(1500):
+        nb = int(rng.integers(1, 1500)) if s % 3 else int(rng.integers(1, 40))
+        r, a = synth.lidar_frame(7000 + s, n_beams=nb, dropout=float(rng.uniform(0, 0.4)), noise=float(rng.choice([0.0, 0.002, 0.02])))
+        if len(r) == 0:
+            r, a = np.array([1.0]), np.array([0.0])
+        if s % 7 == 0 and len(r) > 8:                       # repeated returns
+            r[3:6] = r[3]; a[3:6] = a[3]
+        if s % 11 == 0:                                     # a far wall
+            r = r * 3.0
+        frames.append((r, a))
+    # exactly axis-aligned walls in grid coordinates: x = const / y = const
+    t = np.linspace(-1.0, 1.0, 120)
+    frames.append((np.hypot(2.0, t * 2), np.arctan2(t * 2, 2.0)))
+    frames.append((np.hypot(t * 2, 1.5), np.arctan2(1.5, t * 2)))
+    out = ctx.feature_scan(0.05, -30.0, -12.0, frames, want_rasters=True)
+    nl = 0
+    for f, (r, a) in enumerate(frames):
+        _check(out[f], oraclebind.feature_scan([0, 0, 0.05, -30.0, -12.0], r, a), f)
+        nl += len(out[f]["lines"])
+    assert nl > 3000
+
+
 def test_non_default_parameters(lsdb, ctx):
     frames = [synth.lidar_frame(900 + s) for s in range(16)]
     for prm in (dict(least_point=1, thre_line=0.03, least_dist_m=0.2), dict(least_point=8, thre_line=0.2, least_dist_m=1.0),
