@@ -192,6 +192,14 @@ int lsdb_feature_scan_frames(lsdb_ctx* ctx, double map_resol, double map_ori_x, 
                              const int* beam_off, lsdb_scan_info* info, lsdb_line* lines, int max_lines, int* line_off,
                              double* pts, int max_pts, int* pt_off, uint8_t* line_im, long long line_im_cap,
                              long long* im_off);
+/* LSD on rasterised scans (the reference rasterises a sweep into FS.lineIm and can run myLineSegmentDetector on it): writes
+ * the FeatureScan rasters of n_frames sweeps straight into the source planes of `batch` as occupancy grids (occupied = 1, the
+ * mapValue convention) — frame f becomes map f; the rasters never exist on the host.  `batch` must have been created with
+ * n_frames maps of the sizes (im_cols, im_rows) a sizing query of lsdb_feature_scan_frames reports for the same sweeps;
+ * LSDB_ERR_ARG otherwise.  Replaces lsdb_batch_upload for that batch; lsdb_batch_run follows. */
+int lsdb_batch_upload_scan_rasters(lsdb_batch* batch, double map_resol, double map_ori_x, double map_ori_y,
+                                   const lsdb_rdp_params* prm, int n_frames, const double* ranges, const double* angles,
+                                   const int* beam_off, lsdb_scan_info* info);
 /* The whole scan side of one localisation step for n_frames sweeps: FeatureScan, then the scoring and reduction of
  * lsdb_fa_estimate_frames against map `m`, with lidar_pose = (int)round(FS.lidarPos) as LSD/main_on_windows.cpp:229-230
  * builds it.  Same results as lsdb_feature_scan_frames followed by lsdb_fa_estimate_frames, but scan lines and raster samples

@@ -86,6 +86,7 @@ def lib():
         L.lsdb_fa_last_ms.argtypes = [vp]; L.lsdb_fa_last_ms.restype = C.c_float
         L.lsdb_feature_scan_frames.argtypes = [vp, cd, cd, cd, C.POINTER(_RdpParams), ci, vp, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp,
                                                C.c_longlong, vp]
+        L.lsdb_batch_upload_scan_rasters.argtypes = [vp, cd, cd, cd, C.POINTER(_RdpParams), ci, vp, vp, vp, vp]
         L.lsdb_scan_estimate_frames.argtypes = [vp, vp, cd, cd, cd, C.POINTER(_RdpParams), ci, vp, vp, vp, vp, vp, vp]
         L.lsdb_feature_scan_last_ms.argtypes = [vp]; L.lsdb_feature_scan_last_ms.restype = C.c_float
         _lib = L
@@ -182,6 +183,29 @@ def _ctx_feature_scan(self, map_res, map_ori_x, map_ori_y, frames, want_rasters=
     return out
 
 
+def _marshal_sweeps(sweeps, rdp):
+    nf = len(sweeps)
+    boff = np.zeros(nf + 1, np.int32)
+    for i, (r, _a) in enumerate(sweeps):
+        boff[i + 1] = boff[i] + len(r)
+    rng = np.ascontiguousarray(np.concatenate([np.asarray(r, np.float64) for r, _ in sweeps])) if nf else np.zeros(0)
+    ang = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float64) for _, a in sweeps])) if nf else np.zeros(0)
+    d = dict(RDP_DEFAULTS); d.update(rdp)
+    return nf, boff, rng, ang, _RdpParams(int(d["least_point"]), float(d["thre_line"]), float(d["least_dist_m"]))
+
+
+def _ctx_feature_scan_info(self, map_res, map_ori_x, map_ori_y, sweeps, **rdp):
+    """The sizing query of lsdb_feature_scan_frames: SCAN_INFO_DTYPE per sweep (lines, samples, raster size, lidarPos)."""
+    nf, boff, rng, ang, prm = _marshal_sweeps(sweeps, rdp)
+    info = np.zeros(nf, SCAN_INFO_DTYPE)
+    loff = np.zeros(nf + 1, np.int32); poff = np.zeros(nf + 1, np.int32); ioff = np.zeros(nf + 1, np.int64)
+    self.check(lib().lsdb_feature_scan_frames(self.h, float(map_res), float(map_ori_x), float(map_ori_y), C.byref(prm), nf, _p(rng), _p(ang),
+                                              _p(boff), _p(info), None, 0, _p(loff), None, 0, _p(poff), None, 0, _p(ioff)),
+               "lsdb_feature_scan_frames")
+    return info
+
+
+Context.feature_scan_info = _ctx_feature_scan_info
 Context.feature_scan = _ctx_feature_scan
 Context.feature_scan_last_ms = lambda self: float(lib().lsdb_feature_scan_last_ms(self.h))
 
@@ -218,6 +242,15 @@ class Batch:
                 ptrs[i] = a.ctypes.data
         self._keep = keep
         self.ctx.check(lib().lsdb_batch_upload(self.h, C.cast(ptrs, C.c_void_p)), "lsdb_batch_upload")
+
+    def upload_scan_rasters(self, map_res, map_ori_x, map_ori_y, sweeps, **rdp):
+        """lsdb_batch_upload_scan_rasters: the FeatureScan rasters of `sweeps` become the batch's maps on the device
+        (occupied = 1); the batch must have the raster sizes of Context.feature_scan_info.  Returns the scan info."""
+        nf, boff, rng, ang, prm = _marshal_sweeps(sweeps, rdp)
+        info = np.zeros(nf, SCAN_INFO_DTYPE)
+        self.ctx.check(lib().lsdb_batch_upload_scan_rasters(self.h, float(map_res), float(map_ori_x), float(map_ori_y), C.byref(prm), nf,
+                                                            _p(rng), _p(ang), _p(boff), _p(info)), "lsdb_batch_upload_scan_rasters")
+        return info
 
     def run(self):
         self.ctx.check(lib().lsdb_batch_run(self.h), "lsdb_batch_run")

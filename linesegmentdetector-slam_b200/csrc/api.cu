@@ -740,11 +740,13 @@ static int fa_run_dev(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const in
 extern "C" float lsdb_feature_scan_last_ms(const lsdb_ctx* ctx) { return ctx ? ctx->fsMs : 0.f; }
 
 // keepOnDevice: the chained mode of lsdb_scan_estimate_frames — line records and raster samples stay in ctx->fsOut
-// (ctx->fsLinesDev / fsPtsDev); only info and the offsets come back
+// (ctx->fsLinesDev / fsPtsDev); only info and the offsets come back.
+// into != NULL (implies keepOnDevice): the rasters are written straight into that batch's source planes as occupancy grids
+// (frame f = map f, occupied = 1), lsdb_batch_upload_scan_rasters.
 static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const lsdb_rdp_params* prm, int nFrames,
                   const double* ranges, const double* angles, const int* beamOff, lsdb_scan_info* info,
                   lsdb_line* lines, int maxLines, int* lineOff, double* pts, int maxPts, int* ptOff,
-                  uint8_t* lineIm, long long lineImCap, long long* imOff, bool keepOnDevice) {
+                  uint8_t* lineIm, long long lineImCap, long long* imOff, bool keepOnDevice, lsdb_batch* into = 0) {
     static_assert(sizeof(lsdb_scan_info) == sizeof(LsdbFsInfo), "layout");
     if (!ctx) return LSDB_ERR_ARG;
     if (!prm || nFrames < 0 || !beamOff || !info || !lineOff || !ptOff || (lineIm && !imOff) || (!lines) != (!pts) ||
@@ -768,7 +770,8 @@ static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const l
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t oR = 0, oA = oR + al256(8 * (size_t)nB), oB = oA + al256(8 * (size_t)nB), oInfo = oB + al256(4 * (size_t)(nFrames + 1)),
                  oLoff = oInfo + al256(sizeof(LsdbFsInfo) * (size_t)nFrames), oPoff = oLoff + al256(4 * (size_t)(nFrames + 1)),
-                 oIoff = oPoff + al256(4 * (size_t)(nFrames + 1)), total = oIoff + al256(8 * (size_t)(nFrames + 1));
+                 oIoff = oPoff + al256(4 * (size_t)(nFrames + 1)), oPitch = oIoff + al256(8 * (size_t)(nFrames + 1)),
+                 total = oPitch + al256(4 * (size_t)(nFrames + 1));
     const size_t tmpBytes = sizeof(LsdbFsPiece) * ((size_t)nB + 2 * (size_t)nFrames);   // device only: kept line pieces, n + 2 per frame
     if (tmpBytes > ctx->fsTmpCap) {
         if (ctx->fsTmp) cudaFree(ctx->fsTmp);
@@ -812,6 +815,14 @@ static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const l
         lineOff[f + 1] = (int)nL; ptOff[f + 1] = (int)nP; io[f + 1] = nI;
         if (imOff) imOff[f + 1] = nI;
     }
+    if (into) {
+        for (int f = 0; f < nFrames; f++) {
+            const LsdbImg& im = into->imgs[f];
+            if (info[f].im_cols != im.cols || info[f].im_rows != im.rows)
+                return fail(ctx, LSDB_ERR_ARG, "lsdb_batch_upload_scan_rasters: the raster of frame %s%lld does not have the size of its map in the batch", "", f);
+            io[f] = (long long)im.srcOff; ((int*)(H + oPitch))[f] = im.srcPitch;
+        }
+    }
     if (!lines && !keepOnDevice) return LSDB_OK;   // sizing query
     if (keepOnDevice) { maxLines = (int)nL; maxPts = (int)nP; }
     if (nL > maxLines) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_feature_scan_frames: %s%lld lines exceed max_lines", "", nL);
@@ -842,11 +853,13 @@ static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const l
     memcpy(H + oIoff, io.data(), 8 * (size_t)(nFrames + 1));
     CK(ctx, cudaMemcpyAsync(D + oLoff, H + oLoff, total - oLoff, cudaMemcpyHostToDevice, s));
     if (lineIm && nI > 0) CK(ctx, cudaMemsetAsync(ctx->fsIm, 0, (size_t)nI, s));
+    if (into) CK(ctx, cudaMemsetAsync(into->src, 0, into->totalSrc, s));
     char* O = (char*)ctx->fsOut; char* OH = (char*)ctx->fsOutHost;
     CK(ctx, cudaEventRecord(ctx->faEv[0], s));
     CK(ctx, (cudaError_t)lsdb_launch_fscan_lines(s, nFrames, (int)nL, (int*)(D + oB), (LsdbFsInfo*)(D + oInfo), (LsdbFsPiece*)ctx->fsTmp,
-                                                 (int*)(D + oLoff), (int*)(D + oPoff), (long long*)(D + oIoff), pi, (LsdbFaLine*)(O + oL),
-                                                 (double*)(O + oP), lineIm ? (uint8_t*)ctx->fsIm : 0));
+                                                 (int*)(D + oLoff), (int*)(D + oPoff), (long long*)(D + oIoff), into ? (int*)(D + oPitch) : 0,
+                                                 into ? 1 : 255, pi, (LsdbFaLine*)(O + oL), (double*)(O + oP),
+                                                 into ? into->src : (lineIm ? (uint8_t*)ctx->fsIm : 0)));
     CK(ctx, cudaEventRecord(ctx->faEv[1], s));
     if (hostBytes) CK(ctx, cudaMemcpyAsync(OH, O, hostBytes, cudaMemcpyDeviceToHost, s));
     if (lineIm && nI > 0) CK(ctx, cudaMemcpyAsync(lineIm, ctx->fsIm, (size_t)nI, cudaMemcpyDeviceToHost, s));
@@ -864,6 +877,16 @@ extern "C" int lsdb_feature_scan_frames(lsdb_ctx* ctx, double resol, double oriX
                                         uint8_t* lineIm, long long lineImCap, long long* imOff) {
     return fs_run(ctx, resol, oriX, oriY, prm, nFrames, ranges, angles, beamOff, info, lines, maxLines, lineOff, pts, maxPts, ptOff, lineIm,
                   lineImCap, imOff, false);
+}
+
+// FeatureScan rasters straight into a batch (BASELINE configs[3]: LSD on rasterised scans): no host copy of the rasters
+extern "C" int lsdb_batch_upload_scan_rasters(lsdb_batch* b, double resol, double oriX, double oriY, const lsdb_rdp_params* prm, int nFrames,
+                                              const double* ranges, const double* angles, const int* beamOff, lsdb_scan_info* info) {
+    if (!b) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    if (nFrames != b->n || !info) return fail(ctx, LSDB_ERR_ARG, "lsdb_batch_upload_scan_rasters: n_frames must equal the batch size%s");
+    std::vector<int> lineOff((size_t)nFrames + 1, 0), ptOff((size_t)nFrames + 1, 0);
+    return fs_run(ctx, resol, oriX, oriY, prm, nFrames, ranges, angles, beamOff, info, 0, 0, lineOff.data(), 0, 0, ptOff.data(), 0, 0, 0, true, b);
 }
 
 // lidar sweeps in, one estimate per frame out: FeatureScan -> pair filter -> scoring -> reduction, all on the device; the

@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(FS_NT, 12) lsdb_fscan_frames_kernel(
 __global__ void __launch_bounds__(FS_LW * 32) lsdb_fscan_lines_kernel(
     int nFrames, int nLinesTotal, const int* __restrict__ beamOff, const LsdbFsInfo* __restrict__ info,
     const LsdbFsPiece* __restrict__ pieces, const int* __restrict__ lineOff, const int* __restrict__ ptOff,
-    const long long* __restrict__ imOff, double pi, LsdbFaLine* __restrict__ lines, double* __restrict__ pts,
-    uint8_t* __restrict__ lineIm) {
+    const long long* __restrict__ imOff, const int* __restrict__ imPitch, int imVal, double pi, LsdbFaLine* __restrict__ lines,
+    double* __restrict__ pts, uint8_t* __restrict__ lineIm) {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * FS_LW + (threadIdx.x >> 5);
     if (g >= nLinesTotal) return;
@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(FS_LW * 32) lsdb_fscan_lines_kernel(
     }
     double* outP = pts + 2 * ((size_t)ptOff[f] + (size_t)pc.off);
     uint8_t* im = lineIm ? lineIm + imOff[f] : 0;
+    const int pitch = imPitch ? imPitch[f] : W;              // rasters packed (FS.lineIm) or written into a batch's padded source rows
     int run = 0;
     for (int m0 = 0; m0 < ln.cnt; m0 += 32) {
         int xx = 0, yy = 0;
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(FS_LW * 32) lsdb_fscan_lines_kernel(
         if (ok) {
             const size_t o = (size_t)(run + __popc(m & ((1u << lane) - 1)));
             outP[2 * o] = (double)xx; outP[2 * o + 1] = (double)yy;
-            if (im) im[(size_t)yy * W + xx] = 255;
+            if (im) im[(size_t)yy * pitch + xx] = (uint8_t)imVal;
         }
         run += __popc(m);
     }
@@ -351,10 +352,10 @@ int lsdb_launch_fscan_frames(cudaStream_t s, int nFrames, int maxBeams, const do
 }
 
 int lsdb_launch_fscan_lines(cudaStream_t s, int nFrames, int nLinesTotal, const int* beamOff, const LsdbFsInfo* info,
-                            const LsdbFsPiece* pieces, const int* lineOff, const int* ptOff, const long long* imOff, double pi,
-                            LsdbFaLine* lines, double* pts, uint8_t* lineIm) {
+                            const LsdbFsPiece* pieces, const int* lineOff, const int* ptOff, const long long* imOff, const int* imPitch,
+                            int imVal, double pi, LsdbFaLine* lines, double* pts, uint8_t* lineIm) {
     if (nLinesTotal <= 0) return 0;
     lsdb_fscan_lines_kernel<<<(nLinesTotal + FS_LW - 1) / FS_LW, FS_LW * 32, 0, s>>>(nFrames, nLinesTotal, beamOff, info, pieces, lineOff,
-                                                                                     ptOff, imOff, pi, lines, pts, lineIm);
+                                                                                     ptOff, imOff, imPitch, imVal, pi, lines, pts, lineIm);
     return (int)cudaGetLastError();
 }

@@ -118,5 +118,5 @@ int lsdb_launch_fscan_frames(cudaStream_t s, int nFrames, int maxBeams, const do
                              double resol, double oriX, double oriY, int leastPoint, double threLine, double leastDistM,
                              LsdbFsInfo* info, LsdbFsPiece* pieces);
 int lsdb_launch_fscan_lines(cudaStream_t s, int nFrames, int nLinesTotal, const int* beamOff, const LsdbFsInfo* info,
-                            const LsdbFsPiece* pieces, const int* lineOff, const int* ptOff, const long long* imOff, double pi,
-                            LsdbFaLine* lines, double* pts, uint8_t* lineIm);
+                            const LsdbFsPiece* pieces, const int* lineOff, const int* ptOff, const long long* imOff, const int* imPitch,
+                            int imVal, double pi, LsdbFaLine* lines, double* pts, uint8_t* lineIm);

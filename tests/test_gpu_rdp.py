@@ -174,3 +174,36 @@ def test_scan_to_estimate_chain(lsdb, ctx):
     info3, est3 = fm.scan_estimate(mp[2], mp[3], mp[4], [many[-1]])             # nothing to score at all
     assert info3[0]["n_lines"] == 0 and est3[0]["n_hyp"] == 0 and est3[0]["n_kept"] == 0
     fm.close()
+
+
+def test_scan_rasters_straight_into_a_batch(lsdb, ctx):
+    """lsdb_batch_upload_scan_rasters: sweeps -> rasters on the device -> LSD, equal to rasterising on the host (FeatureScan
+    lineIm > 0 as an occupancy grid) and uploading; the golden LSD-of-scan segment tables of the reference on top"""
+    g = np.load(os.path.join(GOLD, "lidar_frames.npz"))
+    ga = np.load(os.path.join(GOLD, "fa_frames.npz"))
+    mp = g["map_param"]
+    nf = 24
+    sweeps = [_finite(g[f"f{f}/ranges"], g[f"f{f}/angles"]) for f in range(nf)]
+    info = ctx.feature_scan_info(mp[2], mp[3], mp[4], sweeps)
+    sizes = [(int(i["im_cols"]), int(i["im_rows"])) for i in info]
+    b = lsdb.Batch(ctx, sizes, max_lines=512)
+    info2 = b.upload_scan_rasters(mp[2], mp[3], mp[4], sweeps)
+    assert info2.tobytes() == info.tobytes()
+    b.run(); dev = b.download()
+    host = ctx.feature_scan(mp[2], mp[3], mp[4], sweeps, want_rasters=True)
+    b2 = lsdb.Batch(ctx, sizes, max_lines=512)
+    b2.upload([np.ascontiguousarray((o["line_im"] > 0).astype(np.uint8)) for o in host]); b2.run(); ref = b2.download()
+    assert np.array_equal(dev["counts"], ref["counts"]) and dev["counts"].sum() > nf
+    for f in range(nf):
+        n = int(dev["counts"][f])
+        assert dev["lines"][f][:n].tobytes() == ref["lines"][f][:n].tobytes()
+    for f in range(int(ga["n_frames"])):                    # frames 0..11 of the association fixture are the first golden sweeps
+        want = ga[f"f{f}/scan_lsd_lines"]
+        got = lsdb.lines_to_array(dev["lines"][f][:int(dev["counts"][f])])
+        assert got.shape == want.shape and np.allclose(got, want, rtol=1e-9, atol=1e-9, equal_nan=True)
+    # a batch of the wrong shape is refused
+    bad = lsdb.Batch(ctx, [(s[0] + 1, s[1]) for s in sizes], max_lines=64)
+    with pytest.raises(lsdb.LsdbError, match="does not have the size"):
+        bad.upload_scan_rasters(mp[2], mp[3], mp[4], sweeps)
+    for x in (b, b2, bad):
+        x.close()
