@@ -40,6 +40,11 @@ def test_no_cpu_fallback(lsdb):
     h = C.c_void_p()
     assert lsdb.lib().lsdb_create(C.byref(h), 0, None) == 5 and not h     # LSDB_ERR_NO_DEVICE
     assert lsdb.lib().lsdb_batch_run(None) != 0
+    # the scan front-end entry points need a context / batch as well
+    L = lsdb.lib()
+    assert L.lsdb_feature_scan_frames(None, 0.05, 0.0, 0.0, None, 0, None, None, None, None, None, 0, None, None, 0, None, None, 0, None) == 2
+    assert L.lsdb_scan_estimate_frames(None, None, 0.05, 0.0, 0.0, None, 0, None, None, None, None, None, None) == 2
+    assert L.lsdb_batch_upload_scan_rasters(None, 0.05, 0.0, 0.0, None, 0, None, None, None, None) == 2
 
 
 def test_product_does_not_touch_the_oracle():
