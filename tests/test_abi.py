@@ -77,3 +77,37 @@ def test_dropin_library_keeps_the_reference_entry_points():
     assert "mylsd::createMapCache_cpu" in syms
     assert "myrdp::FeatureScan(_structMapParam, myrdp::_structLidarPointPolar*, int, int, double, double)" in syms
     assert "myrdp::FeatureScan_cpu" in syms
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/lsdb200.h compiles as strict C99 and as C++11, and a C program that calls through it links against
+    liblsdb200.so and gets LSDB_ERR_NO_DEVICE / LSDB_ERR_ARG back without a GPU (or a context with one)."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "lsdb200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    src = tmp_path / "abi.c"
+    src.write_text('''
+#include <stdio.h>
+#include "lsdb200.h"
+int main(void) {
+    lsdb_ctx* ctx = 0;
+    int rc = lsdb_create(&ctx, 0, 0);
+    lsdb_rdp_params rdp = {3, 0.08, 0.5};
+    lsdb_scan_info info;
+    int off[2] = {0, 0};
+    long long ioff[2];
+    int rc2 = lsdb_feature_scan_frames(ctx, 0.05, 0, 0, &rdp, 0, 0, 0, off, &info, 0, 0, off, 0, 0, off, 0, 0, ioff);
+    printf("%s %d %d\\n", lsdb_version(), rc, rc2);
+    if (ctx) lsdb_destroy(ctx);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    pkg = os.path.join(ROOT, "linesegmentdetector-slam_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", pkg, "-llsdb200",
+                           "-Wl,-rpath," + pkg])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert "sm_100a" in " ".join(out[:-2])
+    rc, rc2 = int(out[-2]), int(out[-1])
+    assert (rc, rc2) in ((5, 2), (0, 0))      # no device: NO_DEVICE then ARG (null context); with a B200: both succeed
