@@ -89,29 +89,37 @@ __global__ void __launch_bounds__(FA_THREADS) lsdb_fa_score_kernel(int nHyp, con
     fa_endpoints(S, M, i, msx, msy, mex, mey, ssx, ssy, sex, sey);
     const double cs = P.cs, sn = P.sn;
     double sum = 0.0;
-    int nValid = 0, nMax = 0;
-    for (int k = lane; k < nPts; k += 32) {
-        const double2 pt = *reinterpret_cast<const double2*>(&pts[2 * (size_t)(p0 + k)]);
-        const double ox = pt.x - ssx, oy = pt.y - ssy;                                               // :318-319
-        const double rx = ox * cs - oy * sn + msx;                                                   // :334-335
-        const double ry = ox * sn + oy * cs + msy;
-        const int x = lsdb_x86_d2i(round(rx)), y = lsdb_x86_d2i(round(ry));                          // :367-368
-        if (y >= 0 && y < rows && x >= 0 && x < cols) {
-            nValid++;
-            const double v = mapCache[(size_t)y * cols + x];
-            if (v >= 1.0) nMax++; else sum += v;                                                     // z_occ_max_dis, :373-382
+    int nMax = 0, nInvalid = 0;                                  // nInvalid: warp-wide count, the same in every lane
+    const double numAll = nPts, thr = 0.7 * numAll;             // :389-392: fewer than 70 % of the points inside the map -> +inf
+    for (int base = 0; base < nPts; base += 32) {
+        const int k = base + lane;
+        bool outside = false;
+        if (k < nPts) {
+            const double2 pt = *reinterpret_cast<const double2*>(&pts[2 * (size_t)(p0 + k)]);
+            const double ox = pt.x - ssx, oy = pt.y - ssy;                                               // :318-319
+            const double rx = ox * cs - oy * sn + msx;                                                   // :334-335
+            const double ry = ox * sn + oy * cs + msy;
+            const int x = lsdb_x86_d2i(round(rx)), y = lsdb_x86_d2i(round(ry));                          // :367-368
+            if (y >= 0 && y < rows && x >= 0 && x < cols) {
+                const double v = mapCache[(size_t)y * cols + x];
+                if (v >= 1.0) nMax++; else sum += v;                                                     // z_occ_max_dis, :373-382
+            } else outside = true;
         }
+        nInvalid += __popc(__ballot_sync(0xffffffffu, outside));
+        // even if every remaining point fell inside, too few would: the score is +inf whatever the rest says (about half
+        // of the hypotheses of an un-gated frame end here, after 30-60 % of their points)
+        if ((double)(nPts - nInvalid) < thr) return;
     }
+    const int nValid = nPts - nInvalid;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
         nMax += __shfl_xor_sync(0xffffffffu, nMax, o);
     }
     if (lane == 0) {
-        const double numAll = nPts, numValid = nValid;
+        const double numValid = nValid;
         const double sumMax = 10.0 * nMax;                      // sum of nMax tens is exact
-        if (!(numValid < 0.7 * numAll))                         // :389-392
+        if (!(numValid < thr))                                  // :389-392
             out[hyp].score = (sum + sumMax) / numValid + 10 * (numAll - numValid) / numAll;
     }
 }
