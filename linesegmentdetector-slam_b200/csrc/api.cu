@@ -866,7 +866,8 @@ static int fs_run(lsdb_ctx* ctx, double resol, double oriX, double oriY, const l
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ms0, ctx->faEv[0], ctx->faEv[1]));
     ctx->fsMs += ms0;
-    if (!keepOnDevice) { memcpy(lines, OH + oL, sizeof(LsdbFaLine) * (size_t)nL); memcpy(pts, OH + oP, 16 * (size_t)nP); }
+    if (!keepOnDevice && nL > 0) memcpy(lines, OH + oL, sizeof(LsdbFaLine) * (size_t)nL);
+    if (!keepOnDevice && nP > 0) memcpy(pts, OH + oP, 16 * (size_t)nP);
     ctx->fsLinesDev = O + oL; ctx->fsPtsDev = O + oP;
     return LSDB_OK;
 }
