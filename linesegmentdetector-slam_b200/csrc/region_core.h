@@ -19,13 +19,25 @@
 #define RG_HDN __device__ __noinline__
 #define RG_FFS(x) __ffs((int)(x))
 #define RG_LD_STATE(p) lsdb_ld_state(p)
+#define RG_MARK_GROWING(M, spec, p) do { if ((spec) >= 0) atomicOr(&(M).state[p], LSDB_ST_GROWING); } while (0)
+#define RG_LD_STATE_NB(p) __ldcg(p)   /* L2 load the compiler may schedule freely (no asm memory clobber): neighbour gathers */
 #define RG_LD_BM(p) (*(const volatile unsigned int*)(p))
 #define RG_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))
+#define RG_CLOCK() clock64()
+#define RG_ACTIVEMASK() __activemask()
+#define RG_ANY(mask, p) __any_sync((mask), (p))
+#define RG_POPC(x) __popc(x)
 #else
+#define RG_CLOCK() 0ll
+#define RG_ACTIVEMASK() 1u
+#define RG_ANY(mask, p) (p)
+#define RG_POPC(x) __builtin_popcount(x)
 #define RG_HD static inline
 #define RG_HDN static
 #define RG_FFS(x) __builtin_ffs((int)(x))
 #define RG_LD_STATE(p) (*(p))
+#define RG_LD_STATE_NB(p) (*(p))
+#define RG_MARK_GROWING(M, spec, p) do { } while (0)
 #define RG_LD_BM(p) (*(p))
 #define RG_FUNNEL_R(lo, hi, sh) ((unsigned int)(((((unsigned long long)(hi)) << 32) | (unsigned long long)(lo)) >> (sh)))
 #endif
@@ -70,6 +82,11 @@ struct RgEval {
     double logNFA;
     // counters
     int nGrows, nGrownPx, nRegrow, nRrr, nNfa, nNfaPx;
+    long long cycGrow, cycRect, cycNfa;   // lane clock64 deltas (device only)
+    int nSteps, nStepLanes;               // grower steps of this lane, and the lanes that ran them side by side (summed)
+#ifdef RG_COUNT_WORK
+    long long nPass, nVisit, nLoadPts, nCand;
+#endif
 };
 
 RG_HD unsigned int rg_pack(int x, int y) { return ((unsigned int)y << 16) | (unsigned int)x; }
@@ -81,35 +98,25 @@ RG_HD int rg_x86_d2i(double v) {   // x86-64 cvttsd2si: NaN / out of range -> IN
     return (int)v;
 }
 
-// bits (x-1, x, x+1) of one row of a bit plane, bit 0 = x-1; columns outside the image read as `outside`
-RG_HD unsigned int rg_row3(const unsigned int* row, int x, int W, int pw, bool vol, unsigned int outside) {
+// bits (x-1, x, x+1) of one row of the lane's private curMap plane, bit 0 = x-1 (columns outside the image read as 0)
+RG_HD unsigned int rg_row3(const unsigned int* row, int x, int W, int pw) {
     unsigned int out;
-    if (x == 0) {
-        const unsigned int w0 = vol ? RG_LD_BM(row) : row[0];
-        out = ((w0 << 1) | (outside & 1u)) & 7u;
-    } else {
+    if (x == 0) out = (row[0] << 1) & 7u;
+    else {
         const int xl = x - 1, wi = xl >> 5, sh = xl & 31;
-        const unsigned int lo = vol ? RG_LD_BM(row + wi) : row[wi];
-        unsigned int hi = outside ? 0xffffffffu : 0u;
-        if (sh > 29 && wi + 1 < pw) hi = vol ? RG_LD_BM(row + wi + 1) : row[wi + 1];
+        const unsigned int lo = row[wi];
+        const unsigned int hi = (sh > 29 && wi + 1 < pw) ? row[wi + 1] : 0u;
         out = RG_FUNNEL_R(lo, hi, sh) & 7u;
     }
-    if (x + 1 >= W) out = outside ? (out | 4u) : (out & 3u);
+    if (x + 1 >= W) out &= 3u;
     return out;
 }
-// 3x3 neighbourhood in the reference's scan order (:533-535): bit (dy+1)*3 + (dx+1).  ban plane: outside = banned
-RG_HD unsigned int rg_ban9(const RgMap& M, int x, int y) {
-    unsigned int r = 0;
-    r |= (y - 1 >= 0) ? rg_row3(M.bm + (size_t)(y - 1) * M.pw, x, M.W, M.pw, true, 1u) : 7u;
-    r |= rg_row3(M.bm + (size_t)y * M.pw, x, M.W, M.pw, true, 1u) << 3;
-    r |= ((y + 1 < M.H) ? rg_row3(M.bm + (size_t)(y + 1) * M.pw, x, M.W, M.pw, true, 1u) : 7u) << 6;
-    return r;
-}
+// 3x3 neighbourhood in the reference's scan order (:533-535): bit (dy+1)*3 + (dx+1)
 RG_HD unsigned int rg_vis9(const RgMap& M, const unsigned int* vis, int x, int y) {
     unsigned int r = 0;
-    if (y - 1 >= 0) r |= rg_row3(vis + (size_t)(y - 1) * M.pw, x, M.W, M.pw, false, 0u);
-    r |= rg_row3(vis + (size_t)y * M.pw, x, M.W, M.pw, false, 0u) << 3;
-    if (y + 1 < M.H) r |= rg_row3(vis + (size_t)(y + 1) * M.pw, x, M.W, M.pw, false, 0u) << 6;
+    if (y - 1 >= 0) r |= rg_row3(vis + (size_t)(y - 1) * M.pw, x, M.W, M.pw);
+    r |= rg_row3(vis + (size_t)y * M.pw, x, M.W, M.pw) << 3;
+    if (y + 1 < M.H) r |= rg_row3(vis + (size_t)(y + 1) * M.pw, x, M.W, M.pw) << 6;
     return r;
 }
 RG_HD void rg_vis_set(const RgMap& M, unsigned int* vis, int x, int y) { vis[(size_t)y * M.pw + (x >> 5)] |= 1u << (x & 31); }
@@ -148,117 +155,195 @@ RG_HDN double rg_pow(double x, double y) { return lsdm_pow(x, y); }
 // Returns the region size, or -1 when it outgrew B.cap (the lane's curMap bits of list[0..cap-1) are then still set).
 // SMALL = the scout: no curMap plane (membership = search of the lane's own short list) and the growth stops as soon as
 // the region reaches `stopAt` points — enough to know that it is not one of the ~97 % the reference drops at :228.
+// The growth as a step machine: rg_grow_init, then rg_grow_step (ONE listed point per call) while G.running, then
+// rg_grow_finish.  rg_lane_grow below runs it to completion; region.cu steps many of them side by side, one per lane.
+struct RgGrow {
+    unsigned int* list;
+    int num, exNum, startNum, i, stop, np, cap;
+    unsigned int v, rmask;           // the listed point being scanned; its neighbours to look at
+    double cosS, sinS, n2, c2n2, m2, c2, regExact, regDeg0, degThre;
+    int bx0, by0, bx1, by1;
+    int specChunk, stopAt;
+    bool nrmOK, haveExact, tauSmall, running;
+};
+
 template <bool SMALL>
-RG_HDN int rg_lane_grow(const RgMap& M, const RgLane& B, unsigned int* list, int sx, int sy, double regDeg0, double degThre,
-                        int specChunk, int stopAt, int& npnd, double& regDegOut, RgEval& ev) {
-    const int W = M.W;
-    const double pi = M.kc->pi, pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
-    const bool tauSmall = degThre <= 1.5;
-    double c2 = 0.0;
-    if (tauSmall) { const double cTau = degThre == M.kc->degThre ? M.kc->cosDegThre : rg_cos(degThre); c2 = cTau * cTau; }
-    const size_t sp = (size_t)sy * W + sx;
-    double cosS = M.cs[2 * sp], sinS = M.cs[2 * sp + 1];   // cos(regDeg), sin(regDeg) with regDeg = deg[seed]  (:515-516)
-    double n2 = cosS * cosS + sinS * sinS, c2n2 = c2 * n2, m2 = 4e-13 * n2;
-    bool nrmOK = n2 > 1e-18;
-    bool haveExact = true;
-    double regExact = regDeg0;
+RG_HD void rg_grow_init(const RgMap& M, const RgLane& B, RgGrow& G, unsigned int* list, int sx, int sy, double regDeg0, double degThre,
+                        int specChunk, int stopAt, int npnd, const RgEval& ev) {
+    G.list = list; G.regDeg0 = regDeg0; G.degThre = degThre; G.specChunk = specChunk; G.stopAt = stopAt; G.np = npnd; G.cap = B.cap;
+    G.tauSmall = degThre <= 1.5;
+    G.c2 = 0.0;
+    if (G.tauSmall) { const double cTau = degThre == M.kc->degThre ? M.kc->cosDegThre : rg_cos(degThre); G.c2 = cTau * cTau; }
+    const size_t sp = (size_t)sy * M.W + sx;
+    G.cosS = M.cs[2 * sp]; G.sinS = M.cs[2 * sp + 1];   // cos(regDeg), sin(regDeg) with regDeg = deg[seed]  (:515-516)
+    G.n2 = G.cosS * G.cosS + G.sinS * G.sinS; G.c2n2 = G.c2 * G.n2; G.m2 = 4e-13 * G.n2;
+    G.nrmOK = G.n2 > 1e-18;
+    G.haveExact = true;
+    G.regExact = regDeg0;
     list[0] = rg_pack(sx, sy);
     B.rej[0] = 0;
     if (!SMALL) rg_vis_set(M, B.vis, sx, sy);
-    int num = 1, exNum = 0, startNum = 0;
-    int bx0 = ev.x0, by0 = ev.y0, bx1 = ev.x1, by1 = ev.y1;
-    if (sx < bx0) bx0 = sx; if (sx > bx1) bx1 = sx; if (sy < by0) by0 = sy; if (sy > by1) by1 = sy;
-    const int cap = B.cap;
-    while (exNum != num) {
-        exNum = num;
-        for (int i = 0; i < num; i++) {
-            const unsigned int v = list[i];
-            const int x = rg_px(v), y = rg_py(v);
-            unsigned int cm;
-            if (i >= startNum) cm = ~rg_ban9(M, x, y) & 0x1efu;
-            else cm = B.rej[i];
-            if (cm) {   // drop the neighbours that are in the region already
-                if (!SMALL) cm &= ~rg_vis9(M, B.vis, x, y);
-                else {
-                    unsigned int own = 0;
-                    for (int k = 0; k < num; k++) {
-                        const int ddx = rg_px(list[k]) - x + 1, ddy = rg_py(list[k]) - y + 1;
-                        if ((unsigned int)ddx < 3u && (unsigned int)ddy < 3u) own |= 1u << (ddy * 3 + ddx);
-                    }
-                    cm &= ~own;
+    G.num = 1; G.startNum = 0; G.stop = 0;
+    G.exNum = 1;   // list length when the current pass started
+    G.bx0 = ev.x0; G.by0 = ev.y0; G.bx1 = ev.x1; G.by1 = ev.y1;
+    if (sx < G.bx0) G.bx0 = sx; if (sx > G.bx1) G.bx1 = sx; if (sy < G.by0) G.by0 = sy; if (sy > G.by1) G.by1 = sy;
+    G.v = list[0]; G.rmask = 0x1efu; G.i = 0;
+    G.running = true;
+}
+
+// One step = one listed point.  The two loops of the reference (passes over the list until one adds nothing, :525; the
+// points of the list, :527) are one flat sequence of steps.  Structured control flow only: the lanes of a warp step side
+// by side.  G.stop ends the growth: 1 = list overflow, 2 = the scout's region reached stopAt points.
+// v = the listed point being scanned, rmask = its neighbours to look at: all eight on its first scan, in later passes
+// the ones that failed the angle test.  Both are carried from one point to the next (the next point is either listed
+// already — fetched a point ahead — or the first pixel accepted at this point).
+template <bool SMALL>
+RG_HD void rg_grow_step(const RgMap& M, const RgLane& B, RgGrow& G) {
+    const int W = M.W, H = M.H;
+    unsigned int* list = G.list;
+    const int i = G.i;
+    int num = G.num;
+    const int startNum = G.startNum;
+    const int x = rg_px(G.v), y = rg_py(G.v);
+    const int numAt = num;
+    unsigned int nv = 0, nmask = 0x1efu;
+    if (i + 1 < numAt) { nv = list[i + 1]; if (i + 1 < startNum) nmask = B.rej[i + 1]; }
+    unsigned int firstAcc = 0;
+    unsigned int cm = G.rmask;
+    if (i >= startNum) {   // neighbours outside the image (:536)
+        if (y == 0) cm &= ~0x007u;
+        if (y == H - 1) cm &= ~0x1c0u;
+        if (x == 0) cm &= ~0x049u;
+        if (x == W - 1) cm &= ~0x124u;
+    }
+    unsigned int nr = 0;
+    int stop = 0;
+    if (cm) {
+        // round trip 1: the state words of the neighbours (usedMap, parked marks) and the lane's curMap rows
+        unsigned int st8[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int nb = t < 4 ? t : t + 1;
+            st8[t] = LSDB_ST_BAN;
+            if ((cm >> nb) & 1u) st8[t] = RG_LD_STATE_NB(&M.state[(size_t)(y + nb / 3 - 1) * W + (x + nb % 3 - 1)]);
+        }
+        if (!SMALL) cm &= ~rg_vis9(M, B.vis, x, y);   // in the region already
+        else {
+            unsigned int own = 0;
+            for (int k = 0; k < num; k++) {
+                const int ddx = rg_px(list[k]) - x + 1, ddy = rg_py(list[k]) - y + 1;
+                if ((unsigned int)ddx < 3u && (unsigned int)ddy < 3u) own |= 1u << (ddy * 3 + ddx);
+            }
+            cm &= ~own;
+        }
+        // open = candidates: not in the region, usedMap != 1 (:537), not parked for acceptance by an earlier seed
+        unsigned int open = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int nb = t < 4 ? t : t + 1;
+            const unsigned int st = st8[t];
+            if (((cm >> nb) & 1u) && !(st & LSDB_ST_BAN)) {
+                if (rg_pend_applies(st, LSDB_ST_PACC, G.specChunk)) {
+                    if (G.np >= 0 && G.np < B.pndCap) B.pnd[G.np++] = rg_pack(x + nb % 3 - 1, y + nb / 3 - 1); else G.np = -1;
+                } else open |= 1u << nb;
+            }
+        }
+        // round trip 2 (mostly L1 hits: the angle planes are immutable): angle data of the open candidates, four at a
+        // time, then the decisions, in scan order
+        const double pi = M.kc->pi, pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
+        while (open && !stop) {
+            int nb4[4]; double cd4[4], sd4[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                nb4[t] = -1; cd4[t] = 0; sd4[t] = 0;
+                if (open) {
+                    const int nb = RG_FFS(open) - 1;
+                    open &= open - 1;
+                    const size_t p = (size_t)(y + nb / 3 - 1) * W + (x + nb % 3 - 1);
+                    nb4[t] = nb; cd4[t] = M.cs[2 * p]; sd4[t] = M.cs[2 * p + 1];
                 }
             }
-            unsigned int nr = 0;
-            while (cm) {
-                // up to four candidates of this point: issue their loads together, then decide them in scan order
-                int nbv[4]; unsigned int stv[4]; double cdv[4], sdv[4];
-                int k = 0;
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    nbv[t] = 0; stv[t] = 0; cdv[t] = 0; sdv[t] = 0;
-                    if (cm) {
-                        const int nb = RG_FFS(cm) - 1;
-                        cm &= cm - 1;
-                        const int r3 = nb / 3;
-                        const size_t p = (size_t)(y + r3 - 1) * W + (x + (nb - r3 * 3) - 1);
-                        nbv[t] = nb;
-                        stv[t] = RG_LD_STATE(&M.state[p]);
-                        cdv[t] = M.cs[2 * p]; sdv[t] = M.cs[2 * p + 1];
-                        k = t + 1;
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    if (t >= k) break;
-                    const int nb = nbv[t];
-                    const int r3 = nb / 3;
-                    const int m = y + r3 - 1, n = x + (nb - r3 * 3) - 1;
-                    const unsigned int st = stv[t];
-                    if (st & LSDB_ST_BAN) continue;
-                    if (rg_pend_applies(st, LSDB_ST_PACC, specChunk)) {
-                        if (npnd >= 0 && npnd < B.pndCap) B.pnd[npnd++] = rg_pack(n, m); else npnd = -1;
-                        continue;
-                    }
-                    const double cd = cdv[t], sd = sdv[t];
+            for (int t = 0; t < 4; t++) {
+                const int nb = nb4[t];
+                if (nb >= 0 && !stop) {
+                    const int m = y + nb / 3 - 1, n = x + nb % 3 - 1;
+                    const double cd = cd4[t], sd = sd4[t];
                     bool pass = false, unc = true;
-                    if (tauSmall) {
-                        const double dot = cosS * cd + sinS * sd;
-                        const double d2 = dot * dot - c2n2;
+                    if (G.tauSmall) {
+                        const double dot = G.cosS * cd + G.sinS * sd;
+                        const double d2 = dot * dot - G.c2n2;
                         pass = dot > 0 && d2 > 0;
-                        unc = (dot > 0 && !(fabs(d2) > m2)) || !nrmOK;
+                        unc = (dot > 0 && !(fabs(d2) > G.m2)) || !G.nrmOK;
                     }
                     if (unc) {   // the literal test, :540-543
-                        if (!haveExact) { regExact = rg_atan2(sinS, cosS); haveExact = true; }
-                        double degDif = fabs(regExact - M.deg[(size_t)m * W + n]);
+                        if (!G.haveExact) { G.regExact = rg_atan2(G.sinS, G.cosS); G.haveExact = true; }
+                        double degDif = fabs(G.regExact - M.deg[(size_t)m * W + n]);
                         if (degDif > pi32) degDif = fabs(degDif - pi2);
-                        pass = degDif < degThre;
+                        pass = degDif < G.degThre;
                     }
+                    if (pass && num >= G.cap - 1) { stop = 1; pass = false; }
                     if (pass) {
-                        if (num >= cap - 1) { ev.x0 = bx0; ev.y0 = by0; ev.x1 = bx1; ev.y1 = by1; return -1; }
-                        list[num] = rg_pack(n, m);
-                        B.rej[num] = 0;
-                        if (!SMALL) rg_vis_set(M, B.vis, n, m);
+                        const unsigned int pk = rg_pack(n, m);
+                        if (num == numAt) firstAcc = pk;
+                        list[num] = pk;
+                        if (!SMALL) { rg_vis_set(M, B.vis, n, m); RG_MARK_GROWING(M, G.specChunk, (size_t)m * W + n); }
                         num++;
-                        cosS += cd;   // :545-546
-                        sinS += sd;
-                        haveExact = false;
-                        if (SMALL && num >= stopAt) { ev.x0 = bx0; ev.y0 = by0; ev.x1 = bx1; ev.y1 = by1; return num; }
-                        n2 = cosS * cosS + sinS * sinS;
-                        c2n2 = c2 * n2; m2 = 4e-13 * n2; nrmOK = n2 > 1e-18;
-                        if (n < bx0) bx0 = n; if (n > bx1) bx1 = n; if (m < by0) by0 = m; if (m > by1) by1 = m;
-                    } else {
+                        G.cosS += cd;   // :545-546
+                        G.sinS += sd;
+                        G.haveExact = false;
+                        G.n2 = G.cosS * G.cosS + G.sinS * G.sinS;
+                        G.c2n2 = G.c2 * G.n2; G.m2 = 4e-13 * G.n2; G.nrmOK = G.n2 > 1e-18;
+                        if (n < G.bx0) G.bx0 = n; if (n > G.bx1) G.bx1 = n; if (m < G.by0) G.by0 = m; if (m > G.by1) G.by1 = m;
+                        if (SMALL && num >= G.stopAt) stop = 2;
+                    } else if (!stop) {
                         nr |= 1u << nb;
                     }
                 }
             }
-            B.rej[i] = (unsigned short)nr;
         }
-        startNum = num;
     }
-    regDegOut = num > 1 ? (haveExact ? regExact : rg_atan2(sinS, cosS)) : regDeg0;   // :547 after the last accept
-    ev.x0 = bx0; ev.y0 = by0; ev.x1 = bx1; ev.y1 = by1;
-    ev.nGrows++; ev.nGrownPx += num;
-    return num;
+    B.rej[i] = (unsigned short)nr;
+    if (i + 1 < numAt) { G.v = nv; G.rmask = nmask; }
+    else { G.v = firstAcc; G.rmask = 0x1efu; }   // i + 1 == numAt: the first pixel accepted at this point, if any
+    G.num = num;
+    G.i = i + 1;
+    if (stop) { G.stop = stop; G.running = false; }
+    else if (G.i >= num) {   // end of a pass (:525): another one if this one added something
+        G.startNum = num;
+        if (num == G.exNum) G.running = false;
+        else { G.exNum = num; G.i = 0; G.v = list[0]; G.rmask = B.rej[0]; }
+    }
+}
+
+// region size (-1: it outgrew the list; the curMap bits of list[0..cap-1) are then still set); bounding box, pending count
+RG_HD int rg_grow_finish(const RgGrow& G, int& npnd, double& regDegOut, RgEval& ev) {
+    ev.x0 = G.bx0; ev.y0 = G.by0; ev.x1 = G.bx1; ev.y1 = G.by1;
+    npnd = G.np;
+    if (G.stop == 1) return -1;
+    if (G.stop == 2) return G.num;
+    regDegOut = G.num > 1 ? (G.haveExact ? G.regExact : rg_atan2(G.sinS, G.cosS)) : G.regDeg0;   // :547 after the last accept
+    ev.nGrows++; ev.nGrownPx += G.num;
+    return G.num;
+}
+
+// SMALL = the scout: no curMap plane (membership = search of the lane's own short list) and the growth stops as soon as
+// the region reaches `stopAt` points — enough to know that it is not one of the ~97 % the reference drops at :228.
+// The loop head is an explicit warp vote: the lanes that entered together meet there after every step, so that their
+// gathers are in flight at the same time.
+template <bool SMALL>
+RG_HDN int rg_lane_grow(const RgMap& M, const RgLane& B, unsigned int* list, int sx, int sy, double regDeg0, double degThre,
+                        int specChunk, int stopAt, int& npnd, double& regDegOut, RgEval& ev) {
+    RgGrow G;
+    rg_grow_init<SMALL>(M, B, G, list, sx, sy, regDeg0, degThre, specChunk, stopAt, npnd, ev);
+    const unsigned int team = RG_ACTIVEMASK();
+    while (RG_ANY(team, G.running)) {
+        if (G.running) {
+            ev.nSteps++; ev.nStepLanes += RG_POPC(RG_ACTIVEMASK());
+            rg_grow_step<SMALL>(M, B, G);
+        }
+    }
+    return rg_grow_finish(G, npnd, regDegOut, ev);
 }
 
 // ------------------------------------------------------------------ RectangleConverter (:592-734), sums in list order
@@ -266,24 +351,42 @@ RG_HDN RgRect rg_rect(const RgMap& M, const unsigned int* lst, int num, double r
     const int W = M.W;
     const double pi = M.kc->pi;
     double cenX = 0, cenY = 0, weiSum = 0;
-    for (int k = 0; k < num; k++) {   // CenterGetter :608-613
-        const unsigned int v = lst[k];
-        const double w = M.mag[(size_t)rg_py(v) * W + rg_px(v)];
-        cenX += w * rg_px(v);
-        cenY += w * rg_py(v);
-        weiSum += w;
+    // the addends depend on gathers (list entry -> magnitude): fetched eight points at a time so that the round trips
+    // overlap; the sums themselves are accumulated one by one, in list order, like the reference
+    for (int k0 = 0; k0 < num; k0 += 8) {   // CenterGetter :608-613
+        unsigned int v[8]; double w[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) v[t] = k0 + t < num ? lst[k0 + t] : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; t++) w[t] = k0 + t < num ? M.mag[(size_t)rg_py(v[t]) * W + rg_px(v[t])] : 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (k0 + t < num) {
+                cenX += w[t] * rg_px(v[t]);
+                cenY += w[t] * rg_py(v[t]);
+                weiSum += w[t];
+            }
+        }
     }
     cenX = cenX / weiSum; cenY = cenY / weiSum;
     double Ixx = 0, Iyy = 0, Ixy = 0;
     weiSum = 0;
-    for (int k = 0; k < num; k++) {   // OrientationGetter :637-643
-        const unsigned int v = lst[k];
-        const double w = M.mag[(size_t)rg_py(v) * W + rg_px(v)];
-        const double ey = rg_py(v) - cenY, ex = rg_px(v) - cenX;
-        Ixx += w * (ey * ey);
-        Iyy += w * (ex * ex);
-        Ixy -= w * ex * ey;
-        weiSum += w;
+    for (int k0 = 0; k0 < num; k0 += 8) {   // OrientationGetter :637-643
+        unsigned int v[8]; double w[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) v[t] = k0 + t < num ? lst[k0 + t] : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; t++) w[t] = k0 + t < num ? M.mag[(size_t)rg_py(v[t]) * W + rg_px(v[t])] : 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (k0 + t < num) {
+                const double ey = rg_py(v[t]) - cenY, ex = rg_px(v[t]) - cenX;
+                Ixx += w[t] * (ey * ey);
+                Iyy += w[t] * (ex * ex);
+                Ixy -= w[t] * ex * ey;
+                weiSum += w[t];
+            }
+        }
     }
     Ixx /= weiSum; Iyy /= weiSum; Ixy /= weiSum;
     const double dI = Ixx - Iyy;
@@ -398,11 +501,19 @@ RG_HDN double rg_nfa(const RgMap& M, const RgRect& rec, RgEval& ev) {
             else if (xi >= vX1) yh = rg_x86_d2i(floor(vY1 + (xi - vX1) * k1));
             if (xi < 0 || xi >= xLim) continue;
             const int j0 = yl < 0 ? 0 : yl, j1 = yh > yLim - 1 ? yLim - 1 : yh;
-            for (int j = j0; j <= j1; j++) {
-                allPixNum++;
-                double degDif = fabs(rec.deg - M.deg[(size_t)j * xLim + xi]);
-                if (degDif > pi32) degDif = fabs(degDif - pi2);
-                if (degDif < rec.prec) aliPixNum++;
+            for (int j = j0; j <= j1; j += 4) {   // counts are order-free: four gathers in flight
+                double dv[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) dv[t] = j + t <= j1 ? M.deg[(size_t)(j + t) * xLim + xi] : 0.0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (j + t <= j1) {
+                        allPixNum++;
+                        double degDif = fabs(rec.deg - dv[t]);
+                        if (degDif > pi32) degDif = fabs(degDif - pi2);
+                        if (degDif < rec.prec) aliPixNum++;
+                    }
+                }
             }
         }
     }
@@ -495,106 +606,156 @@ RG_HDN double rg_improve(const RgMap& M, RgRect& rec, RgEval& ev) {
 }
 
 // ------------------------------------------------------------------ one seed: grow -> rectangle -> Refiner -> NFA  (:225-250)
-// The lane's private curMap is all zero again on return (except after RG_OC_DEFER by overflow, where it is cleared here too).
-// Lists on return:  G1 = B.L0[0..nG1)   G2 = B.L2[0..nG2) (if usedT)   commit list = (usedT ? B.L1 : B.L0)[0..nCommit)
-RG_HDN void rg_eval_lane(const RgMap& M, const RgLane& B, int p0, int specChunk, RgEval& ev) {
-    const LsdbLsdConst* kc = M.kc;
-    const int W = M.W;
-    const int sx = p0 % W, sy = p0 / W;
+// As a job that alternates between growth steps and the sequential work between two growths:
+//   rg_job_begin;  while (J.g.running) rg_grow_step<false>;  rg_job_after_grow -> true: a re-grow was started, step again
+// The lane's private curMap is all zero again when the job has finished.
+// Lists when finished:  G1 = B.L0[0..nG1)   G2 = B.L2[0..nG2) (if usedT)   commit list = (usedT ? B.L1 : B.L0)[0..nCommit)
+struct RgJob {
+    RgGrow g;
+    RgEval ev;
+    RgRect rec;
+    double regDeg, degThre2;
+    int p0, specChunk, stage, npnd;   // stage: 1 = first grow, 2 = the Refiner's re-grow
+};
+
+RG_HD void rg_job_begin(const RgMap& M, const RgLane& B, RgJob& J, int p0, int specChunk) {
+    RgEval& ev = J.ev;
     ev.oc = RG_OC_NOCHANGE; ev.nG1 = 0; ev.nG2 = 0; ev.nCommit = 0; ev.usedT = 0; ev.npnd = 0; ev.logNFA = 0;
     ev.x0 = ev.y0 = 0x7fffffff; ev.x1 = ev.y1 = -1;
     ev.nGrows = ev.nGrownPx = ev.nRegrow = ev.nRrr = ev.nNfa = ev.nNfaPx = 0;
-    int npnd = 0;
-    double regDeg = M.deg[p0];
-    int num = rg_lane_grow<false>(M, B, B.L0, sx, sy, regDeg, kc->degThre, specChunk, 0, npnd, regDeg, ev);
-    if (num < 0) { rg_vis_clear_list(M, B.vis, B.L0, B.cap - 1); ev.oc = RG_OC_DEFER; ev.npnd = npnd; return; }
-    ev.nG1 = num;
-    if (num < M.regThre) {   // :228
-        rg_vis_clear_list(M, B.vis, B.L0, num);
-        ev.npnd = npnd;
-        return;
-    }
-    RgRect rec = rg_rect(M, B.L0, num, regDeg, kc->aliPro, kc->degThre);
-    const unsigned int* lst = B.L0;
-    double den = rg_density(num, rec);
-    if (!(den >= kc->denThre)) {   // Refiner :804-880
-        const double pi = kc->pi;
-        const double cenDeg = M.deg[p0];
-        double difSum = 0, squSum = 0;
-        int ptNum = 0;
-        for (int k = 0; k < num; k++) {   // :839-853
-            const unsigned int v = B.L0[k];
-            if (rg_dist(sx, sy, (double)rg_px(v), (double)rg_py(v)) < rec.wid) {
-                double dd = M.deg[(size_t)rg_py(v) * W + rg_px(v)] - cenDeg;
-                while (dd <= -pi) dd += 2 * pi;
-                while (dd > pi) dd -= 2 * pi;
-                difSum += dd;
-                squSum += dd * dd;
-                ptNum++;
-            }
+    ev.cycGrow = ev.cycRect = ev.cycNfa = 0; ev.nSteps = ev.nStepLanes = 0;
+    J.p0 = p0; J.specChunk = specChunk; J.stage = 1; J.npnd = 0;
+    J.regDeg = M.deg[p0];
+    rg_grow_init<false>(M, B, J.g, B.L0, p0 % M.W, p0 / M.W, J.regDeg, M.kc->degThre, specChunk, 0, 0, ev);
+}
+
+// Written as a sequence of phases guarded by flags instead of early returns: the lanes of a warp run this side by side, and
+// a lane that skips a phase must meet the others again right after it.
+RG_HDN bool rg_job_after_grow(const RgMap& M, const RgLane& B, RgJob& J) {
+    const LsdbLsdConst* kc = M.kc;
+    const int W = M.W;
+    const int sx = J.p0 % W, sy = J.p0 / W;
+    RgEval& ev = J.ev;
+    long long tc = RG_CLOCK();
+    double regDeg = J.regDeg;
+    int npnd = J.npnd;
+    int num = rg_grow_finish(J.g, npnd, regDeg, ev);
+    J.npnd = npnd; ev.npnd = npnd;
+    bool go = true;        // the evaluation is still running
+    bool again = false;    // a re-grow has been started
+    RgRect rec = J.rec;
+    if (J.stage == 1) {
+        if (num < 0) { rg_vis_clear_list(M, B.vis, B.L0, B.cap - 1); ev.oc = RG_OC_DEFER; go = false; }
+        else {
+            ev.nG1 = num;
+            if (num < M.regThre) { rg_vis_clear_list(M, B.vis, B.L0, num); go = false; }   // :228
         }
-        const double meanDif = difSum / (ptNum * 1.0);
-        const double degThre2 = 2.0 * sqrt((squSum - 2 * meanDif * difSum) / (ptNum * 1.0) + meanDif * meanDif);
-        rg_vis_clear_list(M, B.vis, B.L0, num);
-        regDeg = cenDeg;
-        num = rg_lane_grow<false>(M, B, B.L1, sx, sy, regDeg, degThre2, specChunk, 0, npnd, regDeg, ev);
-        ev.nRegrow++;
-        if (num < 0) { rg_vis_clear_list(M, B.vis, B.L1, B.cap - 1); ev.oc = RG_OC_DEFER; ev.npnd = npnd; return; }
-        for (int k = 0; k < num; k++) B.L2[k] = B.L1[k];
-        ev.usedT = 1; ev.nG2 = num;
-        ev.npnd = npnd;
-        if (num < 2) { rg_vis_clear_list(M, B.vis, B.L2, ev.nG2); return; }   // :861-864
-        rec = rg_rect(M, B.L1, num, regDeg, rec.p, rec.prec);
-        den = rg_density(num, rec);
-        lst = B.L1;
-        if (den < kc->denThre) {
-            // RegionRadiusReducer :736-802, in place, with the `i <= num` quirk
-            bool ok = true;
-            double d2 = den;
-            if (!(d2 > kc->denThre)) {
-                const double rad1 = rg_dist(sx, sy, rec.x1, rec.y1), rad2 = rg_dist(sx, sy, rec.x2, rec.y2);
-                double rad = rad1 > rad2 ? rad1 : rad2;
-                while (d2 < kc->denThre) {
-                    rad *= 0.75;
-                    int i = 0, nn = num;
-                    B.L1[nn] = 0u;   // slot [num] reads as (0,0)
-                    while (i <= nn) {
-                        if (nn <= 0) break;   // the reference would index [-1] here (heap underflow, UB)
-                        const unsigned int v = B.L1[i];
-                        if (rg_dist(sx, sy, (double)rg_px(v), (double)rg_py(v)) > rad) {
-                            rg_vis_clr(M, B.vis, rg_px(v), rg_py(v));
-                            B.L1[i] = B.L1[nn - 1];
-                            B.L1[nn - 1] = 0u;
-                            i--;
-                            nn--;
-                        }
-                        i++;
-                    }
-                    num = nn;
-                    ev.nRrr++;
-                    if (num < 2) { ok = false; break; }
-                    rec = rg_rect(M, B.L1, num, regDeg, rec.p, rec.prec);
-                    d2 = rg_density(num, rec);
+        double den = 0;
+        if (go) {
+            rec = rg_rect(M, B.L0, num, regDeg, kc->aliPro, kc->degThre);
+            den = rg_density(num, rec);
+        }
+        if (go && !(den >= kc->denThre)) {   // Refiner :804-880: new tolerance, re-grow from the seed
+            const double pi = kc->pi;
+            const double cenDeg = M.deg[J.p0];
+            double difSum = 0, squSum = 0;
+            int ptNum = 0;
+            for (int k = 0; k < num; k++) {   // :839-853
+                const unsigned int v = B.L0[k];
+                if (rg_dist(sx, sy, (double)rg_px(v), (double)rg_py(v)) < rec.wid) {
+                    double dd = M.deg[(size_t)rg_py(v) * W + rg_px(v)] - cenDeg;
+                    while (dd <= -pi) dd += 2 * pi;
+                    while (dd > pi) dd -= 2 * pi;
+                    difSum += dd;
+                    squSum += dd * dd;
+                    ptNum++;
                 }
             }
-            if (!ok) { rg_vis_clear_list(M, B.vis, B.L2, ev.nG2); return; }
+            const double meanDif = difSum / (ptNum * 1.0);
+            J.degThre2 = 2.0 * sqrt((squSum - 2 * meanDif * difSum) / (ptNum * 1.0) + meanDif * meanDif);
+            rg_vis_clear_list(M, B.vis, B.L0, num);
+            J.regDeg = cenDeg; J.rec = rec; J.stage = 2;
+            ev.nRegrow++;
+            rg_grow_init<false>(M, B, J.g, B.L1, sx, sy, cenDeg, J.degThre2, J.specChunk, 0, npnd, ev);
+            again = true; go = false;
         }
-    }
-    ev.npnd = npnd;
-    const double logNFA = rg_improve(M, rec, ev);
-    (void)lst;
-    // commit list = pixels whose curMap bit is still set (what :242-248 / :259-265 visit); clear the bits
-    if (!ev.usedT) {
-        rg_vis_clear_list(M, B.vis, B.L0, ev.nG1);
-        ev.nCommit = ev.nG1;
     } else {
-        int outN = 0;
-        for (int k = 0; k < ev.nG2; k++) {
-            const unsigned int v = B.L2[k];
-            if (rg_vis_get(M, B.vis, rg_px(v), rg_py(v))) { B.L1[outN++] = v; rg_vis_clr(M, B.vis, rg_px(v), rg_py(v)); }
+        if (num < 0) { rg_vis_clear_list(M, B.vis, B.L1, B.cap - 1); ev.oc = RG_OC_DEFER; go = false; }
+        else {
+            for (int k = 0; k < num; k++) B.L2[k] = B.L1[k];
+            ev.usedT = 1; ev.nG2 = num;
+            if (num < 2) { rg_vis_clear_list(M, B.vis, B.L2, ev.nG2); go = false; }   // :861-864
         }
-        ev.nCommit = outN;
+        if (go) {
+            rec = rg_rect(M, B.L1, num, regDeg, rec.p, rec.prec);
+            double d2 = rg_density(num, rec);
+            if (d2 < kc->denThre) {
+                // RegionRadiusReducer :736-802, in place, with the `i <= num` quirk
+                bool ok = true;
+                if (!(d2 > kc->denThre)) {
+                    const double rad1 = rg_dist(sx, sy, rec.x1, rec.y1), rad2 = rg_dist(sx, sy, rec.x2, rec.y2);
+                    double rad = rad1 > rad2 ? rad1 : rad2;
+                    while (ok && d2 < kc->denThre) {
+                        rad *= 0.75;
+                        int i = 0, nn = num;
+                        B.L1[nn] = 0u;   // slot [num] reads as (0,0)
+                        while (i <= nn && nn > 0) {   // nn <= 0: the reference would index [-1] here (heap underflow, UB)
+                            const unsigned int v = B.L1[i];
+                            if (rg_dist(sx, sy, (double)rg_px(v), (double)rg_py(v)) > rad) {
+                                rg_vis_clr(M, B.vis, rg_px(v), rg_py(v));
+                                B.L1[i] = B.L1[nn - 1];
+                                B.L1[nn - 1] = 0u;
+                                i--;
+                                nn--;
+                            }
+                            i++;
+                        }
+                        num = nn;
+                        ev.nRrr++;
+                        if (num < 2) ok = false;
+                        else {
+                            rec = rg_rect(M, B.L1, num, regDeg, rec.p, rec.prec);
+                            d2 = rg_density(num, rec);
+                        }
+                    }
+                }
+                if (!ok) { rg_vis_clear_list(M, B.vis, B.L2, ev.nG2); go = false; }
+            }
+        }
     }
-    ev.rec = rec; ev.logNFA = logNFA;
-    ev.oc = logNFA <= 0 ? RG_OC_REJECT : RG_OC_ACCEPT;
+    ev.cycRect += RG_CLOCK() - tc; tc = RG_CLOCK();
+    if (go) {
+        const double logNFA = rg_improve(M, rec, ev);
+        // commit list = pixels whose curMap bit is still set (what :242-248 / :259-265 visit); clear the bits
+        if (!ev.usedT) {
+            rg_vis_clear_list(M, B.vis, B.L0, ev.nG1);
+            ev.nCommit = ev.nG1;
+        } else {
+            int outN = 0;
+            for (int k = 0; k < ev.nG2; k++) {
+                const unsigned int v = B.L2[k];
+                if (rg_vis_get(M, B.vis, rg_px(v), rg_py(v))) { B.L1[outN++] = v; rg_vis_clr(M, B.vis, rg_px(v), rg_py(v)); }
+            }
+            ev.nCommit = outN;
+        }
+        ev.rec = rec; ev.logNFA = logNFA;
+        ev.oc = logNFA <= 0 ? RG_OC_REJECT : RG_OC_ACCEPT;
+        ev.cycNfa += RG_CLOCK() - tc;
+    }
+    return again;
+}
+
+// the whole evaluation of one seed by one lane (the lanes of a warp that enter together step side by side)
+RG_HDN void rg_eval_lane(const RgMap& M, const RgLane& B, int p0, int specChunk, RgEval& evOut) {
+    RgJob J;
+    rg_job_begin(M, B, J, p0, specChunk);
+    const unsigned int team = RG_ACTIVEMASK();
+    bool active = true;
+    while (RG_ANY(team, active)) {
+        if (active) {
+            if (J.g.running) { J.ev.nSteps++; J.ev.nStepLanes += RG_POPC(RG_ACTIVEMASK()); rg_grow_step<false>(M, B, J.g); }
+            else active = rg_job_after_grow(M, B, J);
+        }
+    }
+    evOut = J.ev;
 }

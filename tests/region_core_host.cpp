@@ -3,6 +3,7 @@
 // the oracle, so the lanes' arithmetic and control flow are pinned without a GPU.
 #include "region_core.h"
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <vector>
 
@@ -60,6 +61,9 @@ extern "C" int rgcore_lsd(int W, int H, const double* mag, const double* deg, co
             if (sn < M.T) { st[1]++; st[2] += sn; st[3]++; continue; }
         }
         rg_eval_lane(M, B, p0, -1, ev);
+#ifdef RG_COUNT_WORK
+        if (ev.nG1 >= M.regThre) { static long long tp=0,tv=0,tl=0,tc=0,te=0,tpx=0; tp+=ev.nPass; tv+=ev.nVisit; tl+=ev.nLoadPts; tc+=ev.nCand; te++; tpx+=ev.nGrownPx; if (getenv("RG_PRINT") && (te%200==0)) fprintf(stderr,"large evals %lld: px %lld passes %lld visits %lld loadpts %lld cands %lld\n",te,tpx,tp,tv,tl,tc); }
+#endif
         st[1] += ev.nGrows; st[2] += ev.nGrownPx; st[4] += ev.nRegrow; st[5] += ev.nRrr; st[6] += ev.nNfa; st[7] += ev.nNfaPx;
         if (ev.oc == RG_OC_DEFER) return -1;
         if (ev.oc == RG_OC_NOCHANGE) { if (ev.nG1 < M.regThre) st[3]++; continue; }
