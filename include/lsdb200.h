@@ -64,17 +64,15 @@ enum { LSDB_STAGE_STENCIL = 0, LSDB_STAGE_ORDER = 1, LSDB_STAGE_GROW = 2, LSDB_N
 typedef struct {
     long long cells, live_seeds, grows, grown_px, small, regrows, rrr_passes, nfa_calls, nfa_px,
         rejects, accepts, spec_evals, respec_evals, chunks;
-    /* SM cycles summed over the warps of the region pipeline (lane-0 clock64 deltas): cyc_grow = inside the rounds that
-     * evaluate large seeds, cyc_wait = idle, cyc_retire = the frontier warp retiring chunks, cyc_spec = worker passes,
-     * cyc_respec = evaluations at the frontier.  cyc_rect / cyc_nfa / cyc_lane_grow are LANE cycles (summed over the
-     * evaluating lanes) inside RectangleConverter+Refiner / RectangleImprover / RegionGrower. */
+    /* SM cycles summed over the warps of the region pipeline (lane-0 clock64 deltas): time inside
+     * RegionGrower / RectangleConverter / RectangleNFACalculator, waiting for the commit frontier,
+     * in the retire phase, in the speculative phase, and in frontier re-evaluations */
     long long cyc_grow, cyc_rect, cyc_nfa, cyc_wait, cyc_retire, cyc_spec, cyc_respec;
-    /* per map, summed: SM cycles and wall nanoseconds (globaltimer) a CTA spent on the map; rounds of large-seed evaluation */
-    long long cyc_map, ns_map, rounds;
+    /* per map, summed: SM cycles and wall nanoseconds (globaltimer) a CTA spent on the map; and one spare */
+    long long cyc_map, ns_map, spare_;
     /* frontier re-evaluations by cause: never evaluated / parked result invalidated; how many of them committed a region;
-     * parked accept/reject results that were invalidated; evaluations repeated before parking because an earlier seed
-     * had parked over them; evaluations dropped (list / arena overflow); frontier evaluations on the full-size lists */
-    long long rs_none, rs_conflict, rs_commit, rs_lost_commit, rs_requeue, rs_dropped, rs_big, cyc_lane_grow;
+     * parked accept/reject results that were invalidated */
+    long long rs_none, rs_conflict, rs_commit, rs_lost_commit, rs_pad[4];
 } lsdb_stats;
 
 /* ---- context ---- */

@@ -18,7 +18,7 @@ ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "CAPACITY", 4: "TIMEOUT", 5: "NO_DEVICE"}
 STAGES = ("stencil", "order", "grow")
 STAT_FIELDS = ["cells", "live_seeds", "grows", "grown_px", "small", "regrows", "rrr_passes", "nfa_calls", "nfa_px",
                "rejects", "accepts", "spec_evals", "respec_evals", "chunks", "cyc_grow", "cyc_rect", "cyc_nfa", "cyc_wait",
-               "cyc_retire", "cyc_spec", "cyc_respec", "cyc_map", "ns_map", "rounds", "rs_none", "rs_conflict", "rs_commit", "rs_lost_commit", "rs_requeue", "rs_dropped", "rs_big", "cyc_lane_grow"]
+               "cyc_retire", "cyc_spec", "cyc_respec", "cyc_map", "ns_map", "spare_", "rs_none", "rs_conflict", "rs_commit", "rs_lost_commit", "rs_pad0", "rs_pad1", "rs_pad2", "rs_pad3"]
 
 LINE_DTYPE = np.dtype([("k", "f8"), ("b", "f8"), ("dx", "f8"), ("dy", "f8"), ("x1", "f8"), ("y1", "f8"), ("x2", "f8"),
                        ("y2", "f8"), ("len", "f8"), ("orient", "i4"), ("_pad", "i4")])

@@ -49,7 +49,6 @@ struct lsdb_batch {
     uint8_t* src; double* mag; double* deg; double* cosm; double* sinm; unsigned int* state; unsigned short* bins; unsigned int* cells;
     int* labels; LsdbRect* rects; LsdbImgDyn* dyn; LsdbImg* imgsD; int* tileImg; unsigned int* lists;
     int* imgCounter; LsdbLsdConst* kcD; double* gaussDbg; unsigned char* recBuf; unsigned int* banBits;
-    unsigned int* vis; size_t planeWords, visBytes; bool visDirty;   // private curMap planes of the evaluating lanes (region.cu), all zero between runs
     // host (pinned)
     LsdbImgDyn* dynH; LsdbRect* rectsH;
     cudaEvent_t ev[4];
@@ -149,7 +148,7 @@ extern "C" void lsdb_batch_destroy(lsdb_batch* b) {
     cudaSetDevice(b->ctx->device);
     cudaFree(b->src); cudaFree(b->mag); cudaFree(b->deg); cudaFree(b->cosm); cudaFree(b->state); cudaFree(b->bins); cudaFree(b->cells);
     cudaFree(b->labels); cudaFree(b->rects); cudaFree(b->dyn); cudaFree(b->imgsD); cudaFree(b->tileImg); cudaFree(b->lists);
-    cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg); cudaFree(b->recBuf); cudaFree(b->banBits); cudaFree(b->vis);
+    cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg); cudaFree(b->recBuf); cudaFree(b->banBits);
     cudaFreeHost(b->dynH); cudaFreeHost(b->rectsH);
     for (int i = 0; i < 4; i++) cudaEventDestroy(b->ev[i]);
     if (b->ctx->cached == b) b->ctx->cached = 0;
@@ -167,7 +166,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     memset(&b->kc, 0, sizeof b->kc);
     b->ctx = ctx; b->n = n; b->params = *prm; b->ran = false; b->downloaded = false; b->launches = 0;
     b->src = 0; b->mag = 0; b->deg = 0; b->cosm = 0; b->sinm = 0; b->state = 0; b->bins = 0; b->cells = 0; b->labels = 0; b->rects = 0; b->dyn = 0;
-    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->banBits = 0; b->dynH = 0; b->rectsH = 0; b->vis = 0; b->planeWords = 0; b->visBytes = 0; b->visDirty = false;
+    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->banBits = 0; b->dynH = 0; b->rectsH = 0;
     for (int i = 0; i < 4; i++) cudaEventCreate(&b->ev[i]);
     b->maxSeg = maxLines > 0 ? maxLines : 4096;
 
@@ -232,19 +231,20 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         if (bmMax > bmLimit) bmMax = bmLimit;
         b->bmCapWords = maxBanWords <= bmMax ? maxBanWords : 0;
         if (getenv("LSDB_NO_SMEM_BAN")) b->bmCapWords = 0;
-        // Team size (warp 0 of a team retires in order, the others speculate; a one-warp team does both in turn).  All maps of
-        // a batch are resident at once whenever they fit, so the step ends with the slowest map.  The kernel is built for
-        // 16 warps per SM (128 registers): 16-warp teams for up to one map per SM, 8 for two, ... one warp per map for
-        // thousands of small maps (scan rasters).
-        int nw = 1;
-        {
-            const int opts[] = {16, 8, 5, 4, 3, 2, 1};
-            for (int k = 0; k < 7; k++) { nw = opts[k]; if ((long long)sms * (16 / nw) >= n) break; }
-        }
+        // Team size.  All maps of a batch are resident at once whenever they fit, so the step ends with the slowest map;
+        // a bigger team shortens one map's critical path but speculates further past the commit frontier (more grown
+        // pixels thrown away) and shares the SM's L1 among more growers.  Measured on 4096^2 maps: 16 warps for a
+        // handful of maps, 8 around one map per SM, 4 for 256 maps — about 1200 grower warps on the device in total.
+        int nw = 1184 / n;
+        if (nw > LSDB_GROW_WARPS) nw = LSDB_GROW_WARPS;
         // a small map has a short seed list (~ n/300 chunks): a big team then speculates over all of it at once, against
-        // the initial state, and most large regions end up re-evaluated at the frontier
-        const int sizeCap = maxN < 30000 ? 4 : 16;
+        // the initial state, and most large regions end up re-evaluated at the frontier (measured on the bundled maps:
+        // 1377x428 -> 6.4 ms with 16 warps, 5.3 ms with 8)
+        // Teams of 8: with at most one team per SM that build may use 255 registers (no spills), and 8 such warps beat 16
+        // of the 128-register build on every size measured (4096^2: 105 vs 120 ms, 16384^2: 1.77 vs 1.98 s).
+        const int sizeCap = maxN < 30000 ? 4 : 8;
         if (nw > sizeCap) nw = sizeCap;
+        if (nw < 1) nw = 1;   // thousands of small maps (scan rasters): one warp each beats teams of 4 (2048 rasters: 36.6 vs 54.8 ms)
         if (getenv("LSDB_GROW_WARPS")) { int v = atoi(getenv("LSDB_GROW_WARPS")); if (v >= 1 && v <= LSDB_GROW_WARPS) nw = v; }
         b->nWarps = nw;
         // one-warp teams = thousands of small maps: the shared-memory copy of the ban plane would cap the resident maps per SM
@@ -266,15 +266,11 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     AL(b->bins, b->totalN * 2); AL(b->cells, b->totalN * 4); AL(b->labels, b->totalN * 4);
     AL(b->rects, (size_t)n * b->maxSeg * sizeof(LsdbRect)); AL(b->dyn, (size_t)n * sizeof(LsdbImgDyn));
     AL(b->imgsD, (size_t)n * sizeof(LsdbImg)); AL(b->tileImg, (size_t)b->nTiles * sizeof(int));
-    b->arenaCap = 8 * b->listCap < (1 << 14) ? (1 << 14) : (8 * b->listCap > (1 << 15) ? (1 << 15) : 8 * b->listCap);  // per super-chunk in flight
+    b->arenaCap = 8 * b->listCap < (1 << 14) ? (1 << 14) : (8 * b->listCap > (1 << 16) ? (1 << 16) : 8 * b->listCap);  // per super-chunk in flight
     AL(b->lists, (size_t)b->nCtas * lsdb_grow_words_per_cta(b->listCap, b->arenaCap, b->nWarps) * 4);
     AL(b->recBuf, (size_t)b->nCtas * lsdb_grow_rec_bytes_per_cta());
     AL(b->imgCounter, 64); AL(b->kcD, sizeof(LsdbLsdConst)); AL(b->banBits, (b->totalBan + 4) * 4);
-    b->planeWords = ((size_t)maxBanWords + 3) & ~(size_t)3;
-    b->visBytes = (size_t)b->nCtas * lsdb_grow_vis_planes_per_cta(b->nWarps) * b->planeWords * 4;
-    AL(b->vis, b->visBytes + 16);
 #undef AL
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->vis, 0, b->visBytes + 16, ctx->stream);
     b->sinm = b->cosm ? b->cosm + 1 : 0;
     if (e == cudaSuccess) e = cudaMallocHost((void**)&b->dynH, (size_t)n * sizeof(LsdbImgDyn));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&b->rectsH, (size_t)n * b->maxSeg * sizeof(LsdbRect));
@@ -310,7 +306,6 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaMemsetAsync(b->dyn, 0, (size_t)b->n * sizeof(LsdbImgDyn), s));
     CK(ctx, cudaMemsetAsync(b->labels, 0, b->totalN * 4, s));
     CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
-    if (b->visDirty) { CK(ctx, cudaMemsetAsync(b->vis, 0, b->visBytes + 16, s)); b->visDirty = false; }   // the last run was aborted
     CK(ctx, cudaEventRecord(b->ev[0], s));
     lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->banBits, b->gaussDbg);
     CK(ctx, cudaEventRecord(b->ev[1], s));
@@ -318,7 +313,7 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaEventRecord(b->ev[2], s));
     lsdb_launch_grow(s, b->n, b->nCtas, b->nWarps, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->cosm, b->sinm, b->state, b->cells, b->labels, b->rects,
                      b->maxSeg, b->lists, b->listCap, b->arenaCap, b->runAhead, b->recBuf, ctx->lgammaTab, ctx->lgammaN, b->imgCounter, b->banBits,
-                     b->bmCapWords, b->steal, b->vis, b->planeWords);
+                     b->bmCapWords, b->steal);
     CK(ctx, cudaEventRecord(b->ev[3], s));
     CK(ctx, cudaGetLastError());
     b->ran = true; b->downloaded = false; b->launches = 3;
@@ -333,7 +328,6 @@ static int fetch_dyn(lsdb_batch* b) {
     CK(ctx, cudaMemcpyAsync(b->dynH, b->dyn, (size_t)b->n * sizeof(LsdbImgDyn), cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < b->n; i++) {
-        if (b->dynH[i].err) b->visDirty = true;
         if (b->dynH[i].err == LSDB_ERR_TIMEOUT) return fail(ctx, LSDB_ERR_TIMEOUT, "map %s%lld: ordered-commit watchdog fired", "", i);
         if (b->dynH[i].err) return fail(ctx, LSDB_ERR_CAPACITY, "map %s%lld: region list or segment capacity exceeded", "", i);
     }

@@ -39,13 +39,12 @@ struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec l
 //   bit 2 / 3  : pixel belongs to a PARKED (evaluated, not yet retired) accept / reject candidate.  Speculation by
 //                later seeds treats a parked accept as already banned and skips seeds inside either kind; whether
 //                that guess was right is re-checked pixel by pixel when the dependent evaluation retires.
-//   bit 4      : an evaluation in flight has this pixel in its region (seeds under it wait for that evaluation's outcome)
+//   bits 4-19  : pixel is in the region warp w of the owning CTA is currently growing (curMap)
 //   bits 20-31 : seed-list chunk (mod 4096) of the seed whose parked region set bit 2/3 (the earliest one)
 #define LSDB_ST_BAN 1u
 #define LSDB_ST_REJ 2u
 #define LSDB_ST_PACC 4u
 #define LSDB_ST_PREJ 8u
-#define LSDB_ST_GROWING 16u    // a speculative evaluation in flight has taken the pixel into its region (de-duplicates same-wall seeds)
 #define LSDB_ST_WARP_SHIFT 4
 #define LSDB_ST_TAG_SHIFT 20
 
@@ -89,9 +88,8 @@ void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, con
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,
                       unsigned int* lists, int listCap, int arenaCap, int runAhead, unsigned char* recBuf, const double* lgammaTab, int lgammaN,
-                      int* imgCounter, unsigned int* banBits, int bmCapWords, int steal, unsigned int* vis, size_t planeWords);
+                      int* imgCounter, unsigned int* banBits, int bmCapWords, int steal);
 size_t lsdb_grow_rec_bytes_per_cta(void);
-size_t lsdb_grow_vis_planes_per_cta(int warpsPerCta);
 size_t lsdb_grow_words_per_cta(int listCap, int arenaCap, int warpsPerCta);
 void lsdb_launch_lgamma_table(cudaStream_t s, double* tab, int n);
 void lsdb_launch_used_plane(cudaStream_t s, const unsigned int* state, uint8_t* used, int n);
