@@ -103,6 +103,17 @@ def cpu_reference_throughput(size, n_maps, threads, first_gidx=0):
     return dict(seconds=dt, mpix_per_s=n_maps * size * size / dt / 1e6, segments=int(sum(counts)), n_maps=n_maps)
 
 
+def stencil_traffic(n, size):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE lsdb_stencil_kernel launch, from this round's ncu capture
+    (profiles/r2_stencil_traffic.json, written by tools/ncu_summary.py from the .ncu-rep), scaled to this launch's
+    source pixels.  None when no capture of this round is on record."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_stencil_traffic.json")))
+        return float(t["dram_bytes"]) * (n * size * size) / float(t["source_pixels"])
+    except Exception:
+        return None
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -145,6 +156,10 @@ def main():
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=5, help="resident batches that alternate on their own streams")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns --maps-per-gpu maps; strong: the global batch is --maps-per-gpu maps, split over the ranks "
+                         "(BASELINE configs[2] as written: batch 256 sharded over 1/2/4/8 GPUs)")
+    ap.add_argument("--parity-maps", type=int, default=8, help="maps of the timed batch whose segment tables are checked against the CPU oracle (rank 0)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,11 +188,19 @@ def main():
     ctxs = [lsdb.Context(local, st.cuda_stream) for st in streams]
     ctx = ctxs[0]
 
-    n, size = args.maps_per_gpu, args.size
+    size = args.size
+    if args.scaling == "strong":
+        global_n = args.maps_per_gpu                          # strong scaling: ONE batch of --maps-per-gpu maps, split over the ranks
+        first, n = shard.shard_range(global_n, rank, world)
+        if n <= 0:
+            raise SystemExit("bench.py: more ranks than maps")
+    else:
+        n = args.maps_per_gpu
+        global_n = world * n
+        first, cnt = shard.shard_range(global_n, rank, world)   # weak scaling: every rank owns n maps of the global batch
+        assert cnt == n
     host = torch.empty((n, size, size), dtype=torch.uint8).pin_memory()
     hnp = host.numpy()
-    first, cnt = shard.shard_range(world * n, rank, world)   # weak scaling: every rank owns n maps of the global batch
-    assert cnt == n
     for i in range(n):
         hnp[i] = make_map(size, first + i)
     ptrs = [int(hnp[i].ctypes.data) for i in range(n)]
@@ -212,6 +235,19 @@ def main():
     barrier()
     ms_total = max(e0.elapsed_time(ev) for ev in ends)
     clocks = sampler.stop()
+    # ---------------- the bench checks what it times: segment tables of the first maps of the timed batch against the CPU
+    # oracle (bit for bit), before anything else touches the batches.  A mismatch fails the bench.
+    parity_k = 0
+    if rank == 0 and args.parity_maps > 0:
+        import oraclebind
+        got0 = batches[(args.steps - 1) % NB].download(want_rects=True)
+        parity_k = min(args.parity_maps, n)
+        for i in range(parity_k):
+            o = oraclebind.lsd(hnp[i], want_maps=False, want_line_im=False, max_lines=4096)
+            ok = int(got0["counts"][i]) == o["n"] and np.array_equal(got0["rects"][i], o["rects"], equal_nan=True) and \
+                np.array_equal(lsdb.lines_to_array(got0["lines"][i]), o["lines"], equal_nan=True)
+            if not ok:
+                raise SystemExit(f"bench.py: PARITY FAILURE on map {i} of the timed batch: {int(got0['counts'][i])} segments vs {o['n']} from the oracle")
     # one step alone (nothing else on the device): per-stage times from the library's own events on its stream
     batch.run(); batch.sync()
     last = batch.stage_ms()
@@ -219,10 +255,15 @@ def main():
     counts = batch.counts()
     launches_per_step = batch.launches()
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    per_rank = [ms_total / args.steps]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    value = world * src_px / (ms_step * 1e-3) / 1e6
+    total_px = global_n * size * size
+    value = total_px / (ms_step * 1e-3) / 1e6
 
     # ---------------- end to end through the C ABI with host buffers
     # Every step copies its 256 maps from pinned host memory, runs the pipeline and reads the segment tables back.
@@ -249,7 +290,7 @@ def main():
     dt = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * src_px / (float(dt.item()) / e2e_steps) / 1e6
+    e2e_value = total_px / (float(dt.item()) / e2e_steps) / 1e6
     nseg = nseg_box[0]
     d2h = n * 4 * 32 + nseg * 13 * 8   # per-map result records + one rectangle record per segment
     for cw, bw in workers:
@@ -398,10 +439,12 @@ def main():
         achieved = alg_bytes / (last["stencil"] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"synthetic {size}x{size} occupancy grids, batch {n} per GPU (BASELINE configs[2])",
-                       "maps_per_gpu": n, "global_batch": n * world, "parallelism": f"map-sharded x{world}, no collective",
+            "parity_checked_maps": parity_k,
+            "ms_per_step_per_rank": {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "all": per_rank},
+            "config": {"workload": f"synthetic {size}x{size} occupancy grids, global batch {global_n} (BASELINE configs[2]), {n} per GPU",
+                       "maps_per_gpu": n, "global_batch": global_n, "parallelism": f"map-sharded x{world}, no collective",
                        "l2": f"inputs {n * size * size / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
                        "pipelining": f"{NB} resident batches alternate on {NB} streams (value and e2e alike); stage_ms / roofline are one step alone"},
             "segments_per_s": float(segs.item()) / (ms_step * 1e-3), "segments_per_step": float(segs.item()),
@@ -420,7 +463,7 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 256 maps of 4096^2 (profiles/r1z_ncu_full_summary.txt),
                          # scaled to this launch's map count: the extra over the algorithmic bytes is the cos/sin planes of growable
                          # pixels, the u32 state word (instead of the reference's u8 usedMap) and the ban bit plane
-                         "traffic": 13.02e9 * (n * size * size) / (256 * 4096 * 4096) if size == 4096 else None,
+                         "traffic": stencil_traffic(n, size),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": last["stencil"],
                          "share_of_step": last["stencil"] / sum(last.values())},

@@ -84,7 +84,7 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LSDB_ERR_NO_DEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LSDB_ERR_NO_DEVICE;
-    if (prop.major != 10) return LSDB_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+    if (prop.major != 10 || prop.minor != 0) return LSDB_ERR_NO_DEVICE;  // the kernels are built for sm_100a only (not forward compatible)
     lsdb_ctx* c = new lsdb_ctx();
     c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0; c->faAux = 0; c->faAuxHost = 0; c->faAuxCap = 0;
     c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsOutHostCap = 0; c->fsLinesDev = 0; c->fsPtsDev = 0; c->fsIm = 0; c->fsImCap = 0; c->fsTmp = 0; c->fsTmpCap = 0; c->fsMs = 0;
@@ -96,11 +96,18 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
         c->ownStream = true;
     }
     c->lgammaN = 1 << 16;
-    if (cudaMalloc(&c->lgammaTab, sizeof(double) * c->lgammaN) != cudaSuccess) { delete c; return LSDB_ERR_CUDA; }
+    if (cudaMalloc(&c->lgammaTab, sizeof(double) * c->lgammaN) != cudaSuccess) { if (c->ownStream) cudaStreamDestroy(c->stream); delete c; return LSDB_ERR_CUDA; }
     lsdb_launch_lgamma_table(c->stream, c->lgammaTab, c->lgammaN);
+    const cudaError_t launchErr = cudaGetLastError();   // a failed launch is not reported by the synchronize below
     cudaEventCreate(&c->faEv[0]); cudaEventCreate(&c->faEv[1]);
     c->maxGrowCtas = 0;
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFree(c->lgammaTab); delete c; return LSDB_ERR_CUDA; }
+    if (launchErr != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        cudaFree(c->lgammaTab);
+        cudaEventDestroy(c->faEv[0]); cudaEventDestroy(c->faEv[1]);
+        if (c->ownStream) cudaStreamDestroy(c->stream);
+        delete c;
+        return launchErr == cudaErrorNoKernelImageForDevice ? LSDB_ERR_NO_DEVICE : LSDB_ERR_CUDA;
+    }
     *out = c;
     return LSDB_OK;
 }
@@ -172,6 +179,15 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
 
     const int h = gauss_taps(prm->sca, prm->sig, b->kc.taps);
     if (h != 8) { lsdb_batch_destroy(b); return fail(ctx, LSDB_ERR_ARG, "Gaussian half-width %s%lld != 8: only sig/sca = 2 (0.6/0.3) is supported", "", h); }
+    {   // the stencil stages the source window of one 32x32 tile (33 columns / rows with the gradient's neighbour) in shared
+        // memory: ceil(32/sca) + 2 centres plus the 2h taps around them must fit LSDB_SRC_MAX rows and, with the 16-byte
+        // alignment slack, LSDB_SRC_PITCH bytes per row (sca = 0.3: 125 and 140)
+        const int win = x86_d2i(ceil(LSDB_TILE / prm->sca)) + 2 + 2 * h;
+        if (win > LSDB_SRC_MAX || win + 15 > LSDB_SRC_PITCH) {
+            lsdb_batch_destroy(b);
+            return fail(ctx, LSDB_ERR_ARG, "sca too small for the stencil tile%s: source window of %lld pixels per tile edge", "", win);
+        }
+    }
     const double pi = 4.0 * lsdm_atan(1.0);
     b->kc.sca = prm->sca; b->kc.pi = pi; b->kc.h = h; b->kc.pseBin = prm->pseBin;
     b->kc.degThre = prm->angThre / 180.0 * pi;              // :148
@@ -470,14 +486,15 @@ extern "C" int lsdb_lsd(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, c
                         int maxLines, int* nLines, uint8_t* lineIm, uint8_t* mapRemapped) {
     if (!ctx || !map || !prm || !nLines) return fail(ctx, LSDB_ERR_ARG, "lsdb_lsd: bad argument%s");
     lsdb_batch* b = ctx->cached;
+    const int wantSeg = maxLines > 4096 ? maxLines : 4096;   // segment-table capacity of the cached batch: what the caller can take
     if (b && (b->imgs[0].cols != cols || b->imgs[0].rows != rows || memcmp(&b->params, prm, sizeof(double) * 4) != 0 ||
-              b->params.pseBin != prm->pseBin)) {
+              b->params.pseBin != prm->pseBin || b->maxSeg < wantSeg)) {
         lsdb_batch_destroy(b);
         b = 0;
     }
     int rc;
     if (!b) {
-        rc = lsdb_batch_create(ctx, 1, &cols, &rows, prm, 0, &b);
+        rc = lsdb_batch_create(ctx, 1, &cols, &rows, prm, wantSeg, &b);
         if (rc) return rc;
         ctx->cached = b;
     }
@@ -572,6 +589,11 @@ static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_l
     static_assert(sizeof(lsdb_hypothesis) == sizeof(LsdbFaHyp), "layout");
     static_assert(sizeof(lsdb_line) == sizeof(LsdbFaLine), "layout");
     static_assert(sizeof(lsdb_fa_estimate) == sizeof(LsdbFaEst), "layout");
+    if (lineOff[0] != 0 || ptOff[0] != 0) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score: offsets must start at 0%s");
+    for (int f = 0; f < nFrames; f++)
+        if (lineOff[f + 1] < lineOff[f] || ptOff[f + 1] < ptOff[f]) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score: offsets must not decrease (frame %s%lld)", "", f);
+    if ((lineOff[nFrames] > 0 && !scanLines && !devLines) || (ptOff[nFrames] > 0 && !pts && !devPts))
+        return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score: null lines / points with non-zero counts%s");
     CK(ctx, cudaSetDevice(ctx->device));
     // pair filter, LSD/myFA.cpp:29-41 (ignoreScanLength = 40, scanToMapDiff = 0.35; LSD/baseFunc.h:80-82)
     std::vector<LsdbFaTask> tasks;
@@ -588,6 +610,7 @@ static int fa_run(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_l
                 tasks.push_back(t);
             }
         }
+        if (tasks.size() * 4 > (size_t)INT_MAX) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_fa_score: %s%lld tasks exceed 2^31 hypotheses", "", (long long)tasks.size());
         hypOff[f + 1] = (int)tasks.size() * 4;
     }
     const int nTasks = (int)tasks.size();

@@ -50,6 +50,7 @@ struct LsdbRect { double v[13]; };   // x1 y1 x2 y2 wid cX cY deg dx dy p prec l
 
 #define LSDB_TILE 32            // stencil output tile (scaled pixels)
 #define LSDB_SRC_MAX 136        // max source-window edge of one tile
+#define LSDB_SRC_PITCH 160      // bytes per staged source row of a tile (window + 16-byte alignment slack)
 #define LSDB_GROW_WARPS 16
 #define LSDB_CHUNK 32           // seed-list cells per ordered-commit chunk
 #define LSDB_SUPER 8            // chunks a warp claims and speculates on at once (256 cells)

@@ -22,7 +22,7 @@
 // HBM traffic per source pixel: 1 B read + 0.09*(8+8+4 [+16 for growable pixels]) B written.
 #include "lsdb_common.cuh"
 
-#define SRC_PITCH 160
+#define SRC_PITCH LSDB_SRC_PITCH
 #define ROW_WORDS (SRC_PITCH / 32)
 #define GW 33
 #define NT 256

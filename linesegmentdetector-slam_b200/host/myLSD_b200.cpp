@@ -42,10 +42,16 @@ structLSD myLineSegmentDetector(Mat MapGray, int oriMapCol, int oriMapRow, doubl
 
     lsdb_lsd_params prm;
     prm.sca = sca; prm.sig = sig; prm.angThre = angThre; prm.denThre = denThre; prm.pseBin = (int)pseBin; prm._pad = 0;
-    const int cap = 4096;
+    // the reference has no limit on the number of segments: when the table is too small, ask again with a bigger one
+    int cap = 4096;
     std::vector<lsdb_line> lines(cap);
     int n = 0;
-    const int rc = lsdb_lsd(ctx, in.data(), oriMapCol, oriMapRow, &prm, lines.data(), cap, &n, lineIm.data(), remapped.data());
+    int rc = lsdb_lsd(ctx, in.data(), oriMapCol, oriMapRow, &prm, lines.data(), cap, &n, lineIm.data(), remapped.data());
+    while (rc == LSDB_ERR_CAPACITY && cap < (1 << 20)) {
+        cap *= 4;
+        lines.resize(cap);
+        rc = lsdb_lsd(ctx, in.data(), oriMapCol, oriMapRow, &prm, lines.data(), cap, &n, lineIm.data(), remapped.data());
+    }
     if (rc != LSDB_OK) lsdb_host::die("lsdb_lsd", rc);
 
     for (int y = 0; y < oriMapRow; y++) memcpy(MapGray.ptr<uint8_t>(y), &remapped[(size_t)y * oriMapCol], (size_t)oriMapCol);

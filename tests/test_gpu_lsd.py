@@ -131,6 +131,26 @@ def test_full_size_map_vs_oracle(lsdb, ctx):
     b.close()
 
 
+def test_sixteen_full_size_maps_vs_oracle(lsdb, ctx):
+    """Parity at the benchmark configuration (BASELINE configs[2] shape): 16 distinct 4096x4096 maps in ONE batch — the
+    team shape bench.py runs — four of them with walls along row 0 / column 0.  Segment count, rectangles, log-NFA and
+    line tables bit for bit against the oracle, and the work counters (accepts, rejects, live seeds) per map: the
+    angle decisions on the running sums and the NFA tail break rest on wide differential coverage at this size."""
+    seeds = [1001 + 7 * k for k in range(12)] + [2001, 2002, 2003, 2004]
+    maps = [synth.occupancy_grid(4096, 4096, seed=s_, border_walls=(s_ >= 2001)) for s_ in seeds]
+    b = lsdb.Batch(ctx, [(4096, 4096)] * len(maps))
+    b.upload(maps); b.run()
+    got = b.download(want_rects=True)
+    for i, m in enumerate(maps):
+        o = oraclebind.lsd(m, want_maps=False, want_line_im=False)
+        assert got["counts"][i] == o["n"], (seeds[i], got["counts"][i], o["n"])
+        assert np.array_equal(got["rects"][i], o["rects"], equal_nan=True), seeds[i]
+        assert np.array_equal(lsdb.lines_to_array(got["lines"][i]), o["lines"], equal_nan=True), seeds[i]
+        st = b.map_stats(i)
+        assert (st["accepts"], st["rejects"], st["live_seeds"]) == (o["stats"]["accepts"], o["stats"]["rejects"], o["stats"]["live_seeds"]), seeds[i]
+    b.close()
+
+
 def test_scan_rasters_batched_then_associated(lsdb, ctx):
     """BASELINE config 4 at test scale: rasterised lidar scans (myrdp::FeatureScan lineIm of data/Lidar.txt frames, golden
     fixture) go through LSD as one ragged batch — segment tables equal to the unmodified reference's (1e-9) and the oracle's (bit-exact) — and the frames are
@@ -227,6 +247,8 @@ def test_error_paths_fail_loudly_and_leave_the_context_usable(lsdb, ctx, gold):
         lsdb.Batch(ctx, [(m.shape[1], m.shape[0])], sca=0.5)             # Gaussian half-width != 8: only sig/sca = 2 is built
     with pytest.raises(lsdb.LsdbError, match="ARG"):
         lsdb.Batch(ctx, [(0, 10)])
+    with pytest.raises(lsdb.LsdbError, match="ARG"):                     # half-width 8, but a tile's source window would not fit
+        lsdb.Batch(ctx, [(m.shape[1], m.shape[0])], sca=0.2, sig=0.4)    # the stencil's shared-memory staging
     r = ctx.lsd(m)                                                       # still fine
     assert r["n"] == 41
 
