@@ -123,6 +123,13 @@ int lsdb_lsd(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, const lsdb_l
  * (rows*cols u8, BEFORE the LSD remap), in metres, f64, rows*cols.  max_dist = z_occ_max_dis (LSD/baseFunc.h:60, 1 m).
  * Identical to the reference cell for cell, including its FIFO tie-breaking between sources. */
 int lsdb_map_cache(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double max_dist, double* out);
+/* The same with the value of the cells the brush fire never reaches given apart.  The catkin snapshot's three-argument
+ * createMapCache (ROS/lsd/include/myLSD.h:131, ROS/lsd/src/myLSD.cpp:11-127) stores the literal 2 there (:37) where the current
+ * source stores z_occ_max_dis (LSD/myLSD.cpp:37).  Its down / right neighbour tests (`cur_i >= 1`, ROS/lsd/src/myLSD.cpp:86,105)
+ * read one row / column past the map — undefined behaviour; the bounds of the current source (LSD/myLSD.cpp:86,105) are the
+ * defined behaviour and the one implemented. */
+int lsdb_map_cache_fill(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double max_dist, double unreached,
+                        double* out);
 
 /* ---- association scoring ---- */
 /* structScore (LSD/myFA.h:49-54) plus the indices that identify the hypothesis */

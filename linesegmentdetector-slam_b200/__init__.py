@@ -79,6 +79,7 @@ def lib():
         L.lsdb_batch_launches.argtypes = [vp]
         L.lsdb_lsd.argtypes = [vp, vp, ci, ci, C.POINTER(_Params), vp, ci, vp, vp, vp]
         L.lsdb_map_cache.argtypes = [vp, vp, ci, ci, cd, cd, vp]
+        L.lsdb_map_cache_fill.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp]
         L.lsdb_fa_map_create.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(vp)]
         L.lsdb_fa_map_destroy.argtypes = [vp]; L.lsdb_fa_map_destroy.restype = None
         L.lsdb_fa_score.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
@@ -135,12 +136,16 @@ class Context:
         return dict(n=n.value, lines=lines[:n.value].copy(), line_im=im, map_out=rm)
 
 
-def _ctx_map_cache(self, map_u8, res, max_dist=1.0):
-    """mylsd::createMapCache (LSD/myLSD.h:131) through lsdb_map_cache: rows x cols f64 metres."""
+def _ctx_map_cache(self, map_u8, res, max_dist=1.0, unreached=None):
+    """mylsd::createMapCache (LSD/myLSD.h:131) through lsdb_map_cache: rows x cols f64 metres.  `unreached` = the value of the
+    cells the brush fire never reaches when it is not max_dist (the catkin snapshot's 3-argument flavour stores 2)."""
     m = np.ascontiguousarray(map_u8, np.uint8)
     rows, cols = m.shape
     out = np.zeros((rows, cols), np.float64)
-    self.check(lib().lsdb_map_cache(self.h, _p(m), cols, rows, float(res), float(max_dist), _p(out)), "lsdb_map_cache")
+    if unreached is None:
+        self.check(lib().lsdb_map_cache(self.h, _p(m), cols, rows, float(res), float(max_dist), _p(out)), "lsdb_map_cache")
+    else:
+        self.check(lib().lsdb_map_cache_fill(self.h, _p(m), cols, rows, float(res), float(max_dist), float(unreached), _p(out)), "lsdb_map_cache_fill")
     return out
 
 

@@ -519,15 +519,20 @@ extern "C" int lsdb_lsd(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, c
 
 // ------------------------------------------------------------------------------------------------ mapCache
 extern "C" int lsdb_map_cache_device(int device, void* stream, const uint8_t* map, int cols, int rows, double res, double maxDist,
-                                     double* out, char* err, int errLen);
+                                     double unreached, double* out, char* err, int errLen);
 
-extern "C" int lsdb_map_cache(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double maxDist, double* out) {
+extern "C" int lsdb_map_cache_fill(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double maxDist, double unreached,
+                                   double* out) {
     if (!ctx || !map || !out || cols <= 0 || rows <= 0 || cols > 65535 || rows > 65535 || !(res > 0) || !(maxDist >= 0))
         return fail(ctx, LSDB_ERR_ARG, "lsdb_map_cache: bad argument%s");
     char msg[256]; msg[0] = 0;
-    const int rc = lsdb_map_cache_device(ctx->device, (void*)ctx->stream, map, cols, rows, res, maxDist, out, msg, sizeof msg);
+    const int rc = lsdb_map_cache_device(ctx->device, (void*)ctx->stream, map, cols, rows, res, maxDist, unreached, out, msg, sizeof msg);
     if (rc) ctx->err = msg;
     return rc;
+}
+
+extern "C" int lsdb_map_cache(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double maxDist, double* out) {
+    return lsdb_map_cache_fill(ctx, map, cols, rows, res, maxDist, maxDist, out);   // LSD/myLSD.cpp:37
 }
 
 // ------------------------------------------------------------------------------------------------ association

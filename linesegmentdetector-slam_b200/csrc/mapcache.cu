@@ -197,7 +197,7 @@ __global__ void mc_mark_kernel(const unsigned int* __restrict__ nCur, int n, int
 
 struct lsdb_ctx_view { int device; cudaStream_t stream; };   // leading members of lsdb_ctx (api.cu)
 
-extern "C" int lsdb_map_cache_device(int device, void* streamV, const uint8_t* map, int cols, int rows, double res, double maxDist,
+extern "C" int lsdb_map_cache_device(int device, void* streamV, const uint8_t* map, int cols, int rows, double res, double maxDist, double unreached,
                                      double* out, char* err, int errLen) {
     cudaStream_t s = (cudaStream_t)streamV;
 #define MCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, errLen, "lsdb_map_cache: %s (line %d)", cudaGetErrorString(e_), __LINE__); goto fail; } } while (0)
@@ -214,7 +214,7 @@ extern "C" int lsdb_map_cache_device(int device, void* streamV, const uint8_t* m
     for (int k = 0; k < 4; k++) MCK(cudaMalloc(&f[k], n * 4));
     MCK(cudaMalloc(&tileSum, (size_t)maxTiles * 4)); MCK(cudaMalloc(&count, 4));
     MCK(cudaMemcpyAsync(mapD, map, n, cudaMemcpyHostToDevice, s));
-    mc_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mapD, (int)n, maxDist, cache, flag, claim);
+    mc_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mapD, (int)n, unreached, cache, flag, claim);
     {   // level 0: the occupied cells in raster order (:21-38)
         const int nt = (int)((n + MC_TILE - 1) / MC_TILE);
         mc_src_count_kernel<<<nt, MC_BLOCK, 0, s>>>(flag, (int)n, tileSum);

@@ -25,8 +25,13 @@
 
 static_assert(sizeof(structLinesInfo) == sizeof(lsdb_line), "structLinesInfo layout (LSD/baseFunc.h:33-44)");
 
-// The older ROS flavour of the header (ROS/lsd/include/myLSD.h) declares the last argument as `double pseBin`:
-// build this file with -DLSDB_PSEBIN_T=double against that header.
+// The catkin snapshot of the header (ROS/lsd/include/myLSD.h:131-132, used by LSD/main_on_linux.cpp:130,132) declares
+//   Mat createMapCache(Mat MapGray, double res, double z_occ_max_dis);
+//   structLSD myLineSegmentDetector(..., double pseBin);
+// build this file with -DLSDB_ROS_FLAVOUR (implies LSDB_PSEBIN_T=double) against that header for the ROS node.
+#ifdef LSDB_ROS_FLAVOUR
+#define LSDB_PSEBIN_T double
+#endif
 #ifndef LSDB_PSEBIN_T
 #define LSDB_PSEBIN_T int
 #endif
@@ -66,11 +71,36 @@ structLSD myLineSegmentDetector(Mat MapGray, int oriMapCol, int oriMapRow, doubl
         const lsdb_line& s = lines[i];
         L.k = s.k; L.b = s.b; L.dx = s.dx; L.dy = s.dy; L.x1 = s.x1; L.y1 = s.y1; L.x2 = s.x2; L.y2 = s.y2;
         L.len = s.len; L.orient = s.orient;
+#ifdef LSDB_ROS_FLAVOUR
+        // The snapshot's atand is atan(x / 180 * pi) (ROS/lsd/src/baseFunc.cpp:14-16; the current source: atan(x) * 180 / pi),
+        // so its direction fields differ (ROS/lsd/src/myLSD.cpp:289-293,357-358): recomputed with the tree's OWN atand / cosd /
+        // sind, i.e. whatever the node links, from the same slope.
+        double ang = atand(s.k);
+        int orient = 1;
+        if (ang < 0) { ang += 180; orient = -1; }
+        L.dx = cosd(ang); L.dy = sind(ang); L.orient = orient;
+#endif
     }
     return out;
 }
 
-#ifndef LSDB_KEEP_CPU_MAP_CACHE
+#if defined(LSDB_ROS_FLAVOUR) && !defined(LSDB_KEEP_CPU_MAP_CACHE)
+// ROS/lsd/src/myLSD.cpp:11-127: the same brush fire with the truncation distance as an argument; cells it never reaches hold
+// the literal 2 (:37).  The snapshot's down / right neighbour tests read one row / column past the map (:86,:105, undefined
+// behaviour); the bounds of the current source (LSD/myLSD.cpp:86,105) are what is computed here.
+Mat createMapCache(Mat MapGray, double res, double z_occ_max_dis) {
+    lsdb_ctx* ctx = lsdb_host::context();
+    const int rows = MapGray.rows, cols = MapGray.cols;
+    std::vector<uint8_t> in((size_t)rows * cols);
+    for (int y = 0; y < rows; y++) memcpy(&in[(size_t)y * cols], MapGray.ptr<uint8_t>(y), (size_t)cols);
+    std::vector<double> out((size_t)rows * cols);
+    const int rc = lsdb_map_cache_fill(ctx, in.data(), cols, rows, res, z_occ_max_dis, 2.0, out.data());
+    if (rc != LSDB_OK) lsdb_host::die("lsdb_map_cache_fill", rc);
+    Mat mapCache = Mat::zeros(rows, cols, CV_64FC1);
+    for (int y = 0; y < rows; y++) memcpy(mapCache.ptr<double>(y), &out[(size_t)y * cols], sizeof(double) * (size_t)cols);
+    return mapCache;
+}
+#elif !defined(LSDB_KEEP_CPU_MAP_CACHE)
 // The truncated distance map the association scores against; reads MapGray BEFORE the LSD remap (callers run it
 // first, LSD/main_on_windows.cpp:67-70).  Fresh CV_64FC1 Mat, rows x cols, metres.
 Mat createMapCache(Mat MapGray, double res) {
