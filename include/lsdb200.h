@@ -131,6 +131,16 @@ int lsdb_map_cache(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double
 int lsdb_map_cache_fill(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double max_dist, double unreached,
                         double* out);
 
+/* ---- the reference's text files (host only, no device) ---- */
+/* mapParam.txt: `cols rows resol oriX oriY` (LSD/main_on_windows.cpp:28-34) */
+int lsdb_read_map_param(const char* path, int* cols, int* rows, double* resol, double* ori_x, double* ori_y);
+/* mapValue*.txt: rows*cols integers; a pixel = value & 0xFF, as the reference's `%d` into a uint8 slot leaves it (:38-46) */
+int lsdb_read_map_value(const char* path, int cols, int rows, uint8_t* out);
+/* mapCache.txt: rows*cols doubles, whitespace separated, row-major (LSD/test.cpp:11-17); the writer prints %.17g, which the
+ * reference's `%lf` reader turns back into the same doubles */
+int lsdb_read_map_cache(const char* path, int cols, int rows, double* out);
+int lsdb_write_map_cache(const char* path, int cols, int rows, const double* in);
+
 /* ---- association scoring ---- */
 /* structScore (LSD/myFA.h:49-54) plus the indices that identify the hypothesis */
 typedef struct {

@@ -80,6 +80,10 @@ def lib():
         L.lsdb_lsd.argtypes = [vp, vp, ci, ci, C.POINTER(_Params), vp, ci, vp, vp, vp]
         L.lsdb_map_cache.argtypes = [vp, vp, ci, ci, cd, cd, vp]
         L.lsdb_map_cache_fill.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp]
+        L.lsdb_read_map_param.argtypes = [C.c_char_p, vp, vp, vp, vp, vp]
+        L.lsdb_read_map_value.argtypes = [C.c_char_p, ci, ci, vp]
+        L.lsdb_read_map_cache.argtypes = [C.c_char_p, ci, ci, vp]
+        L.lsdb_write_map_cache.argtypes = [C.c_char_p, ci, ci, vp]
         L.lsdb_fa_map_create.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(vp)]
         L.lsdb_fa_map_destroy.argtypes = [vp]; L.lsdb_fa_map_destroy.restype = None
         L.lsdb_fa_score.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
@@ -150,6 +154,37 @@ def _ctx_map_cache(self, map_u8, res, max_dist=1.0, unreached=None):
 
 
 Context.map_cache = _ctx_map_cache
+
+
+def _io_check(rc, what, path):
+    if rc != 0:
+        raise LsdbError(f"{what}({path}): {ERR_NAMES.get(rc, rc)}")
+
+
+def read_map_param(path):
+    """mapParam.txt -> dict(cols, rows, res, ori_x, ori_y)  (LSD/main_on_windows.cpp:28-34)"""
+    c, r = C.c_int(0), C.c_int(0); res, ox, oy = C.c_double(0), C.c_double(0), C.c_double(0)
+    _io_check(lib().lsdb_read_map_param(os.fsencode(path), C.byref(c), C.byref(r), C.byref(res), C.byref(ox), C.byref(oy)), "lsdb_read_map_param", path)
+    return dict(cols=c.value, rows=r.value, res=res.value, ori_x=ox.value, ori_y=oy.value)
+
+
+def read_map_value(path, cols, rows):
+    """mapValue*.txt -> rows x cols u8 (value & 0xFF, LSD/main_on_windows.cpp:38-46)"""
+    out = np.zeros((rows, cols), np.uint8)
+    _io_check(lib().lsdb_read_map_value(os.fsencode(path), cols, rows, _p(out)), "lsdb_read_map_value", path)
+    return out
+
+
+def read_map_cache(path, cols, rows):
+    """mapCache.txt -> rows x cols f64 (LSD/test.cpp:11-17)"""
+    out = np.zeros((rows, cols), np.float64)
+    _io_check(lib().lsdb_read_map_cache(os.fsencode(path), cols, rows, _p(out)), "lsdb_read_map_cache", path)
+    return out
+
+
+def write_map_cache(path, cache):
+    a = np.ascontiguousarray(cache, np.float64)
+    _io_check(lib().lsdb_write_map_cache(os.fsencode(path), a.shape[1], a.shape[0], _p(a)), "lsdb_write_map_cache", path)
 
 
 def _ctx_feature_scan(self, map_res, map_ori_x, map_ori_y, frames, want_rasters=False, capacity=None, raw=False, **rdp):

@@ -49,6 +49,7 @@ struct lsdb_batch {
     uint8_t* src; double* mag; double* deg; double* cosm; double* sinm; unsigned int* state; unsigned short* bins; unsigned int* cells;
     int* labels; LsdbRect* rects; LsdbImgDyn* dyn; LsdbImg* imgsD; int* tileImg; unsigned int* lists;
     int* imgCounter; LsdbLsdConst* kcD; double* gaussDbg; unsigned char* recBuf; unsigned int* banBits;
+    unsigned int* nzBits; int2* bandOf; int2* bandsOfImg; unsigned int* orderTabs; int nBands;   // ordering stage: "mag != 0" bits, row bands, count tables
     // host (pinned)
     LsdbImgDyn* dynH; LsdbRect* rectsH;
     cudaEvent_t ev[4];
@@ -156,6 +157,7 @@ extern "C" void lsdb_batch_destroy(lsdb_batch* b) {
     cudaFree(b->src); cudaFree(b->mag); cudaFree(b->deg); cudaFree(b->cosm); cudaFree(b->state); cudaFree(b->bins); cudaFree(b->cells);
     cudaFree(b->labels); cudaFree(b->rects); cudaFree(b->dyn); cudaFree(b->imgsD); cudaFree(b->tileImg); cudaFree(b->lists);
     cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg); cudaFree(b->recBuf); cudaFree(b->banBits);
+    cudaFree(b->nzBits); cudaFree(b->bandOf); cudaFree(b->bandsOfImg); cudaFree(b->orderTabs);
     cudaFreeHost(b->dynH); cudaFreeHost(b->rectsH);
     for (int i = 0; i < 4; i++) cudaEventDestroy(b->ev[i]);
     if (b->ctx->cached == b) b->ctx->cached = 0;
@@ -173,7 +175,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     memset(&b->kc, 0, sizeof b->kc);
     b->ctx = ctx; b->n = n; b->params = *prm; b->ran = false; b->downloaded = false; b->launches = 0;
     b->src = 0; b->mag = 0; b->deg = 0; b->cosm = 0; b->sinm = 0; b->state = 0; b->bins = 0; b->cells = 0; b->labels = 0; b->rects = 0; b->dyn = 0;
-    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->banBits = 0; b->dynH = 0; b->rectsH = 0;
+    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->banBits = 0; b->dynH = 0; b->rectsH = 0; b->nzBits = 0; b->bandOf = 0; b->bandsOfImg = 0; b->orderTabs = 0; b->nBands = 0;
     for (int i = 0; i < 4; i++) cudaEventCreate(&b->ev[i]);
     b->maxSeg = maxLines > 0 ? maxLines : 4096;
 
@@ -285,8 +287,29 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     b->arenaCap = 8 * b->listCap < (1 << 14) ? (1 << 14) : (8 * b->listCap > (1 << 16) ? (1 << 16) : 8 * b->listCap);  // per super-chunk in flight
     AL(b->lists, (size_t)b->nCtas * lsdb_grow_words_per_cta(b->listCap, b->arenaCap, b->nWarps) * 4);
     AL(b->recBuf, (size_t)b->nCtas * lsdb_grow_rec_bytes_per_cta());
-    AL(b->imgCounter, 64); AL(b->kcD, sizeof(LsdbLsdConst)); AL(b->banBits, (b->totalBan + 4) * 4);
+    AL(b->imgCounter, 64); AL(b->kcD, sizeof(LsdbLsdConst)); AL(b->banBits, (b->totalBan + 4) * 4); AL(b->nzBits, (b->totalBan + 4) * 4);
+    // ordering stage: every map is cut into K bands of rows, one CTA each — enough bands to cover the device a few times
+    // over (a lone 4096^2 map: 38 bands; 256 of them: 3 each), never fewer than 32 rows of work per warp row-run unless the map is small
+    std::vector<int2> bandOfH, bandsOfImgH(n);
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        int K = (4 * sms + n - 1) / n;
+        for (int i = 0; i < n; i++) {
+            int k = K;
+            const int maxK = (b->imgs[i].H + 31) / 32;   // at least one row per warp
+            if (k > maxK) k = maxK;
+            if (k < 1) k = 1;
+            bandsOfImgH[i] = make_int2((int)bandOfH.size(), k);
+            for (int j = 0; j < k; j++) bandOfH.push_back(make_int2(i, j));
+        }
+        b->nBands = (int)bandOfH.size();
+    }
+    AL(b->bandOf, bandOfH.size() * sizeof(int2)); AL(b->bandsOfImg, (size_t)n * sizeof(int2));
+    AL(b->orderTabs, (size_t)b->nBands * lsdb_order_tab_words_per_band() * 4);
 #undef AL
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->bandOf, bandOfH.data(), bandOfH.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->bandsOfImg, bandsOfImgH.data(), (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
     b->sinm = b->cosm ? b->cosm + 1 : 0;
     if (e == cudaSuccess) e = cudaMallocHost((void**)&b->dynH, (size_t)n * sizeof(LsdbImgDyn));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&b->rectsH, (size_t)n * b->maxSeg * sizeof(LsdbRect));
@@ -323,16 +346,16 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaMemsetAsync(b->labels, 0, b->totalN * 4, s));
     CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
     CK(ctx, cudaEventRecord(b->ev[0], s));
-    lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->banBits, b->gaussDbg);
+    lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->banBits, b->nzBits, b->gaussDbg);
     CK(ctx, cudaEventRecord(b->ev[1], s));
-    lsdb_launch_order(s, b->n, b->imgsD, b->dyn, b->kcD, b->mag, b->bins, b->cells);
+    lsdb_launch_order(s, b->n, b->nBands, b->imgsD, b->dyn, b->kcD, b->mag, b->nzBits, b->bandOf, b->bandsOfImg, b->orderTabs, b->cells);
     CK(ctx, cudaEventRecord(b->ev[2], s));
     lsdb_launch_grow(s, b->n, b->nCtas, b->nWarps, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->cosm, b->sinm, b->state, b->cells, b->labels, b->rects,
                      b->maxSeg, b->lists, b->listCap, b->arenaCap, b->runAhead, b->recBuf, ctx->lgammaTab, ctx->lgammaN, b->imgCounter, b->banBits,
                      b->bmCapWords, b->steal);
     CK(ctx, cudaEventRecord(b->ev[3], s));
     CK(ctx, cudaGetLastError());
-    b->ran = true; b->downloaded = false; b->launches = 3;
+    b->ran = true; b->downloaded = false; b->launches = 5;
     return LSDB_OK;
 }
 

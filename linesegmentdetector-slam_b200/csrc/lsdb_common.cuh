@@ -82,9 +82,11 @@ __device__ __forceinline__ int lsdb_x86_d2i(double v) {
 // launchers (defined in the .cu files, called from api.cu)
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
-                         unsigned int* state, unsigned int* banBits, double* gaussOut);
-void lsdb_launch_order(cudaStream_t s, int nImgs, const LsdbImg* imgs, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
-                       const double* mag, unsigned short* bins, unsigned int* cells);
+                         unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut);
+void lsdb_launch_order(cudaStream_t s, int nImgs, int nBands, const LsdbImg* imgs, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
+                       const double* mag, const unsigned int* nzBits, const int2* bandOf, const int2* bandsOfImg, unsigned int* tabs,
+                       unsigned int* cells);
+size_t lsdb_order_tab_words_per_band(void);
 void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, const LsdbImg* imgs, LsdbImgDyn* dyn,
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
                       unsigned int* state, const unsigned int* cells, int* labels, LsdbRect* rects, int maxSeg,

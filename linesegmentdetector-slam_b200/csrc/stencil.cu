@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
                                                           const uint8_t* __restrict__ src, double* __restrict__ mag,
                                                           double* __restrict__ deg, double* __restrict__ cosm,
                                                           double* __restrict__ sinm, unsigned int* __restrict__ state,
-                                                          unsigned int* __restrict__ banBits, double* __restrict__ gaussOut) {
+                                                          unsigned int* __restrict__ banBits, unsigned int* __restrict__ nzBits,
+                                                          double* __restrict__ gaussOut) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StencilSmem& S = *reinterpret_cast<StencilSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
         const int x = x0 + lane, y = y0 + ly;
         const int t = ly * 32 + lane;
         bool banned = true;   // pixels beyond the row end read as banned in the bit plane
+        bool nonzero = false; // ... and as zero in the "mag != 0" plane of the ordering stage
         if (x < x1 && y < y1) {
             double m = 0.0;
             unsigned int st = 0;
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
                 need = true; axis = true;   // row 0 / column 0: mag = deg = 0, growable — cos/sin of 0 for RegionGrower's sums
             }
             S.u.out.magT[t] = m;
+            nonzero = m != 0.0;
             S.u.out.degT[t] = 0.0;
             S.stT[t] = (unsigned char)st;
             banned = st != 0;
@@ -300,7 +303,8 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
         }
         // usedMap==1 as one bit per pixel, row-pitched: the region pipeline keeps this plane in shared memory
         const unsigned int bal = __ballot_sync(0xffffffffu, banned);
-        if (lane == 0 && y < y1) banBits[im.banOff + (size_t)y * im.pw + (x0 >> 5)] = bal;
+        const unsigned int nzb = __ballot_sync(0xffffffffu, nonzero);
+        if (lane == 0 && y < y1) { banBits[im.banOff + (size_t)y * im.pw + (x0 >> 5)] = bal; nzBits[im.banOff + (size_t)y * im.pw + (x0 >> 5)] = nzb; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
@@ -372,8 +376,8 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
 
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
-                         unsigned int* state, unsigned int* banBits, double* gaussOut) {
+                         unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut) {
     cudaFuncSetAttribute(lsdb_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StencilSmem));   // per device, cheap
     if (nTiles > 0)
-        lsdb_stencil_kernel<<<nTiles, NT, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, gaussOut);
+        lsdb_stencil_kernel<<<nTiles, NT, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut);
 }
