@@ -131,6 +131,20 @@ int lsdb_map_cache(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double
 int lsdb_map_cache_fill(lsdb_ctx* ctx, const uint8_t* map, int cols, int rows, double res, double max_dist, double unreached,
                         double* out);
 
+/* ---- one process, several GPUs ---- */
+/* A batch of independent maps split contiguously over the listed devices (the first n % k devices get one map more), one host
+ * thread and one private stream per device, no collective; tables come back in batch order exactly as from one device
+ * (SURVEY.md 8b `lsdb_create(ctx, device_ids[])`, 8e).  The same device may be listed more than once. */
+typedef struct lsdb_multi lsdb_multi;
+int lsdb_multi_create(lsdb_multi** out, const int* device_ids, int n_devices);
+void lsdb_multi_destroy(lsdb_multi* m);
+int lsdb_multi_devices(const lsdb_multi* m);
+const char* lsdb_multi_last_error(const lsdb_multi* m);
+void lsdb_multi_shard(int n_items, int d, int n_devices, int* first, int* count);
+/* counts[n_maps]; lines / rects: [n_maps][max_lines] (nullable) */
+int lsdb_multi_lsd(lsdb_multi* m, int n_maps, const uint8_t* const* maps, const int* cols, const int* rows,
+                   const lsdb_lsd_params* params, int max_lines, int* counts, lsdb_line* lines, lsdb_rect* rects);
+
 /* ---- the reference's text files (host only, no device) ---- */
 /* mapParam.txt: `cols rows resol oriX oriY` (LSD/main_on_windows.cpp:28-34) */
 int lsdb_read_map_param(const char* path, int* cols, int* rows, double* resol, double* ori_x, double* ori_y);
@@ -163,6 +177,13 @@ int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int n_frames, const lsdb_
                   const int* scan_line_off, const double* scan_pts, const int* scan_pt_off,
                   const double* lidar_pose, const double* last_pose, lsdb_hypothesis* out, int max_hyp,
                   int* n_hyp);
+/* The hypotheses the reference keeps (score < keep_below; LSD/myFA.cpp:261-265 keeps < 3), in (frame, scan line, map line,
+ * pairing) order, for any number of frames.  Lines and raster samples go from the caller's buffers straight to the device,
+ * the pair filter runs there, only the kept hypotheses come back.  *n_kept = how many there are (LSDB_ERR_CAPACITY if more
+ * than max_kept), *n_hyp (nullable) = how many were scored. */
+int lsdb_fa_score_kept(lsdb_ctx* ctx, const lsdb_fa_map* m, int n_frames, const lsdb_line* scan_lines, const int* scan_line_off,
+                       const double* scan_pts, const int* scan_pt_off, const double* lidar_pose, const double* last_pose,
+                       double keep_below, lsdb_hypothesis* out, int max_kept, int* n_kept, int* n_hyp);
 /* The per-frame reduction that follows the scoring in FeatureAssociation (LSD/myFA.cpp:65-171, everything before ukf),
  * done on the device so that only one record per frame comes back instead of every hypothesis:
  *   n_kept  : hypotheses with score < 3 (:261); 0 = "no match, start a new chain" (:70-90)

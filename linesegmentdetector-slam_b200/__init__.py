@@ -80,6 +80,11 @@ def lib():
         L.lsdb_lsd.argtypes = [vp, vp, ci, ci, C.POINTER(_Params), vp, ci, vp, vp, vp]
         L.lsdb_map_cache.argtypes = [vp, vp, ci, ci, cd, cd, vp]
         L.lsdb_map_cache_fill.argtypes = [vp, vp, ci, ci, cd, cd, cd, vp]
+        L.lsdb_multi_create.argtypes = [C.POINTER(vp), vp, ci]
+        L.lsdb_multi_destroy.argtypes = [vp]; L.lsdb_multi_destroy.restype = None
+        L.lsdb_multi_last_error.argtypes = [vp]; L.lsdb_multi_last_error.restype = C.c_char_p
+        L.lsdb_multi_shard.argtypes = [ci, ci, ci, vp, vp]; L.lsdb_multi_shard.restype = None
+        L.lsdb_multi_lsd.argtypes = [vp, ci, vp, vp, vp, C.POINTER(_Params), ci, vp, vp, vp]
         L.lsdb_read_map_param.argtypes = [C.c_char_p, vp, vp, vp, vp, vp]
         L.lsdb_read_map_value.argtypes = [C.c_char_p, ci, ci, vp]
         L.lsdb_read_map_cache.argtypes = [C.c_char_p, ci, ci, vp]
@@ -87,6 +92,7 @@ def lib():
         L.lsdb_fa_map_create.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(vp)]
         L.lsdb_fa_map_destroy.argtypes = [vp]; L.lsdb_fa_map_destroy.restype = None
         L.lsdb_fa_score.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+        L.lsdb_fa_score_kept.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, cd, vp, ci, vp, vp]
         L.lsdb_fa_estimate_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]
         L.lsdb_fa_last_ms.argtypes = [vp]; L.lsdb_fa_last_ms.restype = C.c_float
         L.lsdb_feature_scan_frames.argtypes = [vp, cd, cd, cd, C.POINTER(_RdpParams), ci, vp, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp,
@@ -154,6 +160,39 @@ def _ctx_map_cache(self, map_u8, res, max_dist=1.0, unreached=None):
 
 
 Context.map_cache = _ctx_map_cache
+
+
+class MultiContext:
+    """One process, several GPUs: lsdb_multi_* (a batch of maps split contiguously over the devices, one host thread each)."""
+
+    def __init__(self, devices):
+        self.h = C.c_void_p()
+        d = np.asarray(list(devices), np.int32)
+        rc = lib().lsdb_multi_create(C.byref(self.h), _p(d), len(d))
+        if rc != 0:
+            raise LsdbError(f"lsdb_multi_create: {ERR_NAMES.get(rc, rc)}")
+        self.n = len(d)
+
+    def lsd(self, maps, max_lines=4096, want_rects=False, **params):
+        ms = [np.ascontiguousarray(m, np.uint8) for m in maps]
+        n = len(ms)
+        cols = np.array([m.shape[1] for m in ms], np.int32); rows = np.array([m.shape[0] for m in ms], np.int32)
+        ptrs = (C.c_void_p * max(n, 1))(*[m.ctypes.data for m in ms])
+        prm = _Params(**dict(LSD_DEFAULTS, **params))
+        counts = np.zeros(n, np.int32); lines = np.zeros((n, max_lines), LINE_DTYPE)
+        rects = np.zeros((n, max_lines, 13)) if want_rects else None
+        rc = lib().lsdb_multi_lsd(self.h, n, ptrs, _p(cols), _p(rows), C.byref(prm), max_lines, _p(counts), _p(lines), _p(rects))
+        if rc != 0:
+            raise LsdbError(f"lsdb_multi_lsd: {ERR_NAMES.get(rc, rc)}: {lib().lsdb_multi_last_error(self.h).decode()}")
+        out = dict(counts=counts, lines=[lines[i, :counts[i]].copy() for i in range(n)])
+        if want_rects:
+            out["rects"] = [rects[i, :counts[i]].copy() for i in range(n)]
+        return out
+
+    def close(self):
+        if self.h:
+            lib().lsdb_multi_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 def _io_check(rc, what, path):
@@ -406,6 +445,21 @@ class FaMap:
         self.ctx.check(lib().lsdb_fa_score(self.ctx.h, self.h, nf, _p(lines), _p(loff), _p(pts), _p(poff), _p(lid), _p(last),
                                            _p(out), max_hyp, C.byref(n)), "lsdb_fa_score")
         return out[:n.value].copy()
+
+    def pack(self, frames):
+        """the frames as the flat arrays the C ABI takes (do this once when the same frames are scored repeatedly)"""
+        return self._marshal(frames)
+
+    def score_kept(self, frames, keep_below=3.0, max_kept=None):
+        """lsdb_fa_score_kept: only the hypotheses with score < keep_below (what the reference keeps), compacted on the device.
+        `frames` is a list of frame dicts or the tuple pack() returned.  Returns (kept HYP_DTYPE records, hypotheses scored)."""
+        nf, lines, loff, pts, poff, lid, last = frames if isinstance(frames, tuple) else self._marshal(frames)
+        if max_kept is None:
+            max_kept = max(4 * int(loff[-1]) * max(self.n_lines, 1) // 8, 4096)
+        out = np.zeros(max_kept, HYP_DTYPE); nk = C.c_int(0); nh = C.c_int(0)
+        self.ctx.check(lib().lsdb_fa_score_kept(self.ctx.h, self.h, nf, _p(lines), _p(loff), _p(pts), _p(poff), _p(lid), _p(last),
+                                                float(keep_below), _p(out), max_kept, C.byref(nk), C.byref(nh)), "lsdb_fa_score_kept")
+        return out[:nk.value].copy(), nh.value
 
     def estimate(self, frames):
         """Per-frame reduction on the device (lsdb_fa_estimate_frames): one EST_DTYPE record per frame."""

@@ -29,6 +29,8 @@ struct lsdb_ctx {
     void* faDev; size_t faDevCap;
     void* faHost; size_t faHostCap;
     void* faAux; void* faAuxHost; size_t faAuxCap;   // small staging of the device-resident association path
+    void* faIn; size_t faInCap;                      // scan lines / raster samples uploaded by lsdb_fa_score_kept
+    void* faKeep; size_t faKeepCap;                  // kept-hypothesis compaction: offsets + output
     // scan front-end: ragged outputs (device + pinned mirror) and the raster plane
     void* fsOut; void* fsOutHost; size_t fsOutCap, fsOutHostCap;
     void* fsLinesDev; void* fsPtsDev;   // where the last scan call left its lines / samples on the device
@@ -87,7 +89,7 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LSDB_ERR_NO_DEVICE;
     if (prop.major != 10 || prop.minor != 0) return LSDB_ERR_NO_DEVICE;  // the kernels are built for sm_100a only (not forward compatible)
     lsdb_ctx* c = new lsdb_ctx();
-    c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0; c->faAux = 0; c->faAuxHost = 0; c->faAuxCap = 0;
+    c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0; c->faAux = 0; c->faAuxHost = 0; c->faAuxCap = 0; c->faIn = 0; c->faInCap = 0; c->faKeep = 0; c->faKeepCap = 0;
     c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsOutHostCap = 0; c->fsLinesDev = 0; c->fsPtsDev = 0; c->fsIm = 0; c->fsImCap = 0; c->fsTmp = 0; c->fsTmpCap = 0; c->fsMs = 0;
     c->lgammaTab = 0; c->lgammaN = 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LSDB_ERR_NO_DEVICE; }
@@ -122,6 +124,8 @@ extern "C" void lsdb_destroy(lsdb_ctx* c) {
     if (c->faHost) cudaFreeHost(c->faHost);
     if (c->faAux) cudaFree(c->faAux);
     if (c->faAuxHost) cudaFreeHost(c->faAuxHost);
+    if (c->faIn) cudaFree(c->faIn);
+    if (c->faKeep) cudaFree(c->faKeep);
     if (c->fsOut) cudaFree(c->fsOut);
     if (c->fsOutHost) cudaFreeHost(c->fsOutHost);
     if (c->fsIm) cudaFree(c->fsIm);
@@ -294,10 +298,10 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        int K = (4 * sms + n - 1) / n;
+        int K = (12 * sms + n - 1) / n;   // three 16-warp CTAs per SM, four rounds
         for (int i = 0; i < n; i++) {
             int k = K;
-            const int maxK = (b->imgs[i].H + 31) / 32;   // at least one row per warp
+            const int maxK = (b->imgs[i].H + 15) / 16;   // at least one row per warp
             if (k > maxK) k = maxK;
             if (k < 1) k = 1;
             bandsOfImgH[i] = make_int2((int)bandOfH.size(), k);
@@ -348,7 +352,7 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaEventRecord(b->ev[0], s));
     lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->banBits, b->nzBits, b->gaussDbg);
     CK(ctx, cudaEventRecord(b->ev[1], s));
-    lsdb_launch_order(s, b->n, b->nBands, b->imgsD, b->dyn, b->kcD, b->mag, b->nzBits, b->bandOf, b->bandsOfImg, b->orderTabs, b->cells);
+    lsdb_launch_order(s, b->n, b->nBands, b->imgsD, b->dyn, b->kcD, b->mag, b->nzBits, b->bandOf, b->bandsOfImg, b->orderTabs, b->bins, b->cells);
     CK(ctx, cudaEventRecord(b->ev[2], s));
     lsdb_launch_grow(s, b->n, b->nCtas, b->nWarps, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->cosm, b->sinm, b->state, b->cells, b->labels, b->rects,
                      b->maxSeg, b->lists, b->listCap, b->arenaCap, b->runAhead, b->recBuf, ctx->lgammaTab, ctx->lgammaN, b->imgCounter, b->banBits,
@@ -717,8 +721,11 @@ extern "C" int lsdb_fa_estimate_frames(lsdb_ctx* ctx, const lsdb_fa_map* m, int 
 
 // The same reduction for scan lines / raster samples that are already on the device (output of the scan front-end): the pair
 // filter runs there too (count, prefix sum, write), so only the offsets, lidar / last poses go up and the estimates come back.
+// est == NULL: no per-frame reduction.  keptOut != NULL: the hypotheses with score < keepBelow, in (frame, scan line, map line,
+// pairing) order, compacted on the device (*nKept = how many there are, even when only keptCap of them fit).
 static int fa_run_dev(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const int* lineOff, const int* ptOff, const double* lidarPose,
-                      const double* lastPose, lsdb_fa_estimate* est, const LsdbFaLine* devLines, const double* devPts) {
+                      const double* lastPose, lsdb_fa_estimate* est, const LsdbFaLine* devLines, const double* devPts,
+                      lsdb_hypothesis* keptOut = 0, int keptCap = 0, double keepBelow = 3.0, int* nKept = 0, int* nHypOut = 0) {
     CK(ctx, cudaSetDevice(ctx->device));
     const int nL = lineOff[nFrames];
     cudaStream_t s = ctx->stream;
@@ -748,8 +755,10 @@ static int fa_run_dev(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const in
         CK(ctx, cudaMemcpyAsync(&nTasks, scr + nL, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(ctx, cudaStreamSynchronize(s));
     }
+    if (nKept) *nKept = 0;
+    if (nHypOut) *nHypOut = nTasks * 4;
     if (nTasks == 0) {
-        for (int f = 0; f < nFrames; f++) { memset(&est[f], 0, sizeof est[f]); est[f].best_score = est[f].mean_score = INFINITY; }
+        if (est) for (int f = 0; f < nFrames; f++) { memset(&est[f], 0, sizeof est[f]); est[f].best_score = est[f].mean_score = INFINITY; }
         return LSDB_OK;
     }
     if ((long long)nTasks * 4 > INT_MAX) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_scan_estimate_frames: %s%lld tasks exceed 2^31 hypotheses", "", nTasks);
@@ -769,12 +778,33 @@ static int fa_run_dev(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const in
                                (int*)(A + oHoff));
     lsdb_launch_fa(s, nTasks, (LsdbFaTask*)(D + oTasks), devLines, (int*)(A + oLoff), devPts, (int*)(A + oPoff), (double*)(A + oLid),
                    (double*)(A + oLast), m->linesD, m->cacheD, m->cols, m->rows, 4.0 * lsdm_atan(1.0), (LsdbFaHyp*)(D + oOut), D + oPose);
-    lsdb_launch_fa_reduce(s, nFrames, (LsdbFaHyp*)(D + oOut), (int*)(A + oHoff), (LsdbFaEst*)(A + oEst));
+    if (est) lsdb_launch_fa_reduce(s, nFrames, (LsdbFaHyp*)(D + oOut), (int*)(A + oHoff), (LsdbFaEst*)(A + oEst));
+    int* keepScr = 0; LsdbFaHyp* keepDev = 0;
+    if (keptOut) {
+        const size_t oK = al256(4 * lsdb_fa_keep_scratch_ints(nTasks * 4)), need = oK + sizeof(LsdbFaHyp) * (size_t)(keptCap > 0 ? keptCap : 1);
+        if (need > ctx->faKeepCap) {
+            if (ctx->faKeep) cudaFree(ctx->faKeep);
+            ctx->faKeep = 0; ctx->faKeepCap = 0;
+            CK(ctx, cudaMalloc(&ctx->faKeep, need + need / 4));
+            ctx->faKeepCap = need + need / 4;
+        }
+        keepScr = (int*)ctx->faKeep; keepDev = (LsdbFaHyp*)((char*)ctx->faKeep + oK);
+        lsdb_launch_fa_keep(s, nTasks * 4, (LsdbFaHyp*)(D + oOut), keepBelow, keepScr, keepDev, keptCap);
+    }
     CK(ctx, cudaEventRecord(ctx->faEv[1], s));
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpyAsync(AH + oHoff, A + oHoff, auxTotal - oHoff, cudaMemcpyDeviceToHost, s));   // hypothesis offsets + estimates
+    int nk = 0;
+    if (keptOut) CK(ctx, cudaMemcpyAsync(&nk, keepScr + nTasks * 4, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ctx->faMs, ctx->faEv[0], ctx->faEv[1]));
+    if (keptOut) {
+        if (nKept) *nKept = nk;
+        const int take = nk < keptCap ? nk : keptCap;
+        if (take > 0) CK(ctx, cudaMemcpy(keptOut, keepDev, sizeof(LsdbFaHyp) * (size_t)take, cudaMemcpyDeviceToHost));
+        if (nk > keptCap) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_fa_score_kept: %s%lld kept hypotheses exceed max_kept", "", nk);
+    }
+    if (!est) return LSDB_OK;
     memcpy(est, AH + oEst, sizeof(LsdbFaEst) * (size_t)nFrames);
     const int* hypOff = (const int*)(AH + oHoff);
     for (int f = 0; f < nFrames; f++) {
@@ -785,6 +815,34 @@ static int fa_run_dev(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const in
         host_reduce(hv, est[f]);
     }
     return LSDB_OK;
+}
+
+// What the reference keeps of a frame's hypotheses (LSD/myFA.cpp:261-265: score < 3), for any number of frames, with host
+// buffers: lines and raster samples go straight from the caller's memory to the device (no staging copy), the pair filter of
+// :29-41 runs there (count, prefix sum, write), and only the kept hypotheses come back, compacted in launch order.
+extern "C" int lsdb_fa_score_kept(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFrames, const lsdb_line* scanLines, const int* lineOff,
+                                  const double* pts, const int* ptOff, const double* lidarPose, const double* lastPose, double keepBelow,
+                                  lsdb_hypothesis* out, int maxKept, int* nKept, int* nHyp) {
+    if (!ctx || !m || nFrames < 0 || !lineOff || !ptOff || !nKept || !out || maxKept < 0 || (nFrames > 0 && (!lidarPose || !lastPose)))
+        return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score_kept: bad argument%s");
+    if (lineOff[0] != 0 || ptOff[0] != 0) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score_kept: offsets must start at 0%s");
+    for (int f = 0; f < nFrames; f++)
+        if (lineOff[f + 1] < lineOff[f] || ptOff[f + 1] < ptOff[f]) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score_kept: offsets must not decrease (frame %s%lld)", "", f);
+    const int nL = lineOff[nFrames], nP = ptOff[nFrames];
+    if ((nL > 0 && !scanLines) || (nP > 0 && !pts)) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_score_kept: null lines / points with non-zero counts%s");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t oPts = al256(sizeof(LsdbFaLine) * (size_t)nL), need = oPts + al256(16 * (size_t)nP) + 256;
+    if (need > ctx->faInCap) {
+        if (ctx->faIn) cudaFree(ctx->faIn);
+        ctx->faIn = 0; ctx->faInCap = 0;
+        CK(ctx, cudaMalloc(&ctx->faIn, need + need / 4));
+        ctx->faInCap = need + need / 4;
+    }
+    char* I = (char*)ctx->faIn;
+    if (nL > 0) CK(ctx, cudaMemcpyAsync(I, scanLines, sizeof(LsdbFaLine) * (size_t)nL, cudaMemcpyHostToDevice, ctx->stream));
+    if (nP > 0) CK(ctx, cudaMemcpyAsync(I + oPts, pts, 16 * (size_t)nP, cudaMemcpyHostToDevice, ctx->stream));
+    return fa_run_dev(ctx, m, nFrames, lineOff, ptOff, lidarPose, lastPose, 0, (const LsdbFaLine*)I, (const double*)(I + oPts), out, maxKept,
+                      keepBelow, nKept, nHyp);
 }
 
 // ---- scan front-end ----

@@ -284,6 +284,17 @@ __global__ void lsdb_scan_add_kernel(int n, int* __restrict__ out, const int* __
     if (i == 0) out[n] = *total;
 }
 
+// ---- ordered compaction of the hypotheses the reference keeps (score < 3, LSD/myFA.cpp:261-265) ----
+__global__ void lsdb_fa_keep_flag_kernel(int nHyp, const LsdbFaHyp* __restrict__ hyp, double below, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nHyp) flag[i] = hyp[i].score < below ? 1 : 0;
+}
+__global__ void lsdb_fa_keep_write_kernel(int nHyp, const LsdbFaHyp* __restrict__ hyp, double below, const int* __restrict__ off,
+                                          LsdbFaHyp* __restrict__ out, int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nHyp && hyp[i].score < below && off[i] < cap) out[off[i]] = hyp[i];
+}
+
 // tasks in (frame, scan line, map line) order at their offsets; hypOff[f] = 4 * tasks before frame f
 __global__ void lsdb_fa_pair_write_kernel(int nL, int nFrames, const LsdbFaLine* __restrict__ scanLines, const int* __restrict__ lineOff,
                                           const LsdbFaLine* __restrict__ mapLines, int nMap, const int* __restrict__ taskOff,
@@ -315,6 +326,20 @@ void lsdb_launch_fa_pairs_count(cudaStream_t s, int nL, const LsdbFaLine* scanLi
     lsdb_scan_sums_kernel<<<1, FA_SCAN_TILE, 0, s>>>(nTiles, tileSum, total);
     lsdb_scan_add_kernel<<<(nL + 255) / 256, 256, 0, s>>>(nL, taskOff, tileSum, total);
 }
+// scratch ints of lsdb_launch_fa_keep: off[nHyp + 1], tile sums, total
+size_t lsdb_fa_keep_scratch_ints(int nHyp) { return (size_t)nHyp + 1 + (size_t)(nHyp + FA_SCAN_TILE - 1) / FA_SCAN_TILE + 2; }
+// kept hypotheses (score < below) in launch order -> out[0..cap); scratch[nHyp] = their number
+void lsdb_launch_fa_keep(cudaStream_t s, int nHyp, const LsdbFaHyp* hyp, double below, int* scratch, LsdbFaHyp* out, int cap) {
+    if (nHyp <= 0) return;
+    const int nTiles = (nHyp + FA_SCAN_TILE - 1) / FA_SCAN_TILE;
+    int* off = scratch; int* tileSum = scratch + nHyp + 1; int* total = tileSum + nTiles;
+    lsdb_fa_keep_flag_kernel<<<(nHyp + 255) / 256, 256, 0, s>>>(nHyp, hyp, below, off);
+    lsdb_scan_tiles_kernel<<<nTiles, FA_SCAN_TILE, 0, s>>>(nHyp, off, off, tileSum);
+    lsdb_scan_sums_kernel<<<1, FA_SCAN_TILE, 0, s>>>(nTiles, tileSum, total);
+    lsdb_scan_add_kernel<<<(nHyp + 255) / 256, 256, 0, s>>>(nHyp, off, tileSum, total);
+    lsdb_fa_keep_write_kernel<<<(nHyp + 255) / 256, 256, 0, s>>>(nHyp, hyp, below, off, out, cap);
+}
+
 // phase 2: the task list and the per-frame hypothesis offsets
 void lsdb_launch_fa_pairs_write(cudaStream_t s, int nL, int nFrames, const LsdbFaLine* scanLines, const int* lineOff, const LsdbFaLine* mapLines,
                                 int nMap, const int* scratch, LsdbFaTask* tasks, int* hypOff) {

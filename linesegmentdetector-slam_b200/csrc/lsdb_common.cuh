@@ -85,7 +85,7 @@ void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const 
                          unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut);
 void lsdb_launch_order(cudaStream_t s, int nImgs, int nBands, const LsdbImg* imgs, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
                        const double* mag, const unsigned int* nzBits, const int2* bandOf, const int2* bandsOfImg, unsigned int* tabs,
-                       unsigned int* cells);
+                       unsigned short* bins, unsigned int* cells);
 size_t lsdb_order_tab_words_per_band(void);
 void lsdb_launch_grow(cudaStream_t s, int nImgs, int nCtas, int warpsPerCta, const LsdbImg* imgs, LsdbImgDyn* dyn,
                       const LsdbLsdConst* kc, const double* mag, const double* deg, const double* cosm, const double* sinm,
@@ -109,6 +109,8 @@ size_t lsdb_fa_pose_bytes(int nTasks);
 struct LsdbFaEst { int nHyp, nKept; double bx, by, bang, bscore, mx, my, mang, mscore; };  // == lsdb_fa_estimate
 void lsdb_launch_fa_reduce(cudaStream_t s, int nFrames, const LsdbFaHyp* hyp, const int* hypOff, LsdbFaEst* est);
 size_t lsdb_fa_pairs_scratch_ints(int nL);
+size_t lsdb_fa_keep_scratch_ints(int nHyp);
+void lsdb_launch_fa_keep(cudaStream_t s, int nHyp, const LsdbFaHyp* hyp, double below, int* scratch, LsdbFaHyp* out, int cap);
 void lsdb_launch_fa_pairs_count(cudaStream_t s, int nL, const LsdbFaLine* scanLines, const LsdbFaLine* mapLines, int nMap, int* scratch);
 void lsdb_launch_fa_pairs_write(cudaStream_t s, int nL, int nFrames, const LsdbFaLine* scanLines, const int* lineOff, const LsdbFaLine* mapLines,
                                 int nMap, const int* scratch, LsdbFaTask* tasks, int* hypOff);

@@ -121,3 +121,29 @@ def test_fa_estimate_matches_host_reduction(lsdb, ctx):
         some += 1
     assert some >= 6
     fm.close()
+
+
+def test_kept_hypotheses_equal_the_filtered_full_table(lsdb, ctx):
+    """lsdb_fa_score_kept (device pair filter + ordered compaction of score < 3, LSD/myFA.cpp:261-265) returns exactly the rows of
+    lsdb_fa_score with score < 3, in the same order, and reports how many hypotheses were scored; a table that is too small is
+    an error, not a truncation."""
+    gold_fa = np.load(os.path.join(GOLD, "fa_frames.npz"))
+    gold_maps = np.load(os.path.join(GOLD, "bundled_maps.npz"))
+    mc = ctx.map_cache(gold_maps["mapValue/map"], float(gold_maps["mapValue/param"][2]))
+    frames = [dict(scan_lines=gold_fa[f"f{f}/scan_lines"], pts=gold_fa[f"f{f}/pts"], lidar_pose=gold_fa[f"f{f}/lidar_pose"],
+                   last_pose=[-1.0, -1.0, 0.0]) for f in range(int(gold_fa["n_frames"]))] * 3
+    frames.insert(5, dict(scan_lines=np.zeros((0, 10)), pts=np.zeros((0, 2)), lidar_pose=[0.0, 0.0], last_pose=[-1.0, -1.0, 0.0]))   # an empty frame
+    fm = lsdb.FaMap(ctx, mc, gold_fa["map_lines"])
+    full = fm.score(frames)
+    kept, n_hyp = fm.score_kept(fm.pack(frames))
+    want = full[full["score"] < 3.0]
+    assert n_hyp == len(full) and len(kept) == len(want) > 0
+    for k in ("frame", "i_scan", "i_map", "i_pair", "x", "y", "ang", "score"):
+        assert np.array_equal(kept[k], want[k]), k
+    kept5, _ = fm.score_kept(frames, keep_below=5.0)
+    assert len(kept5) == int((full["score"] < 5.0).sum())
+    with pytest.raises(lsdb.LsdbError, match="CAPACITY"):
+        fm.score_kept(frames, max_kept=max(len(want) - 1, 1))
+    none, nh0 = fm.score_kept([frames[5]])
+    assert len(none) == 0 and nh0 == 0
+    fm.close()

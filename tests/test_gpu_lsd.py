@@ -274,6 +274,28 @@ def test_two_devices_in_one_process(lsdb, gold):
         assert np.array_equal(got, gold[n + "/lines"], equal_nan=True), n
 
 
+def test_one_process_several_devices_entry_point(lsdb, gold):
+    """lsdb_multi_lsd: one process drives several devices, one host thread and stream per device, the batch
+    split contiguously.  On a one-GPU box device 0 is listed three times (three contexts, three threads, uneven shards of
+    2/2/1 maps); with more GPUs the first three devices are used.  Tables must equal the goldens in batch order."""
+    import torch
+    nd = torch.cuda.device_count()
+    devs = [0, 0, 0] if nd < 2 else [d % nd for d in range(3)]
+    names = NAMES[:5]
+    mc = lsdb.MultiContext(devs)
+    out = mc.lsd([gold[n + "/map"] for n in names], want_rects=True)
+    for i, n in enumerate(names):
+        assert out["counts"][i] == len(gold[n + "/lines"]), n
+        assert np.array_equal(lsdb.lines_to_array(out["lines"][i]), gold[n + "/lines"], equal_nan=True), n
+    out2 = mc.lsd([gold[NAMES[0] + "/map"]])                     # fewer maps than devices: two empty shards
+    assert out2["counts"][0] == len(gold[NAMES[0] + "/lines"])
+    with pytest.raises(lsdb.LsdbError, match="device 0"):
+        mc.lsd([gold[NAMES[0] + "/map"]], max_lines=3)          # errors carry the device and the library's message
+    mc.close()
+    with pytest.raises(lsdb.LsdbError):
+        lsdb.MultiContext([99])
+
+
 @pytest.mark.parametrize("params", [dict(angThre=30.0), dict(denThre=0.55), dict(pseBin=512), dict(angThre=15.0, denThre=0.8, pseBin=256)])
 def test_non_default_parameters_vs_oracle(lsdb, ctx, gold, params):
     """arguments 6-8 of myLineSegmentDetector (angThre, denThre, pseBin) other than the constants of LSD/baseFunc.h:64-68"""

@@ -75,3 +75,16 @@ def test_world_size_2_gloo_gathers_in_batch_order():
     res = dict(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     assert res == {0: True, 1: True}
+
+
+def test_c_abi_shard_rule_equals_shard_range(lsdb):
+    """lsdb_multi_shard (the split of the one-process multi-device entry point) is shard.shard_range."""
+    import ctypes as C
+    from lsdb200 import shard
+    L = lsdb.lib()
+    for n in (0, 1, 5, 8, 255, 256, 1000):
+        for k in (1, 2, 3, 8):
+            for d in range(k):
+                a, b = C.c_int(-1), C.c_int(-1)
+                L.lsdb_multi_shard(n, d, k, C.byref(a), C.byref(b))
+                assert (a.value, b.value) == shard.shard_range(n, d, k)
