@@ -112,6 +112,19 @@ int lsdb_batch_map_stats(lsdb_batch* b, int i, lsdb_stats* out);
 /* number of kernel launches issued by the last lsdb_batch_run */
 int lsdb_batch_launches(const lsdb_batch* b);
 
+/* ---- LSD: one map tiled over several GPUs (the stages apart) ---- */
+/* For a single-map batch.  Every GPU uploads the whole source map and runs the stencil stage (LSD/myLSD.cpp:135-174,378-484) on
+ * the tile rows [tile_row0, tile_row1) only (a tile row = 32 scaled rows); the Gaussian's halo rows (floor(y/0.3+0.5) +- 8,
+ * :460,469) are read from the GPU's own copy of the source.  The caller then exchanges the row bands of the planes listed by
+ * lsdb_batch_band_planes (NCCL over NVLink: linesegmentdetector-slam_b200/giant.py), takes the max of lsdb_batch_max_grad over
+ * the GPUs — the bins need the GLOBAL maxGrad (:179) — and runs lsdb_batch_run_regions (pseudo-ordering + the sequential seed
+ * loop, :176-272) on the assembled planes; lsdb_batch_download as usual. */
+int lsdb_batch_run_stencil_rows(lsdb_batch* b, int tile_row0, int tile_row1);
+int lsdb_batch_max_grad(lsdb_batch* b, int set, double* value);   /* set = 0: read, 1: write */
+int lsdb_batch_band_planes(lsdb_batch* b, int max_planes, void** dev_ptrs, long long* row_bytes, int* n_planes, int* tile_rows,
+                           int* rows_per_tile);
+int lsdb_batch_run_regions(lsdb_batch* b);
+
 /* ---- LSD: one map, host buffers in / host buffers out (what the myLSD.h wrapper calls) ---- */
 /* map is NOT modified; map_remapped (nullable) receives the in-place remap the reference applies to
  * its caller's Mat (LSD/myLSD.cpp:135-142); line_im (nullable) = rows*cols u8. */

@@ -365,6 +365,74 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
 
 extern "C" int lsdb_batch_launches(const lsdb_batch* b) { return b ? b->launches : 0; }
 
+// ---- the stages apart: one map tiled over several GPUs (BASELINE configs[4]) ----
+// Every GPU holds the whole source map (its band plus the Gaussian's halo rows are all it reads) and runs the stencil stage on
+// a band of tile rows; the bands of the planes are then exchanged (NCCL, by the caller), the largest gradient is the max over
+// the GPUs (LSD/myLSD.cpp:179 needs the GLOBAL maxGrad before binning), and the ordering + region stages run on the assembled
+// planes: the seed loop is one sequential chain over the whole map (:218-272), so regions that cross bands need no merge.
+extern "C" int lsdb_batch_run_stencil_rows(lsdb_batch* b, int tileRow0, int tileRow1) {
+    if (!b) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    if (b->n != 1) return fail(ctx, LSDB_ERR_ARG, "lsdb_batch_run_stencil_rows: single-map batches only%s");
+    const LsdbImg& im = b->imgs[0];
+    if (tileRow0 < 0 || tileRow1 > im.tilesY || tileRow0 > tileRow1) return fail(ctx, LSDB_ERR_ARG, "lsdb_batch_run_stencil_rows: bad tile-row range%s");
+    cudaStream_t s = ctx->stream;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemsetAsync(b->dyn, 0, sizeof(LsdbImgDyn), s));
+    CK(ctx, cudaMemsetAsync(b->labels, 0, b->totalN * 4, s));
+    CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
+    CK(ctx, cudaEventRecord(b->ev[0], s));
+    lsdb_launch_stencil(s, (tileRow1 - tileRow0) * im.tilesX, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state,
+                        b->banBits, b->nzBits, b->gaussDbg, tileRow0 * im.tilesX);
+    CK(ctx, cudaEventRecord(b->ev[1], s));
+    CK(ctx, cudaGetLastError());
+    b->ran = false; b->downloaded = false; b->launches = 1;
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_max_grad(lsdb_batch* b, int set, double* value) {
+    if (!b || !value || b->n != 1) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (set) { if (!(*value >= 0.0)) return LSDB_ERR_ARG; CK(ctx, cudaMemcpyAsync(&b->dyn[0].maxGradBits, value, 8, cudaMemcpyHostToDevice, ctx->stream)); }
+    else CK(ctx, cudaMemcpyAsync(value, &b->dyn[0].maxGradBits, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSDB_OK;
+}
+
+// the row-major planes the stencil stage writes, for the band exchange: device pointer and bytes per scaled row of map 0
+extern "C" int lsdb_batch_band_planes(lsdb_batch* b, int maxPlanes, void** ptrs, long long* rowBytes, int* nPlanes, int* tileRows, int* rowsPerTile) {
+    if (!b || !ptrs || !rowBytes || !nPlanes || b->n != 1 || maxPlanes < 6) return LSDB_ERR_ARG;
+    const LsdbImg& im = b->imgs[0];
+    ptrs[0] = b->mag + im.nOff; rowBytes[0] = 8ll * im.W;
+    ptrs[1] = b->deg + im.nOff; rowBytes[1] = 8ll * im.W;
+    ptrs[2] = b->cosm + 2 * im.nOff; rowBytes[2] = 16ll * im.W;
+    ptrs[3] = b->state + im.nOff; rowBytes[3] = 4ll * im.W;
+    ptrs[4] = b->banBits + im.banOff; rowBytes[4] = 4ll * im.pw;
+    ptrs[5] = b->nzBits + im.banOff; rowBytes[5] = 4ll * im.pw;
+    *nPlanes = 6;
+    if (tileRows) *tileRows = im.tilesY;
+    if (rowsPerTile) *rowsPerTile = LSDB_TILE;
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_batch_run_regions(lsdb_batch* b) {
+    if (!b) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    cudaStream_t s = ctx->stream;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaEventRecord(b->ev[1], s));
+    lsdb_launch_order(s, b->n, b->nBands, b->imgsD, b->dyn, b->kcD, b->mag, b->nzBits, b->bandOf, b->bandsOfImg, b->orderTabs, b->bins, b->cells);
+    CK(ctx, cudaEventRecord(b->ev[2], s));
+    lsdb_launch_grow(s, b->n, b->nCtas, b->nWarps, b->imgsD, b->dyn, b->kcD, b->mag, b->deg, b->cosm, b->sinm, b->state, b->cells, b->labels, b->rects,
+                     b->maxSeg, b->lists, b->listCap, b->arenaCap, b->runAhead, b->recBuf, ctx->lgammaTab, ctx->lgammaN, b->imgCounter, b->banBits,
+                     b->bmCapWords, b->steal);
+    CK(ctx, cudaEventRecord(b->ev[3], s));
+    CK(ctx, cudaGetLastError());
+    b->ran = true; b->downloaded = false; b->launches += 4;
+    return LSDB_OK;
+}
+
 static int fetch_dyn(lsdb_batch* b) {
     lsdb_ctx* ctx = b->ctx;
     CK(ctx, cudaSetDevice(ctx->device));

@@ -82,7 +82,7 @@ __device__ __forceinline__ int lsdb_x86_d2i(double v) {
 // launchers (defined in the .cu files, called from api.cu)
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
-                         unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut);
+                         unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase = 0);
 void lsdb_launch_order(cudaStream_t s, int nImgs, int nBands, const LsdbImg* imgs, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
                        const double* mag, const unsigned int* nzBits, const int2* bandOf, const int2* bandsOfImg, unsigned int* tabs,
                        unsigned short* bins, unsigned int* cells);

@@ -93,13 +93,14 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
                                                           double* __restrict__ deg, double* __restrict__ cosm,
                                                           double* __restrict__ sinm, unsigned int* __restrict__ state,
                                                           unsigned int* __restrict__ banBits, unsigned int* __restrict__ nzBits,
-                                                          double* __restrict__ gaussOut) {
+                                                          double* __restrict__ gaussOut, int tileBase) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StencilSmem& S = *reinterpret_cast<StencilSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int imgIdx = tileImg[blockIdx.x];
+    const int tileIdx = blockIdx.x + tileBase;   // a launch may cover a range of tiles only (one map tiled over several GPUs)
+    const int imgIdx = tileImg[tileIdx];
     const LsdbImg im = imgs[imgIdx];
-    const int lt = blockIdx.x - im.tile0;
+    const int lt = tileIdx - im.tile0;
     const int tx = lt % im.tilesX, ty = lt / im.tilesX;
     const int x0 = tx * LSDB_TILE, y0 = ty * LSDB_TILE;
     const int x1 = min(x0 + LSDB_TILE, im.W), y1 = min(y0 + LSDB_TILE, im.H);
@@ -376,8 +377,8 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
 
 void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
-                         unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut) {
+                         unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase) {
     cudaFuncSetAttribute(lsdb_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StencilSmem));   // per device, cheap
     if (nTiles > 0)
-        lsdb_stencil_kernel<<<nTiles, NT, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut);
+        lsdb_stencil_kernel<<<nTiles, NT, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase);
 }

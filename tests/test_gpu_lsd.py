@@ -274,6 +274,42 @@ def test_two_devices_in_one_process(lsdb, gold):
         assert np.array_equal(got, gold[n + "/lines"], equal_nan=True), n
 
 
+def test_staged_single_map_path_on_one_gpu(lsdb, ctx, gold):
+    """The pieces of the tiled single-map path (SURVEY §8e, configs[4]) without NCCL: two batches on one GPU play two ranks —
+    each runs the stencil stage on its band of tile rows, the bands are copied into rank 0's planes (what giant.py does with
+    NCCL broadcasts), maxGrad becomes the max of the two, the region stages run on the assembled planes.  Equal to the goldens."""
+    import torch
+    from lsdb200 import giant
+    for name in ("mapValue_aisle1", "mapValue"):
+        m = gold[name + "/map"]
+        bs = [lsdb.Batch(ctx, [(m.shape[1], m.shape[0])]) for _ in range(2)]
+        for b in bs:
+            b.upload([m])
+        planes = [giant.band_planes(b) for b in bs]
+        tile_rows, rpt = planes[0][1], planes[0][2]
+        H = bs[0].scaled(0)[1]
+        bands = [giant.band_rows(tile_rows, rpt, H, r, 2) for r in range(2)]
+        assert bands[0][1] > 0 and bands[1][1] > 0 and bands[0][3] == bands[1][2] and bands[1][3] == H
+        for r, b in enumerate(bs):
+            giant.run_stencil_rows(b, bands[r][0], bands[r][0] + bands[r][1])
+        g = [giant.max_grad(b) for b in bs]
+        giant.max_grad(bs[0], max(g))
+        y0, y1 = bands[1][2], bands[1][3]
+        for (p0, rb), (p1, _rb) in zip(planes[0][0], planes[1][0]):
+            dst = torch.as_tensor(giant._DevView(p0, rb * H), device="cuda"); src = torch.as_tensor(giant._DevView(p1, rb * H), device="cuda")
+            dst[y0 * rb:y1 * rb].copy_(src[y0 * rb:y1 * rb])
+        torch.cuda.synchronize()
+        giant.run_regions(bs[0])
+        got = bs[0].download(want_rects=True)
+        assert got["counts"][0] == len(gold[name + "/lines"])
+        assert np.array_equal(lsdb.lines_to_array(got["lines"][0]), gold[name + "/lines"], equal_nan=True)
+        pl = bs[0].planes(0)
+        assert np.array_equal(pl["used"], gold[name + "/used"]) and np.array_equal(pl["seeds"], gold[name + "/seeds"])
+        assert pl["max_grad"] == max(g) and min(g) > 0
+        for b in bs:
+            b.close()
+
+
 def test_one_process_several_devices_entry_point(lsdb, gold):
     """lsdb_multi_lsd: one process drives several devices, one host thread and stream per device, the batch
     split contiguously.  On a one-GPU box device 0 is listed three times (three contexts, three threads, uneven shards of
