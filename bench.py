@@ -144,6 +144,91 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}))
 
 
+def run_giant(args, rank, world, local):
+    """BASELINE configs[4]: ONE synthetic map (seed 5000) tiled over the ranks — row bands of the stencil stage, NCCL exchange
+    of the bands, max-all-reduce of maxGrad, ordering + the sequential seed loop on rank 0 (giant.lsd_tiled).  A step = the
+    whole map once; value = source Mpixel/s with the map resident, e2e adds the H2D of the map on every rank and the D2H of
+    the tables.  The result of the last step is compared with the CPU oracle on rank 0 (unless --parity-maps 0)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from __graft_entry__ import load_package
+    lsdb = load_package()
+    from lsdb200 import giant
+    import synth
+    size = args.giant_size
+    host = torch.from_numpy(synth.occupancy_grid(size, size, seed=5000)).pin_memory()
+    m = host.numpy()
+    torch.cuda.set_stream(torch.cuda.Stream())
+    ctx = lsdb.Context(local, torch.cuda.current_stream().cuda_stream)
+    for _ in range(max(args.warmup, 1)):
+        out, info = giant.lsd_tiled(ctx, m, rank, world)
+    sampler = ClockSampler(local); sampler.start()
+    ts, infos = [], []
+    for _ in range(args.steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out, info = giant.lsd_tiled(ctx, m, rank, world)
+        torch.cuda.synchronize()
+        ts.append((time.time() - t0) * 1e3); infos.append(info)
+    clocks = sampler.stop()
+    t = torch.tensor([float(np.mean([i["total_ms"] for i in infos])), float(np.mean(ts)), float(np.mean([i["stencil_ms"] for i in infos]))],
+                     dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e, ms_stencil = (float(x) for x in t.tolist())
+    sent = torch.tensor([float(infos[-1]["bytes_sent_by_this_rank"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sent)
+    if rank == 0:
+        parity = None
+        if args.parity_maps > 0:
+            import oraclebind
+            o = oraclebind.lsd(m, want_maps=False, want_line_im=False, max_lines=65536)
+            parity = bool(int(out["counts"][0]) == o["n"] and np.array_equal(out["rects"][0], o["rects"], equal_nan=True))
+            if not parity:
+                raise SystemExit("bench.py: PARITY FAILURE on the tiled map")
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        W = int(size * 0.3); band_px = (infos[-1]["band_rows"][1] - infos[-1]["band_rows"][0]) * W
+        alg = size * size * (infos[-1]["band_rows"][1] - infos[-1]["band_rows"][0]) / infos[-1]["scaled_rows"] + 17 * band_px
+        line = {"metric": METRIC, "value": size * size / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "parity_checked_maps": 1 if parity else 0,
+                "config": {"workload": f"ONE synthetic {size}x{size} occupancy grid tiled over {world} GPU(s) (BASELINE configs[4])",
+                           "partition": "row bands of whole tile rows (32 scaled rows); whole source on every GPU, no halo exchange",
+                           "l2": f"the map's planes ({36.25 * W * W / 1e6:.0f} MB) exceed the 126 MB L2"},
+                "segments_per_step": int(out["counts"][0]),
+                "stage_ms": {"stencil_band_max_over_ranks": ms_stencil, "exchange": infos[-1]["exchange_ms"], "regions_rank0": infos[-1]["regions_ms"]},
+                "exchange": {"collectives": "all_reduce(MAX, 1 x f64) + one broadcast per band and plane (in-place all-gather)",
+                             "bytes_sent_all_ranks": float(sent.item()), "bytes_per_scaled_row": infos[-1]["bytes_per_scaled_row"]},
+                "e2e": {"value": size * size / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": size * size,
+                        "d2h_bytes_per_step": int(out["counts"][0]) * 13 * 8 + 128,
+                        "how": "Batch create + lsdb_batch_upload of the whole map from pinned host memory on every rank + tiled run + download on rank 0"},
+                "gpu_launches": 5 * args.steps,
+                "clocks": clocks,
+                "roofline": {"kernel": "lsdb_stencil_kernel on this rank's band", "bound": "hbm", "achieved": alg / (ms_stencil * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": alg / (ms_stencil * 1e-3) / 1e9 / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": ms_stencil},
+                "note": "the seed loop is one sequential chain over the map: the region stage runs on rank 0 and does not shrink with the GPU count"}
+        if not args.no_cpu_baseline and args.parity_maps > 0:
+            t0 = time.time(); oraclebind.lsd(m, want_maps=False, want_line_im=False, max_lines=65536); dt1 = time.time() - t0
+            line["cpu_baseline"] = {"value": size * size / dt1 / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"the whole map once, oracle C port, {dt1:.1f} s"}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +244,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank owns --maps-per-gpu maps; strong: the global batch is --maps-per-gpu maps, split over the ranks "
                          "(BASELINE configs[2] as written: batch 256 sharded over 1/2/4/8 GPUs)")
+    ap.add_argument("--workload", default="batch", choices=["batch", "giant"],
+                    help="batch: BASELINE configs[2] (the headline); giant: ONE --giant-size^2 map tiled over the ranks (configs[4])")
+    ap.add_argument("--giant-size", type=int, default=16384)
     ap.add_argument("--parity-maps", type=int, default=8, help="maps of the timed batch whose segment tables are checked against the CPU oracle (rank 0)")
     args = ap.parse_args()
 
@@ -166,6 +254,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "giant":
+        run_giant(args, rank, world, local)
         return
 
     import torch

@@ -65,9 +65,13 @@ def lsd_tiled(ctx, map_u8, rank, world, max_lines=65536, want_rects=True):
     H = b.scaled(0)[1]
     stream = torch.cuda.current_stream()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
     ev[0].record(stream)
     t0, cnt, y0, y1 = band_rows(tile_rows, rpt, H, rank, world)
     run_stencil_rows(b, t0, t0 + cnt)
+    # the library launches on the context's stream, NCCL on torch's: unless the caller made them the same stream (pass
+    # torch.cuda.current_stream().cuda_stream of a NON-default stream to Context), order them through the host
+    torch.cuda.synchronize()
     ev[1].record(stream)
     sent = 0
     if world > 1:
@@ -82,6 +86,7 @@ def lsd_tiled(ctx, map_u8, rank, world, max_lines=65536, want_rects=True):
                     dist.broadcast(view[ry0 * rb:ry1 * rb], src=r)   # in-place all-gather of the row bands over NVLink
                     if r == rank:
                         sent += (ry1 - ry0) * rb
+    torch.cuda.synchronize()
     ev[2].record(stream)
     out = None
     if rank == 0:

@@ -29,6 +29,7 @@ def main():
     from lsdb200 import giant
     import synth
     m = synth.occupancy_grid(a.size, a.size, seed=a.seed)
+    torch.cuda.set_stream(torch.cuda.Stream())                # a real stream: handle 0 would make the library create its own
     ctx = lsdb.Context(local, torch.cuda.current_stream().cuda_stream)
     giant.lsd_tiled(ctx, m, rank, world)                      # warm-up (allocations, NCCL channels)
     out, info = giant.lsd_tiled(ctx, m, rank, world)
