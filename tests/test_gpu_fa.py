@@ -97,10 +97,16 @@ def test_fa_estimate_matches_host_reduction(lsdb, ctx):
                    last_pose=[-1.0, -1.0, 0.0]) for f in range(nf)]
     frames.append(dict(scan_lines=np.zeros((0, 10)), pts=np.zeros((0, 2)), lidar_pose=[0, 0], last_pose=[-1, -1, 0]))   # no hypotheses
     frames.append(dict(frames[0], last_pose=[1e6, 1e6, 0.0]))                                                            # everything gated out
+    # a frame that keeps more hypotheses than the device sort holds (2048): its scan lines repeated — the reduction of that
+    # frame then runs on the host from the device's scores (api.cu: est.n_kept < 0), and must give the same numbers
+    big = max(range(nf), key=lambda f: int((g[f"f{f}/val"][:, 3] < 3).sum()))
+    reps = 2048 // max(int((g[f"f{big}/val"][:, 3] < 3).sum()), 1) + 2
+    frames.append(dict(frames[big], scan_lines=np.tile(frames[big]["scan_lines"], (reps, 1))))
     fm = lsdb.FaMap(ctx, mc, g["map_lines"])
     hyp = fm.score(frames)
     est = fm.estimate(frames)
     assert len(est) == len(frames)
+    assert int((hyp[hyp["frame"] == len(frames) - 1]["score"] < 3).sum()) > 2048
     some = 0
     for f in range(len(frames)):
         h = hyp[hyp["frame"] == f]

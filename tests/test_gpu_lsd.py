@@ -55,6 +55,22 @@ def test_bundled_maps_batched_bit_exact(lsdb, ctx, gold):
     b.close()
 
 
+def test_the_two_further_bundled_maps(lsdb, ctx):
+    """BASELINE configs[1] 'all bundled maps': the distinct maps of data_20190513 / data_20190514 against the reference's goldens"""
+    from test_oracle import _extra_maps
+    items = list(_extra_maps())
+    b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for _, m, _ in items])
+    b.upload([m for _, m, _ in items]); b.run()
+    got = b.download()
+    for i, (name, m, g) in enumerate(items):
+        pl = b.planes(i)
+        assert got["counts"][i] == len(g[name + "/lines"])
+        assert np.array_equal(lsdb.lines_to_array(got["lines"][i]), g[name + "/lines"], equal_nan=True)
+        assert np.array_equal(pl["used"], g[name + "/used"]) and np.array_equal((pl["labels"] & 0xFF).astype(np.uint8), g[name + "/reg_idx"])
+        assert np.array_equal(pl["seeds"], g[name + "/seeds"])
+    b.close()
+
+
 def test_single_map_call_matches_reference_entry_point(lsdb, ctx, gold):
     """lsdb_lsd = the body behind mylsd::myLineSegmentDetector (config 1)."""
     m = gold["mapValue/map"]
