@@ -432,8 +432,16 @@ def main():
         # (the frames packed once into the flat arrays of the C ABI), kept hypotheses out: lsdb_fa_score_kept
         packed = fm.pack(frames)
         # ... in pinned host memory, like the maps of the main leg (the C ABI takes any host pointer; pageable costs ~3x here)
-        pins = [torch.from_numpy(a).pin_memory() if isinstance(a, np.ndarray) else a for a in packed]
-        packed = tuple(t.numpy() if isinstance(t, torch.Tensor) else t for t in pins)
+        pins = []   # keeps the pinned storage alive
+
+        def _pin(a):
+            if not isinstance(a, np.ndarray) or a.size == 0:
+                return a
+            t_ = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+            pins.append(t_)
+            return t_.numpy().view(a.dtype).reshape(a.shape)
+
+        packed = tuple(_pin(a) for a in packed)
         kept, n_scored = fm.score_kept(packed)                                           # warm-up: staging buffers
         t0 = time.time(); kept, n_scored = fm.score_kept(packed); dt_fa = time.time() - t0
         assert n_scored == len(hyp) and len(kept) == int((hyp["score"] < 3.0).sum())     # the bench checks what it times
