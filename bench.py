@@ -244,6 +244,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank owns --maps-per-gpu maps; strong: the global batch is --maps-per-gpu maps, split over the ranks "
                          "(BASELINE configs[2] as written: batch 256 sharded over 1/2/4/8 GPUs)")
+    ap.add_argument("--e2e-line-images", default="auto", choices=["auto", "on", "off"],
+                    help="the end-to-end leg also produces every map's lineIm (rasterised on the device, copied to pinned host memory) — "
+                         "the reference's call returns it (LSD/myLSD.cpp:296-355); auto = when the host has the memory for the buffers")
     ap.add_argument("--workload", default="batch", choices=["batch", "giant"],
                     help="batch: BASELINE configs[2] (the headline); giant: ONE --giant-size^2 map tiled over the ranks (configs[4])")
     ap.add_argument("--giant-size", type=int, default=16384)
@@ -363,27 +366,47 @@ def main():
     workers = list(zip(ctxs, batches))
     e2e_steps = NB * max(1, (args.steps + NB - 1) // NB)  # a multiple of the worker count
     nseg_box = [0] * NB
+    # lineIm of every map, too (what the reference's call returns besides the table): one pinned output buffer per worker
+    want_im = args.e2e_line_images == "on"
+    if args.e2e_line_images == "auto":
+        try:
+            import psutil
+            want_im = psutil.virtual_memory().available / max(world, 1) > (NB * n * size * size) * 2 + (16 << 30)   # every rank allocates its own
+        except Exception:
+            want_im = False
+    im_bufs = [torch.empty((n, size, size), dtype=torch.uint8).pin_memory() for _ in range(NB)] if want_im else []
+    im_views = [[bf.numpy()[i] for i in range(n)] for bf in im_bufs]
 
-    def e2e_worker(w, k):
+    def e2e_worker(w, k, with_im):
         cw, bw = workers[w]
         for _ in range(k):
             bw.upload(ptrs); bw.run(); out_w = bw.download()
+            if with_im:
+                bw.line_images(im_views[w])
             nseg_box[w] = int(out_w["counts"].sum())
 
-    for w in range(NB):
-        e2e_worker(w, 1)                             # warm-up: allocations, first-touch
-    barrier()
-    t0 = time.time()
-    th = [threading.Thread(target=e2e_worker, args=(w, e2e_steps // NB)) for w in range(NB)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = total_px / (float(dt.item()) / e2e_steps) / 1e6
+    def e2e_run(with_im):
+        for w in range(NB):
+            e2e_worker(w, 1, with_im)                    # warm-up: allocations, first-touch
+        barrier()
+        t0 = time.time()
+        th = [threading.Thread(target=e2e_worker, args=(w, e2e_steps // NB, with_im)) for w in range(NB)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return total_px / (float(dt.item()) / e2e_steps) / 1e6
+
+    e2e_tables = e2e_run(False)                          # segment tables only (what round 1 reported)
+    e2e_value = e2e_run(True) if want_im else e2e_tables  # + the lineIm of every map: everything the reference's call returns
     nseg = nseg_box[0]
-    d2h = n * 4 * 32 + nseg * 13 * 8   # per-map result records + one rectangle record per segment
+    d2h = n * 4 * 32 + nseg * 13 * 8 + (n * size * size if want_im else 0)   # result records + a rectangle record per segment [+ the lineIm planes]
+    if want_im and rank == 0:   # the bench checks what it times: the first map's lineIm against the host epilogue
+        if not np.array_equal(im_views[0][0], batches[0].line_image(0)):
+            raise SystemExit("bench.py: PARITY FAILURE: device lineIm != host epilogue")
+    im_bufs = None; im_views = None
     for cw, bw in workers:
         bw.close()
 
@@ -565,7 +588,8 @@ def main():
             "scan_front_end": fs,
             "stage_ms": last,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * size * size, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "how": "lsdb_batch_upload (pinned host -> HBM) + lsdb_batch_run + lsdb_batch_download per step; "
+                    "steps": e2e_steps, "line_images": bool(want_im), "tables_only_value": e2e_tables,
+                    "how": "lsdb_batch_upload (pinned host -> HBM) + lsdb_batch_run + lsdb_batch_download" + (" + lsdb_batch_line_images (lineIm of every map -> pinned host)" if want_im else "") + " per step; "
                                                f"{NB} batches on {NB} streams alternate so copies overlap kernels"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,

@@ -98,6 +98,8 @@ int lsdb_batch_sync(lsdb_batch* b);
 int lsdb_batch_download(lsdb_batch* b, int* counts, lsdb_line* lines, lsdb_rect* rects);
 /* rasterise map i's segments the way LSD/myLSD.cpp:296-355 fills lineIm (rows*cols u8, 0/255) */
 int lsdb_batch_line_image(lsdb_batch* b, int i, uint8_t* line_im);
+/* the same for every map of the batch at once, rasterised on the device: line_ims[i] = rows[i]*cols[i] u8 or NULL to skip map i */
+int lsdb_batch_line_images(lsdb_batch* b, uint8_t* const* line_ims);
 /* intermediate planes of map i for parity tests; every pointer may be NULL.
  *   mag/deg : H'*W' f64 (magMap/degMap, LSD/myLSD.cpp:146-147); used : H'*W' u8 (usedMap, :145);
  *   labels : H'*W' int32 (accept index + 1; reference regIdx == labels & 0xFF, :214,261);

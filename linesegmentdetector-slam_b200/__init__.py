@@ -72,6 +72,7 @@ def lib():
         L.lsdb_batch_sync.argtypes = [vp]
         L.lsdb_batch_download.argtypes = [vp, vp, vp, vp]
         L.lsdb_batch_line_image.argtypes = [vp, ci, vp]
+        L.lsdb_batch_line_images.argtypes = [vp, vp]
         L.lsdb_batch_planes.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci, vp, vp]
         L.lsdb_batch_stage_ms.argtypes = [vp, vp]
         L.lsdb_batch_stats.argtypes = [vp, C.POINTER(_Stats)]
@@ -359,6 +360,15 @@ class Batch:
         im = np.zeros((r, c), np.uint8)
         self.ctx.check(lib().lsdb_batch_line_image(self.h, i, _p(im)), "lsdb_batch_line_image")
         return im
+
+    def line_images(self, outs=None):
+        """lineIm of every map, rasterised on the device (lsdb_batch_line_images).  `outs`: list of rows x cols u8 arrays to
+        fill (e.g. views of pinned memory), default fresh arrays."""
+        if outs is None:
+            outs = [np.zeros((r, c), np.uint8) for c, r in self.sizes]
+        ptrs = (C.c_void_p * self.n)(*[o.ctypes.data for o in outs])
+        self.ctx.check(lib().lsdb_batch_line_images(self.h, ptrs), "lsdb_batch_line_images")
+        return outs
 
     def planes(self, i):
         W, H = self.scaled(i)

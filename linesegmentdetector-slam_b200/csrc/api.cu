@@ -51,6 +51,7 @@ struct lsdb_batch {
     uint8_t* src; double* mag; double* deg; double* cosm; double* sinm; unsigned int* state; unsigned short* bins; unsigned int* cells;
     int* labels; LsdbRect* rects; LsdbImgDyn* dyn; LsdbImg* imgsD; int* tileImg; unsigned int* lists;
     int* imgCounter; LsdbLsdConst* kcD; double* gaussDbg; unsigned char* recBuf; unsigned int* banBits;
+    uint8_t* lineImD;   // lineIm planes of all maps (allocated on first use by lsdb_batch_line_images; geometry of src)
     unsigned int* nzBits; int2* bandOf; int2* bandsOfImg; unsigned int* orderTabs; int nBands;   // ordering stage: "mag != 0" bits, row bands, count tables
     // host (pinned)
     LsdbImgDyn* dynH; LsdbRect* rectsH;
@@ -161,7 +162,7 @@ extern "C" void lsdb_batch_destroy(lsdb_batch* b) {
     cudaFree(b->src); cudaFree(b->mag); cudaFree(b->deg); cudaFree(b->cosm); cudaFree(b->state); cudaFree(b->bins); cudaFree(b->cells);
     cudaFree(b->labels); cudaFree(b->rects); cudaFree(b->dyn); cudaFree(b->imgsD); cudaFree(b->tileImg); cudaFree(b->lists);
     cudaFree(b->imgCounter); cudaFree(b->kcD); cudaFree(b->gaussDbg); cudaFree(b->recBuf); cudaFree(b->banBits);
-    cudaFree(b->nzBits); cudaFree(b->bandOf); cudaFree(b->bandsOfImg); cudaFree(b->orderTabs);
+    cudaFree(b->lineImD); cudaFree(b->nzBits); cudaFree(b->bandOf); cudaFree(b->bandsOfImg); cudaFree(b->orderTabs);
     cudaFreeHost(b->dynH); cudaFreeHost(b->rectsH);
     for (int i = 0; i < 4; i++) cudaEventDestroy(b->ev[i]);
     if (b->ctx->cached == b) b->ctx->cached = 0;
@@ -179,7 +180,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
     memset(&b->kc, 0, sizeof b->kc);
     b->ctx = ctx; b->n = n; b->params = *prm; b->ran = false; b->downloaded = false; b->launches = 0;
     b->src = 0; b->mag = 0; b->deg = 0; b->cosm = 0; b->sinm = 0; b->state = 0; b->bins = 0; b->cells = 0; b->labels = 0; b->rects = 0; b->dyn = 0;
-    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->banBits = 0; b->dynH = 0; b->rectsH = 0; b->nzBits = 0; b->bandOf = 0; b->bandsOfImg = 0; b->orderTabs = 0; b->nBands = 0;
+    b->imgsD = 0; b->tileImg = 0; b->lists = 0; b->imgCounter = 0; b->kcD = 0; b->gaussDbg = 0; b->recBuf = 0; b->banBits = 0; b->dynH = 0; b->rectsH = 0; b->lineImD = 0; b->nzBits = 0; b->bandOf = 0; b->bandsOfImg = 0; b->orderTabs = 0; b->nBands = 0;
     for (int i = 0; i < 4; i++) cudaEventCreate(&b->ev[i]);
     b->maxSeg = maxLines > 0 ? maxLines : 4096;
 
@@ -523,6 +524,26 @@ extern "C" int lsdb_batch_line_image(lsdb_batch* b, int i, uint8_t* lineIm) {
     memset(lineIm, 0, (size_t)im.cols * im.rows);
     for (int j = 0; j < b->dynH[i].nSeg; j++) raster_line(b->rectsH[(size_t)i * b->maxSeg + j], im.cols, im.rows, lineIm);
     return LSDB_OK;
+}
+
+// lineIm of every map of the batch, rasterised on the device (csrc/lineim.cu) and copied into the caller's rows*cols buffers
+// (NULL entries are skipped).  Asynchronous on the context stream up to the final synchronize.
+extern "C" int lsdb_batch_line_images(lsdb_batch* b, uint8_t* const* lineIms) {
+    if (!b || !lineIms) return LSDB_ERR_ARG;
+    lsdb_ctx* ctx = b->ctx;
+    if (!b->ran) return fail(ctx, LSDB_ERR_ARG, "lsdb_batch_line_images before lsdb_batch_run%s");
+    cudaStream_t s = ctx->stream;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!b->lineImD) CK(ctx, cudaMalloc((void**)&b->lineImD, b->totalSrc + 64));
+    CK(ctx, cudaMemsetAsync(b->lineImD, 0, b->totalSrc + 64, s));
+    lsdb_launch_line_images(s, b->n, b->maxSeg, b->imgsD, b->dyn, b->rects, b->lineImD);
+    CK(ctx, cudaGetLastError());
+    for (int i = 0; i < b->n; i++) {
+        if (!lineIms[i]) continue;
+        const LsdbImg& im = b->imgs[i];
+        CK(ctx, cudaMemcpy2DAsync(lineIms[i], im.cols, b->lineImD + im.srcOff, im.srcPitch, im.cols, im.rows, cudaMemcpyDeviceToHost, s));
+    }
+    return fetch_dyn(b);   // synchronises the stream and reports device-side errors of the run
 }
 
 extern "C" int lsdb_batch_planes(lsdb_batch* b, int i, double* mag, double* deg, uint8_t* used, int32_t* labels,

@@ -81,8 +81,10 @@ __device__ __forceinline__ void order_walk(const LsdbImg& im, const double* __re
                     t &= 0xffff;                            // pseIdx is CV_16UC1 (:178,187)
                     packed[slot[k]] = (unsigned short)t;
                 }
-                const unsigned int grp = __match_any_sync(0xffffffffu, t);
                 if (WRITE) {
+                    // stable: the lanes of one bin keep their raster order (rank inside the group), the group's run follows
+                    // the bin's earlier pixels of this warp
+                    const unsigned int grp = __match_any_sync(0xffffffffu, t);
                     unsigned int pos = 0;
                     if (t != 0) pos = myTab[t] + __popc(grp & ((1u << lane) - 1u));
                     __syncwarp();
@@ -90,10 +92,10 @@ __device__ __forceinline__ void order_walk(const LsdbImg& im, const double* __re
                         out[pos] = ps[k];
                         if (lane == __ffs(grp) - 1) myTab[t] += __popc(grp);
                     }
-                } else {
-                    if (t != 0 && lane == __ffs(grp) - 1) myTab[t] += __popc(grp);
+                    __syncwarp();
+                } else if (t != 0) {
+                    atomicAdd(&myTab[t], 1u);   // counting needs no order: the warp's private row of the table, conflicts resolved by the hardware
                 }
-                __syncwarp();
             }
         }
     }

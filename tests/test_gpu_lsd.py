@@ -55,6 +55,25 @@ def test_bundled_maps_batched_bit_exact(lsdb, ctx, gold):
     b.close()
 
 
+def test_line_images_on_the_device_equal_the_host_epilogue(lsdb, ctx, gold):
+    """lsdb_batch_line_images (csrc/lineim.cu: every map's lineIm rasterised on the device, LSD/myLSD.cpp:296-355) == the host
+    epilogue lsdb_batch_line_image == the reference's lineIm (goldens), for the bundled maps and two synthetic ones."""
+    maps = [gold[n + "/map"] for n in NAMES] + [synth.occupancy_grid(900, 700, seed=3), synth.occupancy_grid(333, 901, seed=22, border_walls=True)]
+    b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for m in maps])
+    b.upload(maps); b.run()
+    ims = b.line_images()
+    for i, m in enumerate(maps):
+        assert ims[i].shape == m.shape and set(np.unique(ims[i])) <= {0, 255}
+        assert np.array_equal(ims[i], b.line_image(i)), i
+        if i < len(NAMES):
+            assert np.array_equal(np.packbits(ims[i] > 0), gold[NAMES[i] + "/line_im_bits"])
+        else:
+            assert np.array_equal(ims[i], oraclebind.lsd(m)["line_im"])
+    b.run(); again = b.line_images()                 # the plane is cleared on every call
+    assert all(np.array_equal(x, y) for x, y in zip(ims, again))
+    b.close()
+
+
 def test_the_two_further_bundled_maps(lsdb, ctx):
     """BASELINE configs[1] 'all bundled maps': the distinct maps of data_20190513 / data_20190514 against the reference's goldens"""
     from test_oracle import _extra_maps

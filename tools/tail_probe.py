@@ -19,4 +19,6 @@ print("stage", b.stage_ms())
 print("ms per map: min %.0f p50 %.0f p90 %.0f max %.0f" % (ms.min(), np.median(ms), np.percentile(ms, 90), ms.max()))
 o = np.argsort(-ms)[:8]
 for i in o: print(f"  map {i}: {ms[i]:.0f} ms cells={cells[i]} live={live[i]} grown_px={gpx[i]} spec={spec[i]:.0f}M retire={ret[i]:.0f}M accepts={st[i]['accepts']} respec={st[i]['respec_evals']} cyc_respec={st[i]['cyc_respec']/1e6:.0f}M")
-print("corr(ms, live)=%.2f corr(ms, grown_px)=%.2f" % (np.corrcoef(ms, live)[0, 1], np.corrcoef(ms, gpx)[0, 1]))
+print("corr(ms, live)=%.2f corr(ms, grown_px)=%.2f corr(ms, cells)=%.2f" % (np.corrcoef(ms, live)[0, 1], np.corrcoef(ms, gpx)[0, 1], np.corrcoef(ms, cells)[0, 1]))
+acc = np.array([s["accepts"] for s in st]); print("corr(ms, accepts)=%.2f  mean ms %.1f  sum/256 %.1f" % (np.corrcoef(ms, acc)[0, 1], ms.mean(), ms.sum() / n))
+np.save(os.path.join(ROOT, "gpurun_out", "tail_ms.npy"), np.stack([ms, cells, live, gpx, acc]))
