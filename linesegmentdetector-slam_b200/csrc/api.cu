@@ -280,6 +280,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         if (getenv("LSDB_SUPER_SHIFT")) b->steal |= ((atoi(getenv("LSDB_SUPER_SHIFT")) & 3) + 1) << 8;   // chunks per claim = 1 << n (default: per map)
         const int maxCtas = lsdb_grow_max_ctas(ctx->device, nw, b->bmCapWords);
         b->nCtas = n < maxCtas ? n : maxCtas;
+        if (getenv("LSDB_GROW_CTAS")) { int v = atoi(getenv("LSDB_GROW_CTAS")); if (v >= 1 && v < b->nCtas) b->nCtas = v; }
         (void)sms;
     }
 
