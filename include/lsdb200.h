@@ -199,6 +199,20 @@ int lsdb_fa_score(lsdb_ctx* ctx, const lsdb_fa_map* m, int n_frames, const lsdb_
 int lsdb_fa_score_kept(lsdb_ctx* ctx, const lsdb_fa_map* m, int n_frames, const lsdb_line* scan_lines, const int* scan_line_off,
                        const double* scan_pts, const int* scan_pt_off, const double* lidar_pose, const double* last_pose,
                        double keep_below, lsdb_hypothesis* out, int max_kept, int* n_kept, int* n_hyp);
+/* The catkin snapshot's association, SURVEY.md §8 f4 — replaces myfa::FeatureAssociation of ROS/lsd/include/FeatureAssociation.h:46-60
+ * (ROS/lsd/src/FeatureAssociation.cpp:36-130; ScanToMapMatch :132-200, ScanToMapMatchScore :202-252, RotateScanIm :254-299), the
+ * 13-argument call of LSD/main_on_linux.cpp:132.  `m` holds MapCache (the three-argument createMapCache: cells beyond z_occ_max_dis
+ * read exactly 2.0, which the score counts apart, :239) and MaplinesInfo; its size is the size of MaplineIm.
+ *   scan_lines : ScanlinesInfo (x1 y1 x2 y2 len are used)      lidar_pos : LidarPos[2], scan-image pixels
+ *   ranges/angles : ScanRanges / ScanAngles, n_rays of each (Inf / NaN ranges fall outside the map, as in the reference)
+ * Output: pose_all = up to max_cols records of 15 doubles, the COLUMNS of the reference's 15 x T poseAll in its order (pose x y
+ * angle[deg], score, map end points, scan end points, scan-line index, map-line index, pairing 0..3); *n_cols = T;
+ * estimate_pose[3] (pixels, radians) / estimate_pose_realworld[3] (metres) = the first strict minimum of the score row (:117-127),
+ * both nullable.  Scores carry the bits of the reference's sequential sum.  T == 0 (the reference then reads an empty matrix):
+ * LSDB_OK, nothing estimated.  T > max_cols > 0: the first max_cols records, the estimates, and LSDB_ERR_CAPACITY. */
+int lsdb_fa_legacy(lsdb_ctx* ctx, const lsdb_fa_map* m, const lsdb_line* scan_lines, int n_scan, double map_resol, double map_ori_x,
+                   double map_ori_y, const int* lidar_pos, const double* ranges, const double* angles, int n_rays, double* pose_all,
+                   int max_cols, int* n_cols, double* estimate_pose, double* estimate_pose_realworld);
 /* The per-frame reduction that follows the scoring in FeatureAssociation (LSD/myFA.cpp:65-171, everything before ukf),
  * done on the device so that only one record per frame comes back instead of every hypothesis:
  *   n_kept  : hypotheses with score < 3 (:261); 0 = "no match, start a new chain" (:70-90)

@@ -94,6 +94,7 @@ def lib():
         L.lsdb_fa_map_destroy.argtypes = [vp]; L.lsdb_fa_map_destroy.restype = None
         L.lsdb_fa_score.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
         L.lsdb_fa_score_kept.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, cd, vp, ci, vp, vp]
+        L.lsdb_fa_legacy.argtypes = [vp, vp, vp, ci, cd, cd, cd, vp, vp, vp, ci, vp, ci, vp, vp, vp]
         L.lsdb_fa_estimate_frames.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]
         L.lsdb_fa_last_ms.argtypes = [vp]; L.lsdb_fa_last_ms.restype = C.c_float
         L.lsdb_feature_scan_frames.argtypes = [vp, cd, cd, cd, C.POINTER(_RdpParams), ci, vp, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp,
@@ -455,6 +456,25 @@ class FaMap:
         self.ctx.check(lib().lsdb_fa_score(self.ctx.h, self.h, nf, _p(lines), _p(loff), _p(pts), _p(poff), _p(lid), _p(last),
                                            _p(out), max_hyp, C.byref(n)), "lsdb_fa_score")
         return out[:n.value].copy()
+
+    def legacy(self, scan_lines, map_resol, map_ori, lidar_pos, ranges, angles, max_cols=None):
+        """lsdb_fa_legacy — the catkin snapshot's FeatureAssociation (ROS/lsd/src/FeatureAssociation.cpp:36-130) for one frame.
+        Returns (pose_all (T,15): the columns of the reference's poseAll, estimate_pose (3,), estimate_pose_realworld (3,));
+        the two estimates are None when no scan line pairs with any map line."""
+        sl = scan_lines if getattr(scan_lines, "dtype", None) == LINE_DTYPE else array_to_lines(scan_lines)
+        sl = np.ascontiguousarray(sl)
+        r = np.ascontiguousarray(ranges, np.float64); a = np.ascontiguousarray(angles, np.float64)
+        if len(r) != len(a):
+            raise ValueError("ranges and angles differ in length")
+        lp = np.ascontiguousarray(lidar_pos, np.int32)
+        if max_cols is None:
+            max_cols = max(4 * len(sl) * max(self.n_lines, 1), 4)
+        out = np.zeros((max_cols, 15)); n = C.c_int(0); est = np.zeros(3); real = np.zeros(3)
+        self.ctx.check(lib().lsdb_fa_legacy(self.ctx.h, self.h, _p(sl), len(sl), float(map_resol), float(map_ori[0]), float(map_ori[1]), _p(lp),
+                                            _p(r), _p(a), len(r), _p(out), max_cols, C.byref(n), _p(est), _p(real)), "lsdb_fa_legacy")
+        if n.value == 0:
+            return out[:0].copy(), None, None
+        return out[:n.value].copy(), est, real
 
     def pack(self, frames):
         """the frames as the flat arrays the C ABI takes (do this once when the same frames are scored repeatedly)"""

@@ -935,6 +935,64 @@ extern "C" int lsdb_fa_score_kept(lsdb_ctx* ctx, const lsdb_fa_map* m, int nFram
                       keepBelow, nKept, nHyp);
 }
 
+// The catkin snapshot's association (ROS/lsd/src/FeatureAssociation.cpp:36-130): the length filter of :63-70 on the host (n_scan x
+// n_map comparisons, in the reference's order), every hypothesis of the frame on the device (fa_legacy.cu), the strict-minimum
+// scan of :117-119 and the two estimates of :120-127 on the host.  poseAll = T records of 15 doubles (the reference's columns).
+extern "C" int lsdb_fa_legacy(lsdb_ctx* ctx, const lsdb_fa_map* m, const lsdb_line* scanLines, int nScan, double mapResol, double mapOriX,
+                              double mapOriY, const int* lidarPos, const double* ranges, const double* angles, int nRays, double* poseAll,
+                              int maxCols, int* nCols, double* estimatePose, double* estimatePoseReal) {
+    if (!ctx || !m || nScan < 0 || nRays < 0 || !lidarPos || !nCols || maxCols < 0 || (nScan > 0 && !scanLines) || (nRays > 0 && (!ranges || !angles)) ||
+        (maxCols > 0 && !poseAll))
+        return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_legacy: bad argument%s");
+    if (!(mapResol > 0)) return fail(ctx, LSDB_ERR_ARG, "lsdb_fa_legacy: mapResol must be positive%s");
+    std::vector<int2> pairs;
+    const double lenDiff = 0.3 / mapResol;   // :61-62
+    for (int i = 0; i < nScan; i++)
+        for (int j = 0; j < m->nLines; j++)
+            if (m->lines[j].len >= scanLines[i].len - lenDiff && m->lines[j].len <= scanLines[i].len + lenDiff) pairs.push_back(make_int2(i, j));
+    if (pairs.size() > (size_t)(1 << 28)) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_fa_legacy: too many candidate pairs%s");
+    const int nPairs = (int)pairs.size(), T = 4 * nPairs;
+    *nCols = T;
+    ctx->faMs = 0.f;
+    if (T == 0) return LSDB_OK;   // the reference reads column 0 of an empty matrix here (:119): nothing is estimated
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t oPairs = al256(sizeof(LsdbFaLine) * (size_t)nScan), oRng = oPairs + al256(sizeof(int2) * (size_t)nPairs),
+                 oAng = oRng + al256(8 * (size_t)nRays), oOut = oAng + al256(8 * (size_t)nRays), need = oOut + al256(120 * (size_t)T) + 256;
+    if (need > ctx->faInCap) {
+        if (ctx->faIn) cudaFree(ctx->faIn);
+        ctx->faIn = 0; ctx->faInCap = 0;
+        CK(ctx, cudaMalloc(&ctx->faIn, need + need / 4));
+        ctx->faInCap = need + need / 4;
+    }
+    char* I = (char*)ctx->faIn;
+    CK(ctx, cudaMemcpyAsync(I, scanLines, sizeof(LsdbFaLine) * (size_t)nScan, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemcpyAsync(I + oPairs, pairs.data(), sizeof(int2) * (size_t)nPairs, cudaMemcpyHostToDevice, s));
+    if (nRays > 0) {
+        CK(ctx, cudaMemcpyAsync(I + oRng, ranges, 8 * (size_t)nRays, cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaMemcpyAsync(I + oAng, angles, 8 * (size_t)nRays, cudaMemcpyHostToDevice, s));
+    }
+    CK(ctx, cudaEventRecord(ctx->faEv[0], s));
+    lsdb_launch_fa_legacy(s, nPairs, (const int2*)(I + oPairs), (const LsdbFaLine*)I, m->linesD, lidarPos[0], lidarPos[1], m->cacheD, m->cols, m->rows,
+                          mapResol, (const double*)(I + oRng), (const double*)(I + oAng), nRays, (double*)(I + oOut));
+    CK(ctx, cudaEventRecord(ctx->faEv[1], s));
+    CK(ctx, cudaGetLastError());
+    std::vector<double> rec((size_t)T * 15);
+    CK(ctx, cudaMemcpyAsync(rec.data(), I + oOut, 120 * (size_t)T, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    CK(ctx, cudaEventElapsedTime(&ctx->faMs, ctx->faEv[0], ctx->faEv[1]));
+    const int take = T < maxCols ? T : maxCols;
+    if (take > 0) memcpy(poseAll, rec.data(), 120 * (size_t)take);
+    int t = 0;   // :117-119
+    for (int i = 0; i < T; i++) t = rec[(size_t)i * 15 + 3] < rec[(size_t)t * 15 + 3] ? i : t;
+    const double pi = 3.14159265358979323846;
+    const double e0 = rec[(size_t)t * 15], e1 = rec[(size_t)t * 15 + 1], e2 = rec[(size_t)t * 15 + 2] / 180 * pi;
+    if (estimatePose) { estimatePose[0] = e0; estimatePose[1] = e1; estimatePose[2] = e2; }
+    if (estimatePoseReal) { estimatePoseReal[0] = e0 * mapResol + mapOriX; estimatePoseReal[1] = e1 * mapResol + mapOriY; estimatePoseReal[2] = e2; }
+    if (T > maxCols && maxCols > 0) return fail(ctx, LSDB_ERR_CAPACITY, "lsdb_fa_legacy: %s%lld hypotheses exceed max_cols", "", T);
+    return LSDB_OK;
+}
+
 // ---- scan front-end ----
 extern "C" float lsdb_feature_scan_last_ms(const lsdb_ctx* ctx) { return ctx ? ctx->fsMs : 0.f; }
 

@@ -52,6 +52,13 @@ int lsdo_fa_scores(const double* scan_lines, int n_scan, const double* map_lines
                    const double* lidar_pose, const double* last_pose, int32_t* out_idx,
                    double* out_val, int max_rec);
 
+/* the catkin snapshot's association (ROS/lsd/src/FeatureAssociation.cpp:36-299), serial: every (scan line, map line of similar
+ * length, pairing) hypothesis with its ray re-projection score.  pose_all: T records of 15 doubles = the columns of the reference's
+ * 15 x T poseAll; est / est_real = estimatePose / estimatePose_realworld (set when T > 0).  Returns T. */
+int lsdo_fa_legacy(const double* scan_lines, int n_scan, const double* map_lines, int n_map, double resol, double ori_x, double ori_y,
+                   const int* lidar_pos, int cols, int rows, const double* map_cache, const double* ranges, const double* angles,
+                   int n_rays, double* pose_all, int max_cols, double* est, double* est_real);
+
 /* myrdp::FeatureScan restated (LSD/myRDP.cpp:9-375), one frame of finite beams.  map_param = cols rows resol oriX oriY.
  * Same outputs as oracle/ref_harness.cpp:ref_feature_scan: lines [max_lines][10] (k b dx dy x1 y1 x2 y2 len orient),
  * pts [max_pts][2], lidar_pos[2], im_size = cols, rows of the raster, line_im (0/255) when it fits line_im_cap.

@@ -1,7 +1,7 @@
 // Minimal stand-in for <opencv.hpp>: this image has no OpenCV C++ headers.
 // The LSD-SLAM sources use cv::Mat purely as a ref-counted 2-D array
-// (Mat::zeros, ptr<T>(row), rows, cols, size[i], clone, release), so that is
-// all this header provides.  It is used (a) to compile the unmodified
+// (Mat::zeros, ptr<T>(row), rows, cols, size[i], clone, release — and, in the catkin snapshot's
+// FeatureAssociation.cpp, ptr<T>(row, col), colRange / row views and copyTo), so that is all this header provides.  It is used (a) to compile the unmodified
 // reference into oracle/_ref and (b) to compile this repo's host wrappers.
 //
 // A test-only allocation registry lets a harness recover Mats that are local
@@ -107,6 +107,27 @@ public:
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
+    template <typename T> T* ptr(int r, int c) { return (T*)(data + (size_t)r * step) + c; }
+    template <typename T> const T* ptr(int r, int c) const { return (const T*)(data + (size_t)r * step) + c; }
+
+    // views share the buffer (and its reference count) with the matrix they were cut from
+    Mat colRange(int c0, int c1) const {
+        Mat v(*this);
+        v.data = data + (size_t)c0 * elemSize();
+        v.cols = c1 - c0; v.size.dims[1] = v.cols;
+        return v;
+    }
+    Mat row(int r) const {
+        Mat v(*this);
+        v.data = data + (size_t)r * step;
+        v.rows = 1; v.size.dims[0] = 1;
+        return v;
+    }
+    // dst of the same shape (a view, typically) is written in place; anything else is re-created, like cv::Mat::copyTo
+    void copyTo(Mat dst) const {
+        if (!dst.data || dst.rows != rows || dst.cols != cols || dst.type_ != type_) return;
+        for (int r = 0; r < rows; r++) memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * elemSize());
+    }
 
 private:
     MatBuf* buf_;

@@ -39,6 +39,9 @@ def lib():
         L.lsdo_fa_scores.restype = C.c_int
         L.lsdo_fa_scores.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.lsdo_fa_legacy.restype = C.c_int
+        L.lsdo_fa_legacy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.lsdo_feature_scan.restype = C.c_int
         L.lsdo_feature_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                         C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -118,6 +121,24 @@ def fa_scores(scan_lines, map_lines, pts, mc, lidar_pose, last_pose):
     n = lib().lsdo_fa_scores(_p(sl), len(sl), _p(ml), len(ml), _p(pt), len(pt), _p(mc), cols, rows, _p(lp), _p(la),
                              _p(idx), _p(val), cap)
     return idx[:n].copy(), val[:n].copy()
+
+
+def fa_legacy(scan_lines, map_lines, resol, ori, lidar_pos, mc, ranges, angles, fn=None):
+    """the catkin snapshot's FeatureAssociation restated (oracle/fa_legacy_oracle.c): (pose_all (T,15), est (3,), est_real (3,)).
+    fn = a ros_fa entry point of oracle/_ref/libref_rosfa*.so instead of the restatement (same arguments, 15 x T matrix out)."""
+    sl = np.ascontiguousarray(scan_lines, np.float64).reshape(-1, 10)
+    ml = np.ascontiguousarray(map_lines, np.float64).reshape(-1, 10)
+    mc = np.ascontiguousarray(mc, np.float64)
+    rows, cols = mc.shape
+    r = np.ascontiguousarray(ranges, np.float64); a = np.ascontiguousarray(angles, np.float64)
+    lp = np.ascontiguousarray(lidar_pos, np.int32)
+    cap = 4 * len(sl) * len(ml) + 4
+    out = np.zeros((cap, 15)) if fn is None else np.zeros((15, cap))
+    est = np.zeros(3); real = np.zeros(3)
+    f = lib().lsdo_fa_legacy if fn is None else fn
+    T = f(_p(sl), len(sl), _p(ml), len(ml), C.c_double(resol), C.c_double(ori[0]), C.c_double(ori[1]), _p(lp), cols, rows, _p(mc), _p(r), _p(a),
+          len(r), _p(out), cap, _p(est), _p(real))
+    return (out[:T].copy() if fn is None else out[:, :T].T.copy()), est, real
 
 
 def feature_scan_many(map_param, frames):
