@@ -480,16 +480,24 @@ class FaMap:
         """the frames as the flat arrays the C ABI takes (do this once when the same frames are scored repeatedly)"""
         return self._marshal(frames)
 
-    def score_kept(self, frames, keep_below=3.0, max_kept=None):
+    def score_kept(self, frames, keep_below=3.0, max_kept=None, out=None):
         """lsdb_fa_score_kept: only the hypotheses with score < keep_below (what the reference keeps), compacted on the device.
-        `frames` is a list of frame dicts or the tuple pack() returned.  Returns (kept HYP_DTYPE records, hypotheses scored)."""
+        `frames` is a list of frame dicts or the tuple pack() returned.  Returns (kept HYP_DTYPE records, hypotheses scored).
+        `out`: a caller-owned HYP_DTYPE array (pinned host memory, say) the records are written to; the result is then a view of it."""
         nf, lines, loff, pts, poff, lid, last = frames if isinstance(frames, tuple) else self._marshal(frames)
-        if max_kept is None:
-            max_kept = max(4 * int(loff[-1]) * max(self.n_lines, 1) // 8, 4096)
-        out = np.zeros(max_kept, HYP_DTYPE); nk = C.c_int(0); nh = C.c_int(0)
+        own = out is None
+        if own:
+            if max_kept is None:
+                max_kept = max(4 * int(loff[-1]) * max(self.n_lines, 1) // 8, 4096)
+            out = np.empty(max_kept, HYP_DTYPE)
+        else:
+            if out.dtype != HYP_DTYPE or not out.flags.c_contiguous:
+                raise ValueError("out must be a contiguous HYP_DTYPE array")
+            max_kept = len(out) if max_kept is None else min(int(max_kept), len(out))
+        nk = C.c_int(0); nh = C.c_int(0)
         self.ctx.check(lib().lsdb_fa_score_kept(self.ctx.h, self.h, nf, _p(lines), _p(loff), _p(pts), _p(poff), _p(lid), _p(last),
                                                 float(keep_below), _p(out), max_kept, C.byref(nk), C.byref(nh)), "lsdb_fa_score_kept")
-        return out[:nk.value].copy(), nh.value
+        return (out[:nk.value].copy() if own else out[:nk.value]), nh.value
 
     def estimate(self, frames):
         """Per-frame reduction on the device (lsdb_fa_estimate_frames): one EST_DTYPE record per frame."""
