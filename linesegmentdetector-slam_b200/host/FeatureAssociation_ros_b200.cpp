@@ -24,16 +24,31 @@ static_assert(sizeof(structLinesInfo) == sizeof(lsdb_line), "structLinesInfo lay
 
 namespace {
 struct MapKey {
-    const void* data; int rows, cols, nLines; unsigned long long hash;
-    bool operator==(const MapKey& o) const { return data == o.data && rows == o.rows && cols == o.cols && nLines == o.nLines && hash == o.hash; }
+    const void* data; int rows, cols, nLines; unsigned long long hash, sample;
+    bool operator==(const MapKey& o) const {
+        return data == o.data && rows == o.rows && cols == o.cols && nLines == o.nLines && hash == o.hash && sample == o.sample;
+    }
 };
-MapKey g_key = {0, 0, 0, 0, 0};
+MapKey g_key = {0, 0, 0, 0, 0, 0};
 lsdb_fa_map* g_map = 0;
 
 unsigned long long fnv1a(const void* p, size_t n) {
     const unsigned char* b = (const unsigned char*)p;
     unsigned long long h = 1469598103934665603ull;
     for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// a fingerprint of the cache's CONTENT (4096 cells spread over the matrix): a map rewritten in place, or a new Mat that got the
+// old one's address, must not be served from the stale device copy
+unsigned long long sample_cells(const cv::Mat& m) {
+    unsigned long long h = 1469598103934665603ull;
+    const size_t n = (size_t)m.rows * (size_t)m.cols, step = n / 4096 + 1;
+    for (size_t i = 0; i < n; i += step) {
+        const double v = m.ptr<double>((int)(i / m.cols))[i % m.cols];
+        unsigned long long b; memcpy(&b, &v, 8);
+        h ^= b; h *= 1099511628211ull;
+    }
     return h;
 }
 }  // namespace
@@ -52,7 +67,8 @@ void FeatureAssociation(const Mat& ScanlineIm, const vector<structLinesInfo>& Sc
                 MaplineIm.cols, MaplineIm.rows);
         abort();
     }
-    MapKey k = {MapCache.data, MapCache.rows, MapCache.cols, nMap, nMap ? fnv1a(&MaplinesInfo[0], sizeof(structLinesInfo) * (size_t)nMap) : 0ull};
+    MapKey k = {MapCache.data, MapCache.rows, MapCache.cols, nMap, nMap ? fnv1a(&MaplinesInfo[0], sizeof(structLinesInfo) * (size_t)nMap) : 0ull,
+                sample_cells(MapCache)};
     if (!g_map || !(k == g_key)) {
         if (g_map) lsdb_fa_map_destroy(g_map);
         g_map = 0;

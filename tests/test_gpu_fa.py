@@ -146,6 +146,11 @@ def test_kept_hypotheses_equal_the_filtered_full_table(lsdb, ctx):
     assert n_hyp == len(full) and len(kept) == len(want) > 0
     for k in ("frame", "i_scan", "i_map", "i_pair", "x", "y", "ang", "score"):
         assert np.array_equal(kept[k], want[k]), k
+    table = np.zeros(len(want) + 7, lsdb.HYP_DTYPE)                      # a caller-owned table: the result is a view of it
+    mine, _ = fm.score_kept(frames, out=table)
+    assert mine.base is table and len(mine) == len(want) and np.array_equal(mine, want)
+    with pytest.raises(lsdb.LsdbError, match="CAPACITY"):
+        fm.score_kept(frames, out=table[:len(want) - 1])
     kept5, _ = fm.score_kept(frames, keep_below=5.0)
     assert len(kept5) == int((full["score"] < 5.0).sum())
     with pytest.raises(lsdb.LsdbError, match="CAPACITY"):
