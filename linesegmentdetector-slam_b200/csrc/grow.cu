@@ -513,70 +513,99 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
 // the evaluation at retire time anyway).
 // Returns the region size (T when large).  lst[] holds the accepted pixels (packed y<<16|x), pnd[0..npnd) the pixels
 // skipped because an earlier seed's parked accept covers them (npnd = -1: more than SG_PND of them).
-__device__ __noinline__ int small_grow(const WarpCtx& c, int p0, int T, unsigned int* lst, int myChunk, unsigned int* pnd, int& npnd) {
+// The 32 lanes run their seeds as ONE instruction stream: every trip of the loop below, each running lane first opens its
+// next point if the current one has no candidate left (at most one point per trip), then tests at most one candidate.  The
+// per-lane sequence of operations is the sequential one; what changes is that the lanes no longer sit in different loop
+// nests (5 of 32 threads active per instruction before — and the kernel is bound by instruction supply).
+// A lane's own pixels are found through a 64-bit filter on (x + 8y) first; the list is only searched on a filter hit.
+__device__ __forceinline__ unsigned long long sg_bit(int x, int y) { return 1ull << ((x + 8 * y) & 63); }
+
+__device__ __noinline__ int small_grow(const WarpCtx& c, bool act, int p0, int T, unsigned int* lst, int myChunk, unsigned int* pnd, int& npnd) {
     const int W = c.W;
     const double pi = c.kc->pi, pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
     const double degThre = c.kc->degThre, cTau = c.kc->cosDegThre;
     unsigned short rej[SG_CAP];
-    const int sx = p0 % W, sy = p0 / W;
     const double c2 = cTau * cTau;
-    double cosS = c.cosm[2 * (size_t)p0], sinS = c.sinm[2 * (size_t)p0];
-    double n2 = cosS * cosS + sinS * sinS, c2n2 = c2 * n2, m2 = 4e-13 * n2;   // see grow_region: the test on the squares
-    bool nrmOK = n2 > 1e-18;
-    lst[0] = pack_xy(sx, sy);
-    rej[0] = 0;
-    int num = 1, exNum = 0, startNum = 0;
-    while (exNum != num) {
-        exNum = num;
-        for (int i = 0; i < num; i++) {
-            const unsigned int v = lst[i];
-            const int x = px_of(v), y = py_of(v);
-            unsigned int cm = i >= startNum ? (~ban9(c, x, y)) & 0x1efu : (unsigned int)rej[i];
-            unsigned int nr = 0;
-            while (cm) {
-                const int nb = __ffs(cm) - 1;
-                cm &= cm - 1;
-                const int r3 = nb / 3;
-                const int m = y + r3 - 1, n = x + (nb - r3 * 3) - 1;
-                const unsigned int pk = pack_xy(n, m);
-                bool own = false;
+    double cosS = 0.0, sinS = 0.0, n2 = 0.0, c2n2 = 0.0, m2 = 0.0;   // see grow_region: the test on the squares
+    bool nrmOK = false;
+    unsigned long long mine = 0ull;
+    int num = 0;
+    if (act) {
+        const int sx = p0 % W, sy = p0 / W;
+        cosS = c.cosm[2 * (size_t)p0]; sinS = c.sinm[2 * (size_t)p0];
+        n2 = cosS * cosS + sinS * sinS; c2n2 = c2 * n2; m2 = 4e-13 * n2;
+        nrmOK = n2 > 1e-18;
+        lst[0] = pack_xy(sx, sy);
+        rej[0] = 0;
+        mine = sg_bit(sx, sy);
+        num = 1;
+    }
+    int i = -1, exNum = num, startNum = 0;   // current point; points when the pass began; points below startNum re-test their rejects only
+    int x = 0, y = 0;
+    unsigned int cm = 0, nr = 0;
+    bool running = act;
+    while (__any_sync(FULL, running)) {
+        if (running && cm == 0) {   // close the point, open the next one
+            if (i >= 0) rej[i] = (unsigned short)nr;
+            i++;
+            if (i >= num) {         // a pass is over (:525): another one only if this one added a pixel
+                if (exNum == num) running = false;
+                else { startNum = num; exNum = num; i = 0; }
+            }
+            if (running) {
+                const unsigned int v = lst[i];
+                x = px_of(v); y = py_of(v);
+                cm = i >= startNum ? (~ban9(c, x, y)) & 0x1efu : (unsigned int)rej[i];
+                nr = 0;
+            }
+        }
+        if (running && cm != 0) {   // one candidate
+            const int nb = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int r3 = nb / 3;
+            const int m = y + r3 - 1, n = x + (nb - r3 * 3) - 1;
+            const unsigned int pk = pack_xy(n, m);
+            bool own = false;
+            if (mine & sg_bit(n, m))
                 for (int k = 0; k < num; k++) own |= lst[k] == pk;
-                if (own) continue;
+            if (!own) {
                 const size_t p = (size_t)m * W + n;
                 const unsigned int st = lsdb_ld_state(&c.state[p]);
                 const double cd = c.cosm[2 * p], sd = c.sinm[2 * p];
-                if (st & LSDB_ST_BAN) continue;
-                if (pend_applies(st, LSDB_ST_PACC, myChunk)) {   // parked for acceptance by an earlier seed: counts as banned,
-                    bool dup = false;                            // to be confirmed when this evaluation retires
-                    for (int j = 0; j < npnd; j++) dup |= pnd[j] == pk;
-                    if (!dup) { if (npnd >= 0 && npnd < SG_PND) pnd[npnd++] = pk; else npnd = -1; }
-                    continue;
-                }
-                const double dot = cosS * cd + sinS * sd;
-                const double d2 = dot * dot - c2n2;
-                bool pass = dot > 0 && d2 > 0;
-                if ((dot > 0 && !(fabs(d2) > m2)) || !nrmOK) {  // knife edge: the literal test of :540-543
-                    const double regDeg = num == 1 ? c.deg[p0] : d_atan2(sinS, cosS);
-                    double degDif = fabs(regDeg - c.deg[p]);
-                    if (degDif > pi32) degDif = fabs(degDif - pi2);
-                    pass = degDif < degThre;
-                }
-                if (pass) {
-                    lst[num] = pk;
-                    rej[num] = 0;
-                    num++;
-                    cosS += cd;  // :545-546
-                    sinS += sd;
-                    if (num >= T) return num;
-                    n2 = cosS * cosS + sinS * sinS;
-                    c2n2 = c2 * n2; m2 = 4e-13 * n2; nrmOK = n2 > 1e-18;
-                } else {
-                    nr |= 1u << nb;
+                if (!(st & LSDB_ST_BAN)) {
+                    if (pend_applies(st, LSDB_ST_PACC, myChunk)) {   // parked for acceptance by an earlier seed: counts as banned,
+                        bool dup = false;                            // to be confirmed when this evaluation retires
+                        for (int j = 0; j < npnd; j++) dup |= pnd[j] == pk;
+                        if (!dup) { if (npnd >= 0 && npnd < SG_PND) pnd[npnd++] = pk; else npnd = -1; }
+                    } else {
+                        const double dot = cosS * cd + sinS * sd;
+                        const double d2 = dot * dot - c2n2;
+                        bool pass = dot > 0 && d2 > 0;
+                        if ((dot > 0 && !(fabs(d2) > m2)) || !nrmOK) {  // knife edge: the literal test of :540-543
+                            const double regDeg = num == 1 ? c.deg[p0] : d_atan2(sinS, cosS);
+                            double degDif = fabs(regDeg - c.deg[p]);
+                            if (degDif > pi32) degDif = fabs(degDif - pi2);
+                            pass = degDif < degThre;
+                        }
+                        if (pass) {
+                            lst[num] = pk;
+                            rej[num] = 0;
+                            num++;
+                            mine |= sg_bit(n, m);
+                            cosS += cd;  // :545-546
+                            sinS += sd;
+                            if (num >= T) running = false;   // large: the warp-cooperative path grows it in full
+                            else {
+                                n2 = cosS * cosS + sinS * sinS;
+                                c2n2 = c2 * n2; m2 = 4e-13 * n2; nrmOK = n2 > 1e-18;
+                            }
+                        } else {
+                            nr |= 1u << nb;
+                        }
+                    }
                 }
             }
-            rej[i] = (unsigned short)nr;
         }
-        startNum = num;
     }
     return num;
 }
@@ -1270,9 +1299,9 @@ __device__ void speculate_super(WarpCtx& c, int chunk0, int nSub, const unsigned
         bool large = act;
         const int L0 = sh.nSeg;
         __threadfence_block();
-        if (act && T <= SG_CAP) {
-            num = small_grow(c, myp, T, lst, myChunk, pnd, npnd);
-            large = num >= T;
+        if (T <= SG_CAP) {   // warp-uniform: all 32 lanes enter, the ones without a seed idle
+            num = small_grow(c, act, myp, T, lst, myChunk, pnd, npnd);
+            large = act && num >= T;
         }
         __syncwarp();
         const bool small = act && !large && npnd >= 0;
