@@ -271,7 +271,8 @@ struct GrowSums {
     bool nrmOK;
 };
 
-__device__ __forceinline__ void sums_refresh(GrowSums& g, double c2, double cTau, bool tauSmall) {
+template <bool tauSmall>
+__device__ __forceinline__ void sums_refresh(GrowSums& g, double c2, double cTau) {
     g.n2 = g.cosDeg * g.cosDeg + g.sinDeg * g.sinDeg;
     g.nrmOK = g.n2 > 1e-18;
     if (tauSmall) {
@@ -287,9 +288,10 @@ __device__ __forceinline__ void sums_refresh(GrowSums& g, double c2, double cTau
 // accept loop over the (up to 32) candidates the lanes hold, in lane order.  cand: lane holds a live candidate
 // (in the image, not banned, not in the region); p/n/m its pixel; dg/cd/sd its angle data.  On return cand is
 // true exactly for the candidates that failed the angle test (the rest joined the region or dropped out).
+template <bool tauSmall>
 __device__ __forceinline__ int accept_lanes(WarpCtx& c, GrowSums& g, bool& cand, size_t p, int n, int m, double dg, double cd, double sd,
                                             int& num, bool& haveExact, double& regExact, double degThre, double c2, double cTau,
-                                            bool tauSmall, bool tauGtPi, float tauF) {
+                                            bool tauGtPi, float tauF) {
     const double pi = c.kc->pi;
     const double pi32 = pi * 3 / 2.0, pi2 = 2.0 * pi;
     int start = 0;
@@ -337,7 +339,7 @@ __device__ __forceinline__ int accept_lanes(WarpCtx& c, GrowSums& g, bool& cand,
                     g.cosDeg += __shfl_sync(FULL, cd, f);
                     g.sinDeg += __shfl_sync(FULL, sd, f);
                 }
-                sums_refresh(g, c2, cTau, tauSmall);
+                sums_refresh<tauSmall>(g, c2, cTau);
                 haveExact = false;
                 num += na;
                 if (cand && (grp & acc)) cand = false;   // joined, or the same pixel seen from another point
@@ -382,7 +384,7 @@ __device__ __forceinline__ int accept_lanes(WarpCtx& c, GrowSums& g, bool& cand,
         const int fn = __shfl_sync(FULL, n, f), fm = __shfl_sync(FULL, m, f);
         g.cosDeg += __shfl_sync(FULL, cd, f);  // :545-546
         g.sinDeg += __shfl_sync(FULL, sd, f);
-        sums_refresh(g, c2, cTau, tauSmall);
+        sums_refresh<tauSmall>(g, c2, cTau);
         haveExact = false;
         if (num >= c.listCap - 1) return -1;
         if (c.lane == f) {
@@ -396,7 +398,10 @@ __device__ __forceinline__ int accept_lanes(WarpCtx& c, GrowSums& g, bool& cand,
     return 0;
 }
 
-__device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double degThre, BBox& bb) {
+// two builds of the grower: the common one (tolerance <= pi/2: the test on the squares only) keeps the float / sqrt / un-wrapped-band
+// code of the wide tolerances (Refiner re-grows with 2 sigma, :857) out of its loop
+template <bool tauSmall>
+__device__ __noinline__ int grow_region_t(WarpCtx& c, int sx, int sy, double& regDeg, double degThre, BBox& bb) {
     const int W = c.W, H = c.H;
     const double pi = c.kc->pi;
     TIC;
@@ -404,7 +409,6 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
     const double regDeg0 = regDeg;
     GrowSums g;
     g.sinDeg = c.sinm[2 * sp]; g.cosDeg = c.cosm[2 * sp];  // sin(regDeg), cos(regDeg)  (:515-516)
-    const bool tauSmall = degThre <= pi / 2.0;
     const bool tauGtPi = degThre > pi;
     const double cTau = degThre == c.kc->degThre ? c.kc->cosDegThre : (tauGtPi ? -1.0 : d_cos(degThre));
     const double c2 = cTau * cTau;
@@ -415,7 +419,7 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
     }
     __syncwarp();
     int num = 1;
-    sums_refresh(g, c2, cTau, tauSmall);
+    sums_refresh<tauSmall>(g, c2, cTau);
     bool haveExact = true;
     double regExact = regDeg0;
     const unsigned int lt = (1u << c.lane) - 1u;
@@ -472,7 +476,7 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
                     if (pend) cand = false;
                 }
             }
-            if (accept_lanes(c, g, cand, p, n, m, dg, cd, sd, num, haveExact, regExact, degThre, c2, cTau, tauSmall, tauGtPi, tauF) < 0) return -1;
+            if (accept_lanes<tauSmall>(c, g, cand, p, n, m, dg, cd, sd, num, haveExact, regExact, degThre, c2, cTau, tauGtPi, tauF) < 0) return -1;
             if (!literal) {
                 const unsigned int rb = __ballot_sync(FULL, cand);
                 if (rb) {
@@ -501,6 +505,10 @@ __device__ __noinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regD
     STAT(c, ST_GROWS, 1); STAT(c, ST_GROWNPX, num);
     TOC(c, TM_GROW);
     return num;
+}
+
+__device__ __forceinline__ int grow_region(WarpCtx& c, int sx, int sy, double& regDeg, double degThre, BBox& bb) {
+    return degThre <= c.kc->pi / 2.0 ? grow_region_t<true>(c, sx, sy, regDeg, degThre, bb) : grow_region_t<false>(c, sx, sy, regDeg, degThre, bb);
 }
 
 // ------------------------------------------------------------------ RegionGrower, one LANE per seed
