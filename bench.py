@@ -240,7 +240,7 @@ def main():
     ap.add_argument("--cpu-sample-maps", type=int, default=0, help="maps for the cpu_baseline leg (0 = one per core, max 8)")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=5, help="resident batches that alternate on their own streams")
+    ap.add_argument("--inflight", type=int, default=0, help="resident batches that alternate on their own streams (0 = five 256-map batches' worth of maps, 5..12)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank owns --maps-per-gpu maps; strong: the global batch is --maps-per-gpu maps, split over the ranks "
                          "(BASELINE configs[2] as written: batch 256 sharded over 1/2/4/8 GPUs)")
@@ -275,13 +275,6 @@ def main():
     # two explicit streams: their handles are what the library launches on.  Two resident batches (A, B) of the same
     # maps alternate, step by step: while the last, slow maps of one step finish, the next step's maps already occupy the
     # SMs they left idle — the steady state of a caller that keeps the device fed.
-    NB = max(1, args.inflight)
-    streams = [torch.cuda.Stream() for _ in range(NB)]
-    torch.cuda.set_stream(streams[0])
-    stream = streams[0]
-    ctxs = [lsdb.Context(local, st.cuda_stream) for st in streams]
-    ctx = ctxs[0]
-
     size = args.size
     if args.scaling == "strong":
         global_n = args.maps_per_gpu                          # strong scaling: ONE batch of --maps-per-gpu maps, split over the ranks
@@ -293,6 +286,20 @@ def main():
         global_n = world * n
         first, cnt = shard.shard_range(global_n, rank, world)   # weak scaling: every rank owns n maps of the global batch
         assert cnt == n
+    # batches in flight: enough to keep ~1280 maps on the device (what five 256-map batches are) when a rank's share is smaller
+    # (strong scaling), at most 12; the region stage's rate depends on how many maps are resident, not on how they are batched
+    NB = args.inflight if args.inflight > 0 else max(5, min(12, -(-1280 // n)))
+    # The library sizes a batch's teams as if the batch were alone on the device (8 warps per map below ~150 maps).  With NB such
+    # batches in flight the device is full of maps anyway, and 4-warp teams (four per SM instead of one) are what fills it.
+    team_note = "library default"
+    if "LSDB_GROW_WARPS" not in os.environ and n < 256 and NB * n >= 256:
+        os.environ["LSDB_GROW_WARPS"] = "4"
+        team_note = "4 warps per map (LSDB_GROW_WARPS=4: the batches in flight fill the device)"
+    streams = [torch.cuda.Stream() for _ in range(NB)]
+    torch.cuda.set_stream(streams[0])
+    stream = streams[0]
+    ctxs = [lsdb.Context(local, st.cuda_stream) for st in streams]
+    ctx = ctxs[0]
     host = torch.empty((n, size, size), dtype=torch.uint8).pin_memory()
     hnp = host.numpy()
     for i in range(n):
@@ -581,7 +588,8 @@ def main():
             "config": {"workload": f"synthetic {size}x{size} occupancy grids, global batch {global_n} (BASELINE configs[2]), {n} per GPU",
                        "maps_per_gpu": n, "global_batch": global_n, "parallelism": f"map-sharded x{world}, no collective",
                        "l2": f"inputs {n * size * size / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
-                       "pipelining": f"{NB} resident batches alternate on {NB} streams (value and e2e alike); stage_ms / roofline are one step alone"},
+                       "pipelining": f"{NB} resident batches alternate on {NB} streams (value and e2e alike); stage_ms / roofline are one step alone",
+                       "teams": team_note},
             "segments_per_s": float(segs.item()) / (ms_step * 1e-3), "segments_per_step": float(segs.item()),
             "ms_per_map_amortised": ms_step / n,
             "single_map_latency": lat,
