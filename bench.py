@@ -292,14 +292,15 @@ def main():
     # The library sizes a batch's teams as if the batch were alone on the device (8 warps per map below ~150 maps).  With NB such
     # batches in flight the device is full of maps anyway, and 4-warp teams (four per SM instead of one) are what fills it.
     team_note = "library default"
-    if "LSDB_GROW_WARPS" not in os.environ and n < 256 and NB * n >= 256:
-        os.environ["LSDB_GROW_WARPS"] = "4"
-        team_note = "4 warps per map (LSDB_GROW_WARPS=4: the batches in flight fill the device)"
     streams = [torch.cuda.Stream() for _ in range(NB)]
     torch.cuda.set_stream(streams[0])
     stream = streams[0]
     ctxs = [lsdb.Context(local, st.cuda_stream) for st in streams]
     ctx = ctxs[0]
+    if n < 256 and NB * n >= 256:
+        for c_ in ctxs:
+            c_.set_team_warps(4)
+        team_note = "4 warps per map (lsdb_set_team_warps: the batches in flight fill the device)"
     host = torch.empty((n, size, size), dtype=torch.uint8).pin_memory()
     hnp = host.numpy()
     for i in range(n):

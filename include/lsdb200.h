@@ -78,6 +78,11 @@ typedef struct {
 /* ---- context ---- */
 /* `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private stream. */
 int lsdb_create(lsdb_ctx** out, int device, void* stream);
+/* Warps per map of the region stage (the seed loop, LSD/myLSD.cpp:218-272) for batches created from now on; 0 = chosen from the batch
+ * size as if the batch were alone on the device (16 warps for a lone map ... 4 for 256 maps ... 1 for thousands of rasters).  A caller
+ * that keeps SEVERAL small batches in flight on one device (contexts on different streams) fills it better with 4.  Results do not
+ * depend on it.  Has no counterpart in the reference (its seed loop is one thread). */
+int lsdb_set_team_warps(lsdb_ctx* ctx, int warps);
 void lsdb_destroy(lsdb_ctx* ctx);
 const char* lsdb_last_error(const lsdb_ctx* ctx);
 const char* lsdb_version(void);

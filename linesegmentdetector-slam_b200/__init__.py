@@ -77,6 +77,7 @@ def lib():
         L.lsdb_batch_stage_ms.argtypes = [vp, vp]
         L.lsdb_batch_stats.argtypes = [vp, C.POINTER(_Stats)]
         L.lsdb_batch_map_stats.argtypes = [vp, ci, C.POINTER(_Stats)]
+        L.lsdb_set_team_warps.argtypes = [vp, ci]
         L.lsdb_batch_launches.argtypes = [vp]
         L.lsdb_lsd.argtypes = [vp, vp, ci, ci, C.POINTER(_Params), vp, ci, vp, vp, vp]
         L.lsdb_map_cache.argtypes = [vp, vp, ci, ci, cd, cd, vp]
@@ -133,6 +134,10 @@ class Context:
         if self.h:
             lib().lsdb_destroy(self.h)
             self.h = C.c_void_p()
+
+    def set_team_warps(self, warps):
+        """lsdb_set_team_warps: warps per map of the region stage for batches created from now on (0 = by batch size)."""
+        self.check(lib().lsdb_set_team_warps(self.h, int(warps)), "lsdb_set_team_warps")
 
     def lsd(self, map_u8, want_line_im=True, want_remap=False, max_lines=4096, **params):
         """mylsd::myLineSegmentDetector on one host map (LSD/myLSD.h:132) through lsdb_lsd."""

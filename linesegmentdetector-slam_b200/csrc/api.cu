@@ -22,6 +22,7 @@ struct lsdb_ctx {
     double* lgammaTab;
     int lgammaN;
     int maxGrowCtas;
+    int teamWarps;       // lsdb_set_team_warps: warps per map of the region stage for batches created from now on (0 = by batch size)
     lsdb_batch* cached;  // single-map batch reused by lsdb_lsd
     cudaEvent_t faEv[2];
     float faMs;
@@ -92,7 +93,7 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
     lsdb_ctx* c = new lsdb_ctx();
     c->device = device; c->cached = 0; c->faMs = 0; c->faDev = 0; c->faDevCap = 0; c->faHost = 0; c->faHostCap = 0; c->faAux = 0; c->faAuxHost = 0; c->faAuxCap = 0; c->faIn = 0; c->faInCap = 0; c->faKeep = 0; c->faKeepCap = 0;
     c->fsOut = 0; c->fsOutHost = 0; c->fsOutCap = 0; c->fsOutHostCap = 0; c->fsLinesDev = 0; c->fsPtsDev = 0; c->fsIm = 0; c->fsImCap = 0; c->fsTmp = 0; c->fsTmpCap = 0; c->fsMs = 0;
-    c->lgammaTab = 0; c->lgammaN = 0;
+    c->lgammaTab = 0; c->lgammaN = 0; c->teamWarps = 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return LSDB_ERR_NO_DEVICE; }
     if (stream) { c->stream = (cudaStream_t)stream; c->ownStream = false; }
     else {
@@ -113,6 +114,12 @@ extern "C" int lsdb_create(lsdb_ctx** out, int device, void* stream) {
         return launchErr == cudaErrorNoKernelImageForDevice ? LSDB_ERR_NO_DEVICE : LSDB_ERR_CUDA;
     }
     *out = c;
+    return LSDB_OK;
+}
+
+extern "C" int lsdb_set_team_warps(lsdb_ctx* ctx, int warps) {
+    if (!ctx || warps < 0 || warps > LSDB_GROW_WARPS) return fail(ctx, LSDB_ERR_ARG, "lsdb_set_team_warps: 0 (automatic) .. 16%s");
+    ctx->teamWarps = warps;
     return LSDB_OK;
 }
 
@@ -268,6 +275,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         const int sizeCap = maxN < 30000 ? 4 : 8;
         if (nw > sizeCap) nw = sizeCap;
         if (nw < 1) nw = 1;   // thousands of small maps (scan rasters): one warp each beats teams of 4 (2048 rasters: 36.6 vs 54.8 ms)
+        if (ctx->teamWarps > 0) nw = ctx->teamWarps;
         if (getenv("LSDB_GROW_WARPS")) { int v = atoi(getenv("LSDB_GROW_WARPS")); if (v >= 1 && v <= LSDB_GROW_WARPS) nw = v; }
         b->nWarps = nw;
         // one-warp teams = thousands of small maps: the shared-memory copy of the ban plane would cap the resident maps per SM

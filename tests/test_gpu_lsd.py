@@ -251,6 +251,26 @@ def test_result_is_independent_of_team_shape(lsdb, ctx, gold, env):
     b.close()
 
 
+@pytest.mark.parametrize("warps", [1, 4, 16])
+def test_team_size_set_through_the_abi(lsdb, warps):
+    """lsdb_set_team_warps: the caller's team size (several small batches in flight want 4 where one alone gets 8) — same result."""
+    c = lsdb.Context(0)
+    try:
+        c.set_team_warps(warps)
+        maps = [synth.occupancy_grid(1200, 900, seed=91), synth.occupancy_grid(700, 1000, seed=92, border_walls=True)]
+        b = lsdb.Batch(c, [(m.shape[1], m.shape[0]) for m in maps])
+        b.upload(maps); b.run()
+        got = b.download(want_rects=True)
+        for i, m in enumerate(maps):
+            _compare_with_oracle(lsdb, b, i, m, got, check_planes=False)
+        b.close()
+        with pytest.raises(lsdb.LsdbError, match="ARG"):
+            c.set_team_warps(17)
+        c.set_team_warps(0)
+    finally:
+        c.close()
+
+
 def test_giant_map_on_one_gpu(lsdb, ctx):
     """BASELINE config 5 shape (one 16384x16384 map, seed 5000) on a single GPU: segment table and rectangles bit-exact
     against the oracle.  (Tiling it across GPUs is not built; this pins the single-GPU result the tiled version must keep.)"""
