@@ -289,18 +289,23 @@ def main():
     # batches in flight: enough to keep ~1280 maps on the device (what five 256-map batches are) when a rank's share is smaller
     # (strong scaling), at most 12; the region stage's rate depends on how many maps are resident, not on how they are batched
     NB = args.inflight if args.inflight > 0 else max(5, min(12, -(-1280 // n)))
-    # The library sizes a batch's teams as if the batch were alone on the device (8 warps per map below ~150 maps).  With NB such
-    # batches in flight the device is full of maps anyway, and 4-warp teams (four per SM instead of one) are what fills it.
     team_note = "library default"
     streams = [torch.cuda.Stream() for _ in range(NB)]
     torch.cuda.set_stream(streams[0])
     stream = streams[0]
     ctxs = [lsdb.Context(local, st.cuda_stream) for st in streams]
     ctx = ctxs[0]
-    if n < 256 and NB * n >= 256:
-        for c_ in ctxs:
-            c_.set_team_warps(4)
-        team_note = "4 warps per map (lsdb_set_team_warps: the batches in flight fill the device)"
+    # Team size of the region stage.  The library picks it as if a batch were alone on the device (4 warps per map at 256 maps,
+    # 8 below ~150).  With NB batches in flight the device is full of maps, the stage is bound by instruction supply (DESIGN.md
+    # §4.3) and smaller teams do less speculative work per map: measured 250.8 / 189.8 / 207.6 / 216.6 ms per 256-map step with
+    # 1 / 2 / 3 / 4 warps per map (1 184 two-warp teams fit on 148 SMs).
+    tw = 0
+    if "LSDB_GROW_WARPS" not in os.environ:
+        tw = 2 if NB * n >= 1184 else (4 if n < 256 and NB * n >= 256 else 0)
+        if tw:
+            for c_ in ctxs:
+                c_.set_team_warps(tw)
+            team_note = f"{tw} warps per map (lsdb_set_team_warps: the batches in flight fill the device)"
     host = torch.empty((n, size, size), dtype=torch.uint8).pin_memory()
     hnp = host.numpy()
     for i in range(n):
@@ -371,8 +376,19 @@ def main():
     # Every step copies its 256 maps from pinned host memory, runs the pipeline and reads the segment tables back.
     # Two batches on two private streams alternate (one host thread each; ctypes drops the GIL), so the H2D copy of
     # one step overlaps the kernels of the other: the steady state of a caller that streams batches through the library.
+    # The copy phases of a worker leave the device less full than the resident loop does: the library's 4-warp teams are the faster
+    # ones here (measured, 20 steps: 19.7 Gpixel/s against 18.0 with 2-warp teams) — fresh batches with that team size.
+    e2e_team_note = team_note
+    if tw == 2:
+        for bt in batches:
+            bt.close()
+        for c_ in ctxs:
+            c_.set_team_warps(4)
+        batches = [lsdb.Batch(c, [(size, size)] * n) for c in ctxs]
+        batch = batches[0]
+        e2e_team_note = "4 warps per map (the library's choice for a 256-map batch)"
     workers = list(zip(ctxs, batches))
-    e2e_steps = NB * max(1, (args.steps + NB - 1) // NB)  # a multiple of the worker count
+    e2e_steps = NB * max(4, (args.steps + NB - 1) // NB)  # a multiple of the worker count; four rounds or more, so that the ramp and the tail of the pipeline do not dominate
     nseg_box = [0] * NB
     # lineIm of every map, too (what the reference's call returns besides the table): one pinned output buffer per worker
     want_im = args.e2e_line_images == "on"
@@ -419,6 +435,8 @@ def main():
         bw.close()
 
     # the side measurements below run with the big batches released (they allocate batches of their own)
+    for c_ in ctxs:
+        c_.set_team_warps(0)   # the side measurements below run one batch at a time: the library's own team sizes
     # ---------------- config 1 latency: the reference's own single-map run (data/mapValue.txt, 1377x428), one map per call
     lat = None
     try:
@@ -600,7 +618,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * size * size, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "line_images": bool(want_im), "tables_only_value": e2e_tables,
                     "how": "lsdb_batch_upload (pinned host -> HBM) + lsdb_batch_run + lsdb_batch_download" + (" + lsdb_batch_line_images (lineIm of every map -> pinned host)" if want_im else "") + " per step; "
-                                               f"{NB} batches on {NB} streams alternate so copies overlap kernels"},
+                                               f"{NB} batches on {NB} streams alternate so copies overlap kernels", "teams": e2e_team_note},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"kernel": "lsdb_stencil_kernel (remap+Gaussian+gradient)", "bound": "hbm", "achieved": achieved, "peak": peak,
