@@ -360,7 +360,8 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaMemsetAsync(b->labels, 0, b->totalN * 4, s));
     CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
     CK(ctx, cudaEventRecord(b->ev[0], s));
-    lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->banBits, b->nzBits, b->gaussDbg);
+    const int nStencil = lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->banBits, b->nzBits, b->gaussDbg, 0,
+                        b->cells, b->totalN * 4, b->imgCounter + 8);   // the seed-list plane is free until the ordering stage: scratch for the deferred pixels
     CK(ctx, cudaEventRecord(b->ev[1], s));
     lsdb_launch_order(s, b->n, b->nBands, b->imgsD, b->dyn, b->kcD, b->mag, b->nzBits, b->bandOf, b->bandsOfImg, b->orderTabs, b->bins, b->cells);
     CK(ctx, cudaEventRecord(b->ev[2], s));
@@ -369,7 +370,7 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
                      b->bmCapWords, b->steal);
     CK(ctx, cudaEventRecord(b->ev[3], s));
     CK(ctx, cudaGetLastError());
-    b->ran = true; b->downloaded = false; b->launches = 5;
+    b->ran = true; b->downloaded = false; b->launches = 4 + nStencil;
     return LSDB_OK;
 }
 
@@ -392,11 +393,11 @@ extern "C" int lsdb_batch_run_stencil_rows(lsdb_batch* b, int tileRow0, int tile
     CK(ctx, cudaMemsetAsync(b->labels, 0, b->totalN * 4, s));
     CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
     CK(ctx, cudaEventRecord(b->ev[0], s));
-    lsdb_launch_stencil(s, (tileRow1 - tileRow0) * im.tilesX, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state,
-                        b->banBits, b->nzBits, b->gaussDbg, tileRow0 * im.tilesX);
+    const int nStencil = lsdb_launch_stencil(s, (tileRow1 - tileRow0) * im.tilesX, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state,
+                        b->banBits, b->nzBits, b->gaussDbg, tileRow0 * im.tilesX, b->cells, b->totalN * 4, b->imgCounter + 8);
     CK(ctx, cudaEventRecord(b->ev[1], s));
     CK(ctx, cudaGetLastError());
-    b->ran = false; b->downloaded = false; b->launches = 1;
+    b->ran = false; b->downloaded = false; b->launches = nStencil;
     return LSDB_OK;
 }
 

@@ -257,6 +257,25 @@ LSDM_FN double lsdm_sincos_eval(double x, int want_cos) {
 LSDM_FN double lsdm_sin(double x) { return lsdm_sincos_eval(x, 0); }
 LSDM_FN double lsdm_cos(double x) { return lsdm_sincos_eval(x, 1); }
 
+/* Phase 1 of lsdm_sin AND lsdm_cos of the same argument, sharing the reduction.  Returns 1 with *s == lsdm_sin(x) and
+ * *c == lsdm_cos(x) (the same operations in the same order as lsdm_sincos_eval, hence the same bits) when both rounding
+ * tests pass; returns 0 — outputs unspecified — when either needs phase 2 or x is not finite: the caller then calls
+ * lsdm_sin / lsdm_cos.  Lets a kernel keep its warps on the short path and collect the rare phase-2 arguments elsewhere. */
+LSDM_FN int lsdm_sincos_try(double x, double* s, double* c) {
+    if (lsdm_isnan(x) || lsdm_isinf(x)) return 0;
+    if (fabs(x) < 0x1p-27) { *s = x; *c = 1.0; return 1; }
+    lsdm_dd r;
+    const int n = lsdm_rem_pio2(x, &r);
+    const int ns = n & 3, nc = (n + 1) & 3;
+    lsdm_dd fs = lsdm_sincos_fast(r.h, r.l, ns & 1);
+    lsdm_dd fc = lsdm_sincos_fast(r.h, r.l, nc & 1);
+    if (ns & 2) { fs.h = -fs.h; fs.l = -fs.l; }
+    if (nc & 2) { fc.h = -fc.h; fc.l = -fc.l; }
+    const int oks = lsdm_round_ok(fs.h, fs.l, s);
+    const int okc = lsdm_round_ok(fc.h, fc.l, c);
+    return oks & okc;
+}
+
 /* =====================================================================  atan2 / atan  */
 
 /* phase 2: atan(a/b) for 0 < a <= b (finite), ~2^-100 */
@@ -346,6 +365,25 @@ LSDM_FN double lsdm_atan2(double y, double x) {
     return yneg ? -r : r;
 }
 LSDM_FN double lsdm_atan(double x) { return lsdm_atan2(x, 1.0); }
+
+/* Phase 1 of lsdm_atan2 for finite non-zero operands: returns 1 with *out == lsdm_atan2(y, x) when the rounding test
+ * passes, 0 (output unspecified) when phase 2 is needed or an operand is zero / infinite / NaN — the caller then calls
+ * lsdm_atan2.  Same operations as lsdm_atan2's general branch; the operands of the ratio are selected instead of the
+ * call being duplicated, so a warp whose lanes disagree on |y| > |x| runs the ratio code once. */
+LSDM_FN int lsdm_atan2_try(double y, double x, double* out) {
+    const double ay = fabs(y), ax = fabs(x);
+    if (!(ay > 0.0) || !(ax > 0.0) || lsdm_isinf(ax) || lsdm_isinf(ay)) return 0;   /* zero, NaN or infinite */
+    const int yneg = lsdm_signbit(y), xneg = lsdm_signbit(x);
+    const int swap = ay > ax;
+    const double lo = swap ? ax : ay, hi = swap ? ay : ax;
+    lsdm_dd f = lsdm_atan_ratio_fast(lo, hi);
+    if (swap) f = lsdm_const_minus(LSDM_PIO2_H, LSDM_PIO2_L, f);
+    if (xneg) f = lsdm_const_minus(LSDM_PI_H, LSDM_PI_L, f);
+    double r;
+    const int ok = lsdm_round_ok(f.h, f.l, &r);
+    *out = yneg ? -r : r;
+    return ok;
+}
 
 /* =====================================================================  exp / log family (double-double)  */
 

@@ -20,6 +20,7 @@
 //
 // One CTA per 32x32 tile of the scaled image; source window <= 136 x 160 bytes.
 // HBM traffic per source pixel: 1 B read + 0.09*(8+8+4 [+16 for growable pixels]) B written.
+#include <stdlib.h>
 #include "lsdb_common.cuh"
 
 #define SRC_PITCH LSDB_SRC_PITCH
@@ -375,10 +376,20 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
     }
 }
 
-void lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
+int lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
-                         unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase) {
+                         unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase,
+                         void* deferBuf, size_t deferBytes, int* deferCount) {
+    // LSDB_STENCIL=1: this file's kernel (the first cut); anything else: stencil2.cu.  LSDB_STENCIL_DEFER=0 keeps the deferred
+    // pixels of stencil2.cu inside their tiles.
+    static const int version = [] { const char* e = getenv("LSDB_STENCIL"); return e && e[0] == '1' ? 1 : 2; }();
+    static const bool defer = [] { const char* e = getenv("LSDB_STENCIL_DEFER"); return !(e && e[0] == '0'); }();
+    if (version == 2) {
+        return lsdb_launch_stencil_v2(s, nTiles, imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase,
+                                      defer ? deferBuf : nullptr, deferBytes, deferCount);
+    }
     cudaFuncSetAttribute(lsdb_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StencilSmem));   // per device, cheap
     if (nTiles > 0)
         lsdb_stencil_kernel<<<nTiles, NT, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase);
+    return nTiles > 0 ? 1 : 0;
 }

@@ -38,3 +38,14 @@ void v_log(const double* x, double* o, int n) { for (int i = 0; i < n; i++) o[i]
 void v_log10(const double* x, double* o, int n) { for (int i = 0; i < n; i++) o[i] = lsdm_log10(x[i]); }
 void v_sinh(const double* x, double* o, int n) { for (int i = 0; i < n; i++) o[i] = lsdm_sinh(x[i]); }
 void v_pow(const double* x, const double* y, double* o, int n) { for (int i = 0; i < n; i++) o[i] = lsdm_pow(x[i], y[i]); }
+/* the phase-1-only entry points the stencil stage uses: out = value where ok, count of ok returned */
+int v_atan2_try(const double* y, const double* x, double* o, unsigned char* ok, int n) {
+    int k = 0;
+    for (int i = 0; i < n; i++) { ok[i] = (unsigned char)lsdm_atan2_try(y[i], x[i], &o[i]); k += ok[i]; }
+    return k;
+}
+int v_sincos_try(const double* x, double* s, double* c, unsigned char* ok, int n) {
+    int k = 0;
+    for (int i = 0; i < n; i++) { ok[i] = (unsigned char)lsdm_sincos_try(x[i], &s[i], &c[i]); k += ok[i]; }
+    return k;
+}
