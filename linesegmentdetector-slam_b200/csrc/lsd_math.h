@@ -299,12 +299,16 @@ LSDM_SLOW lsdm_dd lsdm_atan_ratio_dd(double a, double b) {
     return lsdm_dd_add(lsdm_tab_dd(LSDM_ATAN_TAB, j), at);
 }
 
+/* x / b for b > 0.  A zero numerator — the remainder of an exact quotient, e.g. |y| == |x| — is returned as it is (0 / b is that
+ * same zero): the GPU's double division leaves its short path for a zero dividend, and a diagonal gradient has three of them. */
+LSDM_FN double lsdm_div_pos(double x, double b) { return x == 0.0 ? x : x / b; }
+
 /* phase 1: atan(a/b) for 0 < a <= b, result (h,l) with relative error < 2^-63 */
 LSDM_FN lsdm_dd lsdm_atan_ratio_fast(double a, double b) {
     double th = a / b;
     lsdm_dd p = lsdm_two_prod(th, b);
     double rem = (a - p.h) - p.l; /* exact remainder of the division */
-    double tl = rem / b;
+    double tl = lsdm_div_pos(rem, b);
     int j = (int)(th * 64.0 + 0.5);
     double uh, ul, Ah = 0.0, Al = 0.0;
     if (j == 0) {
@@ -315,10 +319,10 @@ LSDM_FN lsdm_dd lsdm_atan_ratio_fast(double a, double b) {
         lsdm_dd cp = lsdm_two_prod(c, th);
         lsdm_dd den = lsdm_fast_two_sum(1.0, cp.h);
         double denl = (den.l + cp.l) + c * tl;
-        uh = num.h / den.h;
+        uh = lsdm_div_pos(num.h, den.h);
         lsdm_dd q = lsdm_two_prod(uh, den.h);
         double r3 = ((num.h - q.h) - q.l) + (num.l - uh * denl);
-        ul = r3 / den.h;
+        ul = lsdm_div_pos(r3, den.h);
         Ah = LSDM_ATAN_TAB[2 * j]; Al = LSDM_ATAN_TAB[2 * j + 1];
     }
     double u2 = uh * uh;

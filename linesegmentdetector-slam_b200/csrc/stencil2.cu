@@ -227,13 +227,13 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
     const uint8_t* win = src + im.srcOff + ax0;   // window column 0 of source row 0
     {
         unsigned int any = 0;
-        for (int o = tid; o < nRows * nVec; o += NT) {
-            int r = o / nVec, v = o - r * nVec;
-            int gy = sy0 + r;
-            const uint4 q = *reinterpret_cast<const uint4*>(win + (size_t)gy * im.srcPitch + 16 * v);
+        // element o of the window = (row o / nVec, vector o % nVec); nVec <= 10 and o < 1360: the quotient by a multiply
+        const unsigned int inv = (65536u + (unsigned int)nVec - 1u) / (unsigned int)nVec;
+        const int nEl = nRows * nVec;
+        auto flag = [&](const uint4 q, int r, int v) {
+            if ((q.x | q.y | q.z | q.w) == 0u) return;   // free space: stays 0, nothing to flag (the common case)
             unsigned int w[4] = {q.x, q.y, q.z, q.w};
-            if ((q.x | q.y | q.z | q.w) == 0u) continue;   // free space: stays 0, nothing to flag (the common case)
-            if (gy >= 1) {
+            if (sy0 + r >= 1) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     unsigned int e1 = __vcmpeq4(w[k], 0x01010101u), e255 = __vcmpeq4(w[k], 0xffffffffu);
@@ -247,6 +247,17 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
                 atomicOr(&S.rowBits[r * ROW_WORDS + (v >> 1)], nz << ((v & 1) * 16));
                 any = 1;
             }
+        };
+        // two loads in flight per thread before the first is looked at
+        for (int o = tid; o < nEl; o += 2 * NT) {
+            const int o2 = o + NT;
+            const int r = (int)(((unsigned int)o * inv) >> 16), v = o - r * nVec;
+            const int r2 = (int)(((unsigned int)o2 * inv) >> 16), v2 = o2 - r2 * nVec;
+            const uint4 q = *reinterpret_cast<const uint4*>(win + (size_t)(sy0 + r) * im.srcPitch + 16 * v);
+            uint4 q2 = make_uint4(0u, 0u, 0u, 0u);
+            if (o2 < nEl) q2 = *reinterpret_cast<const uint4*>(win + (size_t)(sy0 + r2) * im.srcPitch + 16 * v2);
+            flag(q, r, v);
+            flag(q2, r2, v2);
         }
         if (any) S.anySrc = 1;
     }
@@ -393,12 +404,19 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
             S.stT[t] = (unsigned char)st;
             banned = st != 0;
         }
-        const int sg = st2_append(&S.qn, needG, lane);
-        const int sb = st2_append(&S.qb, needB, lane);
-        const int sa = st2_append(&S.qt, needA, lane);
-        if (sg >= 0) S.queue[sg] = (unsigned short)t;             // at most 1024 pixels in all: the front and the back never meet
-        if (sb >= 0) S.u.out.queueB[sb] = (unsigned short)t;
-        if (sa >= 0) S.queue[1023 - sa] = (unsigned short)t;
+        {   // the three queues in one go: lanes 0..2 reserve for one queue each (qn, qb, qt are consecutive ints)
+            const unsigned int balG = __ballot_sync(0xffffffffu, needG), balB = __ballot_sync(0xffffffffu, needB), balA = __ballot_sync(0xffffffffu, needA);
+            int base = 0;
+            if (lane < 3) {
+                const unsigned int bl = lane == 0 ? balG : (lane == 1 ? balB : balA);
+                if (bl) base = atomicAdd(&S.qn + lane, __popc(bl));
+            }
+            const int bG = __shfl_sync(0xffffffffu, base, 0), bB = __shfl_sync(0xffffffffu, base, 1), bA = __shfl_sync(0xffffffffu, base, 2);
+            const unsigned int below = (1u << lane) - 1u;
+            if (needG) S.queue[bG + __popc(balG & below)] = (unsigned short)t;             // at most 1024 pixels in all: the front and the back never meet
+            if (needB) S.u.out.queueB[bB + __popc(balB & below)] = (unsigned short)t;
+            if (needA) S.queue[1023 - (bA + __popc(balA & below))] = (unsigned short)t;
+        }
         // usedMap==1 as one bit per pixel, row-pitched: the region pipeline keeps this plane in shared memory
         const unsigned int bal = __ballot_sync(0xffffffffu, banned);
         const unsigned int nzb = __ballot_sync(0xffffffffu, nonzero);
