@@ -104,9 +104,9 @@ def cpu_reference_throughput(size, n_maps, threads, first_gidx=0):
 
 
 def stencil_traffic(n, size):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE lsdb_stencil_kernel launch, from this round's ncu capture
-    (profiles/r2_stencil_traffic.json, written by tools/ncu_summary.py from the .ncu-rep), scaled to this launch's
-    source pixels.  None when no capture of this round is on record."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE stencil launch (lsdb_stencil2_kernel), from this round's ncu
+    capture (profiles/r2_stencil_traffic.json, written by tools/stencil_traffic.py from the .ncu-rep), scaled to this
+    launch's source pixels.  None when no capture of this round is on record."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r2_stencil_traffic.json")))
         return float(t["dram_bytes"]) * (n * size * size) / float(t["source_pixels"])
@@ -213,9 +213,9 @@ def run_giant(args, rank, world, local):
                 "e2e": {"value": size * size / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": size * size,
                         "d2h_bytes_per_step": int(out["counts"][0]) * 13 * 8 + 128,
                         "how": "Batch create + lsdb_batch_upload of the whole map from pinned host memory on every rank + tiled run + download on rank 0"},
-                "gpu_launches": 5 * args.steps,
+                "gpu_launches": 6 * args.steps,   # stencil tiles + its deferred pixels, ordering x3, regions (rank 0)
                 "clocks": clocks,
-                "roofline": {"kernel": "lsdb_stencil_kernel on this rank's band", "bound": "hbm", "achieved": alg / (ms_stencil * 1e-3) / 1e9,
+                "roofline": {"kernel": "lsdb_stencil2_kernel on this rank's band", "bound": "hbm", "achieved": alg / (ms_stencil * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": alg / (ms_stencil * 1e-3) / 1e9 / peak, "traffic": None,
                              "algorithmic_bytes_per_launch": alg, "kernel_ms": ms_stencil},
                 "note": "the seed loop is one sequential chain over the map: the region stage runs on rank 0 and does not shrink with the GPU count"}
@@ -621,7 +621,7 @@ def main():
                                                f"{NB} batches on {NB} streams alternate so copies overlap kernels", "teams": e2e_team_note},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "lsdb_stencil_kernel (remap+Gaussian+gradient)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "lsdb_stencil2_kernel (remap+Gaussian+gradient; + lsdb_stencil_deferred_kernel, 0.02 ms)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 256 maps of 4096^2 (profiles/r1z_ncu_full_summary.txt),
                          # scaled to this launch's map count: the extra over the algorithmic bytes is the cos/sin planes of growable

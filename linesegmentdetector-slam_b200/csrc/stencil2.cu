@@ -21,6 +21,7 @@
 //     deg / cos / sin after the tiles are done.  A tile whose reservation does not fit the list evaluates its own.
 //
 // One CTA per 32x32 tile of the scaled image; source window <= 136 x 160 bytes; four CTAs per SM.
+#include <stdlib.h>
 #include "lsdb_common.cuh"
 
 #define SRC_PITCH LSDB_SRC_PITCH
@@ -33,7 +34,7 @@
 
 struct LsdbDeferRec { unsigned long long p; double gx, gy; };   // pixel (index into the planes), gradX, gradY
 
-struct Stencil2Smem {
+struct __align__(16) Stencil2Smem {
     union {
         double aux[LSDB_SRC_MAX * GW];                       // X-pass output (only flagged elements are written/read)
         struct {                                             // after the Y pass: output tiles and the second angle queue
@@ -168,18 +169,26 @@ __device__ __noinline__ void st2_angle_full(double gradX, double gradY, double p
     if (growable) { *c_ = lsdm_cos(d); *s_ = lsdm_sin(d); }
 }
 
-__global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __restrict__ imgs, const int* __restrict__ tileImg,
+// G tiles per CTA, one group of NT threads each, all groups in step from barrier to barrier.  An experiment that stays
+// selectable (LSDB_STENCIL_G): ncu shows the GPC-level instruction cache at 85 % of its request peak with four independent
+// 8-warp CTAs per SM walking ~50 KB of code once per tile, and warps that run the same phase at the same time share what they
+// fetch — but they also wait on each other's barriers, and G = 2 / 4 measured 13 % / 33 % slower than G = 1.
+template <int G>
+__global__ void __launch_bounds__(NT * G, 4 / G) lsdb_stencil2_kernel(const LsdbImg* __restrict__ imgs, const int* __restrict__ tileImg,
                                                            LsdbImgDyn* __restrict__ dyn, const LsdbLsdConst* __restrict__ kc,
                                                            const uint8_t* __restrict__ src, double* __restrict__ mag,
                                                            double* __restrict__ deg, double* __restrict__ cosm,
                                                            double* __restrict__ sinm, unsigned int* __restrict__ state,
                                                            unsigned int* __restrict__ banBits, unsigned int* __restrict__ nzBits,
-                                                           double* __restrict__ gaussOut, int tileBase,
+                                                           double* __restrict__ gaussOut, int tileBase, int nTilesLaunch,
                                                            LsdbDeferRec* __restrict__ deferBuf, long long deferCap, int* __restrict__ deferCount) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Stencil2Smem& S = *reinterpret_cast<Stencil2Smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tileIdx = blockIdx.x + tileBase;   // a launch may cover a range of tiles only (one map tiled over several GPUs)
+    const int grp = G == 1 ? 0 : (int)threadIdx.x / NT;
+    Stencil2Smem& S = reinterpret_cast<Stencil2Smem*>(smem_raw)[grp];
+    const int tid = (int)threadIdx.x - grp * NT, lane = tid & 31, warp = tid >> 5;
+    int launchTile = (int)blockIdx.x * G + grp;
+    if (launchTile >= nTilesLaunch) launchTile = nTilesLaunch - 1;   // a group past the end repeats the last tile: the same values written twice
+    const int tileIdx = launchTile + tileBase;   // a launch may cover a range of tiles only (one map tiled over several GPUs)
     const int imgIdx = tileImg[tileIdx];
     const LsdbImg im = imgs[imgIdx];
     const int lt = tileIdx - im.tile0;
@@ -213,13 +222,17 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
     if (tid < 51) S.taps[tid] = kc->taps[tid];
     if (tid < gw) {   // tap positions of column tid (window-relative); consecutive unless reflected at an image border
         const int xc = lsdb_x86_d2i(floor((gxs + tid) / sca + 0.5));
+#pragma unroll 1
         for (int i = 0; i < 17; i++) S.idxX[tid * 17 + i] = (short)((contigX ? xc - h + i : st2_reflect(xc - h + i, im.cols)) - ax0);
     } else if (tid >= 64 && tid < 64 + gh) {
         const int r = tid - 64;
         const int yc = lsdb_x86_d2i(floor((gys + r) / sca + 0.5));
+#pragma unroll 1
         for (int i = 0; i < 17; i++) S.idxY[r * 17 + i] = (short)((contigY ? yc - h + i : st2_reflect(yc - h + i, im.rows)) - sy0);
     }
+#pragma unroll 1
     for (int o = tid; o < nRows * ROW_WORDS; o += NT) S.rowBits[o] = 0u;
+#pragma unroll 1
     for (int o = tid; o < GW * ROW_WORDS; o += NT) S.colBits[o] = 0u;
     __syncthreads();
 
@@ -259,12 +272,12 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
             flag(q, r, v);
             flag(q2, r2, v2);
         }
-        if (any) S.anySrc = 1;
+        (void)any;
     }
     __syncthreads();
-    const bool tileHasData = S.anySrc != 0;   // uniform
 
-    if (tileHasData) {
+    {   // (no shortcut for a tile whose window is all zero: its lists stay empty and the Y pass writes the zeros — every barrier
+        // below is reached by every thread of the CTA whatever its group's tile holds)
         // ---- X pass.  The rows that hold a non-zero pixel are listed first.
         for (int r = tid; r < nRows; r += NT) {
             const unsigned int* rb = &S.rowBits[r * ROW_WORDS];
@@ -273,23 +286,17 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
         __syncthreads();
         const int nNe = S.nNe;
         // phase 1: which (row, column) outputs have a non-zero tap.  A warp takes a listed row for columns 0..31; the 33rd
-        // column of all rows is swept afterwards, one row per thread (nNe <= LSDB_SRC_MAX < NT).
-        for (int k = warp; k < nNe; k += NT / 32) {
-            const int r = S.neRows[k];
-            const unsigned int m = lane < gw ? st2_mask(&S.rowBits[r * ROW_WORDS], &S.idxX[lane * 17], contigX) : 0u;
+        // column comes as extra trips of the same loop, 32 listed rows per trip (one copy of the code).
+        const int nExtraX = gw > 32 ? (nNe + 31) >> 5 : 0;
+        for (int k = warp; k < nNe + nExtraX; k += NT / 32) {
+            int r, c; bool valid;
+            if (k < nNe) { r = S.neRows[k]; c = lane; valid = lane < gw; }
+            else { const int kk = (k - nNe) * 32 + lane; valid = kk < nNe; r = valid ? S.neRows[kk] : 0; c = 32; }
+            const unsigned int m = valid ? st2_mask(&S.rowBits[r * ROW_WORDS], &S.idxX[c * 17], contigX) : 0u;
             const int slot = st2_append(&S.nX, m != 0u, lane);
             if (slot >= 0) {
-                if (slot < XCAP) S.v.xItems[slot] = (unsigned short)((r << 6) | lane);
-                else st2_x_item_cold(S, r, lane, m, win, im.srcPitch, sy0, ax0, gxs);
-            }
-        }
-        {
-            unsigned int m = 0u; int r = 0;
-            if (gw > 32 && tid < nNe) { r = S.neRows[tid]; m = st2_mask(&S.rowBits[r * ROW_WORDS], &S.idxX[32 * 17], contigX); }
-            const int slot = st2_append(&S.nX, m != 0u, lane);
-            if (slot >= 0) {
-                if (slot < XCAP) S.v.xItems[slot] = (unsigned short)((r << 6) | 32);
-                else st2_x_item_cold(S, r, 32, m, win, im.srcPitch, sy0, ax0, gxs);
+                if (slot < XCAP) S.v.xItems[slot] = (unsigned short)((r << 6) | c);
+                else st2_x_item_cold(S, r, c, m, win, im.srcPitch, sy0, ax0, gxs);
             }
         }
         __syncthreads();
@@ -306,41 +313,26 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
         __syncthreads();   // aux and colBits complete; the X work list (in the storage of g) is dead
 
         // ---- Y pass, same two phases; an output without a non-zero tap is 0
-        for (int r = warp; r < gh; r += NT / 32) {
+        const int nExtraY = gw > 32 ? (gh + 31) >> 5 : 0;   // the 33rd column: extra trips, 32 rows each
+        for (int k = warp; k < gh + nExtraY; k += NT / 32) {
+            int r, c; bool valid;
+            if (k < gh) { r = k; c = lane; valid = lane < gw; }
+            else { r = (k - gh) * 32 + lane; valid = r < gh; c = 32; }
             unsigned int m = 0u;
-            if (lane < gw) {
-                m = st2_mask(&S.colBits[lane * ROW_WORDS], &S.idxY[r * 17], contigY);
+            if (valid) {
+                m = st2_mask(&S.colBits[c * ROW_WORDS], &S.idxY[r * 17], contigY);
                 if (m == 0u) {
-                    S.v.g[r * GW + lane] = 0.0;
-                    if (gaussOut) { const int gx = gxs + lane, gy = gys + r; if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = 0.0; }
+                    S.v.g[r * GW + c] = 0.0;
+                    if (gaussOut) { const int gx = gxs + c, gy = gys + r; if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = 0.0; }
                 }
             }
             const int slot = st2_append(&S.nY, m != 0u, lane);
             if (slot >= 0) {
-                if (slot < YCAP) S.queue[slot] = (unsigned short)((r << 6) | lane);
+                if (slot < YCAP) S.queue[slot] = (unsigned short)((r << 6) | c);
                 else {
-                    const double v = st2_y_item_cold(S, r, lane, m, gys);
-                    S.v.g[r * GW + lane] = v;
-                    if (gaussOut) { const int gx = gxs + lane, gy = gys + r; if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = v; }
-                }
-            }
-        }
-        {
-            unsigned int m = 0u; const int r = tid;
-            if (gw > 32 && r < gh) {
-                m = st2_mask(&S.colBits[32 * ROW_WORDS], &S.idxY[r * 17], contigY);
-                if (m == 0u) {
-                    S.v.g[r * GW + 32] = 0.0;
-                    if (gaussOut) { const int gx = gxs + 32, gy = gys + r; if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = 0.0; }
-                }
-            }
-            const int slot = st2_append(&S.nY, m != 0u, lane);
-            if (slot >= 0) {
-                if (slot < YCAP) S.queue[slot] = (unsigned short)((r << 6) | 32);
-                else {
-                    const double v = st2_y_item_cold(S, r, 32, m, gys);
-                    S.v.g[r * GW + 32] = v;
-                    if (gaussOut) { const int gx = gxs + 32, gy = gys + r; if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = v; }
+                    const double v = st2_y_item_cold(S, r, c, m, gys);
+                    S.v.g[r * GW + c] = v;
+                    if (gaussOut) { const int gx = gxs + c, gy = gys + r; if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = v; }
                 }
             }
         }
@@ -354,14 +346,6 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
                 const double v = st2_y_item(S, r, c, m, gys);
                 S.v.g[r * GW + c] = v;
                 if (gaussOut) { const int gx = gxs + c, gy = gys + r; if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = v; }
-            }
-        }
-    } else {
-        for (int o = tid; o < gh * gw; o += NT) {
-            S.v.g[o / gw * GW + o % gw] = 0.0;
-            if (gaussOut) {
-                int gx = gxs + o % gw, gy = gys + o / gw;
-                if (gx >= x0 && gy >= y0) gaussOut[im.nOff + (size_t)gy * im.W + gx] = 0.0;
             }
         }
     }
@@ -486,43 +470,41 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil2_kernel(const LsdbImg* __r
 
     // ---- the pixels whose rounding test failed: into the deferred list in HBM (pixel, gradient), or, when the tile's
     // reservation does not fit the list, evaluated here
-    const int nSlow = min(S.nSlow, SLOW_CAP);   // uniform
-    if (nSlow > 0) {
-        if (tid == 0) {
+    if (warp == 0) {   // a handful of pixels at most: one warp, no barrier inside
+        const int nSlow = min(S.nSlow, SLOW_CAP);
+        if (nSlow > 0) {
             long long base = -1;
-            if (deferBuf) {
+            if (lane == 0 && deferBuf) {
                 base = atomicAdd(deferCount, nSlow);
                 if (base + nSlow > deferCap) {
                     for (long long q = base; q < deferCap; q++) deferBuf[q].p = ~0ull;   // the part of the reservation inside the list: no-ops
                     base = -1;
                 }
             }
-            S.slowBase = base;
-        }
-        __syncthreads();
-        const long long base = S.slowBase;
-        for (int k = tid; k < nSlow; k += NT) {
-            const int t = S.slowQ[k];
-            const int gr = y0 + (t >> 5) - gys, gc = x0 + (t & 31) - gxs;
-            const double A = S.v.g[gr * GW + gc], B = S.v.g[gr * GW + gc - 1];
-            const double C = S.v.g[(gr - 1) * GW + gc], D = S.v.g[(gr - 1) * GW + gc - 1];
-            const double gradX = (B + D - A - C) / 2.0;
-            const double gradY = (C + D - A - B) / 2.0;
-            if (base >= 0) {
-                LsdbDeferRec rec;
-                rec.p = im.nOff + (unsigned long long)(y0 + (t >> 5)) * im.W + (x0 + (t & 31));
-                rec.gx = gradX; rec.gy = gradY;
-                deferBuf[base + k] = rec;
-            } else {
-                const bool growable = S.stT[t] == 0;
-                double d, cv = 0.0, sv = 0.0;
-                st2_angle_full(gradX, gradY, pi, growable, &d, &cv, &sv);
-                S.u.out.degT[t] = d;
-                if (growable) { S.u.out.cosT[t] = cv; S.u.out.sinT[t] = sv; }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int k = lane; k < nSlow; k += 32) {
+                const int t = S.slowQ[k];
+                const int gr = y0 + (t >> 5) - gys, gc = x0 + (t & 31) - gxs;
+                const double A = S.v.g[gr * GW + gc], B = S.v.g[gr * GW + gc - 1];
+                const double C = S.v.g[(gr - 1) * GW + gc], D = S.v.g[(gr - 1) * GW + gc - 1];
+                const double gradX = (B + D - A - C) / 2.0;
+                const double gradY = (C + D - A - B) / 2.0;
+                if (base >= 0) {
+                    LsdbDeferRec rec;
+                    rec.p = im.nOff + (unsigned long long)(y0 + (t >> 5)) * im.W + (x0 + (t & 31));
+                    rec.gx = gradX; rec.gy = gradY;
+                    deferBuf[base + k] = rec;
+                } else {
+                    const bool growable = S.stT[t] == 0;
+                    double d, cv = 0.0, sv = 0.0;
+                    st2_angle_full(gradX, gradY, pi, growable, &d, &cv, &sv);
+                    S.u.out.degT[t] = d;
+                    if (growable) { S.u.out.cosT[t] = cv; S.u.out.sinT[t] = sv; }
+                }
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- coalesced write-out (a deferred pixel gets deg = 0 here; lsdb_stencil_deferred_kernel writes its values afterwards)
     for (int ly = warp; ly < LSDB_TILE; ly += NT / 32) {
@@ -562,16 +544,29 @@ __global__ void __launch_bounds__(128) lsdb_stencil_deferred_kernel(const LsdbDe
     }
 }
 
+template <int G>
+static void st2_launch(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn, const LsdbLsdConst* kc,
+                       const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm, unsigned int* state, unsigned int* banBits,
+                       unsigned int* nzBits, double* gaussOut, int tileBase, LsdbDeferRec* recs, long long cap, int* deferCount) {
+    const int smem = (int)sizeof(Stencil2Smem) * G;
+    cudaFuncSetAttribute(lsdb_stencil2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, cheap
+    lsdb_stencil2_kernel<G><<<(nTiles + G - 1) / G, NT * G, smem, s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut,
+                                                                       tileBase, nTiles, recs, cap, deferCount);
+}
+
 int lsdb_launch_stencil_v2(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
-                            const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
-                            unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase,
-                            void* deferBuf, size_t deferBytes, int* deferCount) {
-    cudaFuncSetAttribute(lsdb_stencil2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Stencil2Smem));   // per device, cheap
+                           const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
+                           unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase,
+                           void* deferBuf, size_t deferBytes, int* deferCount) {
     if (nTiles <= 0) return 0;
+    // tiles per CTA (LSDB_STENCIL_G = 1, 2 or 4).  Measured on 64 maps of 4096^2: 3.66 / 4.14 / 4.87 ms — groups in step share
+    // their instruction fetches but wait on each other's barriers, and the waiting costs more: one tile per CTA is the default.
+    static const int groups = [] { const char* e = getenv("LSDB_STENCIL_G"); const int g = e ? atoi(e) : 1; return g == 2 || g == 4 ? g : 1; }();
     const long long cap = deferBuf && deferCount ? (long long)(deferBytes / sizeof(LsdbDeferRec)) : 0;
     LsdbDeferRec* recs = cap > 0 ? (LsdbDeferRec*)deferBuf : nullptr;
-    lsdb_stencil2_kernel<<<nTiles, NT, sizeof(Stencil2Smem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut,
-                                                                    tileBase, recs, cap, deferCount);
+    if (groups == 1) st2_launch<1>(s, nTiles, imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase, recs, cap, deferCount);
+    else if (groups == 4) st2_launch<4>(s, nTiles, imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase, recs, cap, deferCount);
+    else st2_launch<2>(s, nTiles, imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase, recs, cap, deferCount);
     if (recs) {
         // expected: ~1 record per tile; the grid is sized for that and strides over whatever the count turns out to be
         long long want = ((long long)nTiles + 127) / 128;

@@ -99,14 +99,16 @@ if __name__ == "__main__":
         rep = sys.argv[2]
         e1 = dict(os.environ, LSDB_STENCIL="1")
         e2 = dict(os.environ); e2.pop("LSDB_STENCIL", None)
-        e3 = dict(e2, LSDB_STENCIL_DEFER="0")
+        variants = [("stencil2.cu, 1 tile per CTA", dict(e2, LSDB_STENCIL_G="1"), "/tmp/ab_g1.npz"),
+                    ("stencil2.cu, 2 tiles per CTA", dict(e2, LSDB_STENCIL_G="2"), "/tmp/ab_g2.npz"),
+                    ("stencil2.cu, 4 tiles per CTA", dict(e2, LSDB_STENCIL_G="4"), "/tmp/ab_g4.npz"),
+                    ("stencil2.cu, 2 tiles per CTA, deferred pixels kept in the tile", dict(e2, LSDB_STENCIL_G="2", LSDB_STENCIL_DEFER="0"), "/tmp/ab_g2n.npz")]
         subprocess.check_call([sys.executable, __file__, "dump", "/tmp/ab_v1.npz"], env=e1)
-        subprocess.check_call([sys.executable, __file__, "dump", "/tmp/ab_v2.npz"], env=e2)
-        subprocess.check_call([sys.executable, __file__, "dump", "/tmp/ab_v2_nodefer.npz"], env=e3)
+        bad = 0
         with open(rep, "w") as f:
-            print("== stencil.cu (A) vs stencil2.cu (B)", file=f)
-            bad = compare("/tmp/ab_v1.npz", "/tmp/ab_v2.npz", f)
-            print("== stencil.cu (A) vs stencil2.cu without the deferred kernel (B)", file=f)
-            bad += compare("/tmp/ab_v1.npz", "/tmp/ab_v2_nodefer.npz", f)
+            for name, env, path in variants:
+                subprocess.check_call([sys.executable, __file__, "dump", path], env=env)
+                print("== stencil.cu (A) vs", name, "(B)", file=f)
+                bad += compare("/tmp/ab_v1.npz", path, f)
         print(open(rep).read())
         sys.exit(1 if bad else 0)
