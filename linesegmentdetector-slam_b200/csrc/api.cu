@@ -44,7 +44,7 @@ struct lsdb_batch {
     lsdb_ctx* ctx;
     int n;
     lsdb_lsd_params params;
-    int maxSeg, listCap, arenaCap, nTiles, nCtas, nWarps, runAhead, bmCapWords, steal;
+    int maxSeg, listCap, arenaCap, nTiles, nCtas, nWarps, runAhead, bmCapWords, steal, stencilMode;
     size_t totalN, totalSrc, totalBan;
     std::vector<LsdbImg> imgs;
     LsdbLsdConst kc;
@@ -283,6 +283,7 @@ extern "C" int lsdb_batch_create(lsdb_ctx* ctx, int n, const int* cols, const in
         if (nw == 1 && !getenv("LSDB_SMEM_BAN_KB")) b->bmCapWords = 0;
         b->runAhead = 0;   // chunks a map's team may speculate ahead of its commit frontier (0 = as far as the ring allows)
         if (getenv("LSDB_RUNAHEAD")) b->runAhead = atoi(getenv("LSDB_RUNAHEAD"));
+        b->stencilMode = lsdb_stencil_mode();
         b->steal = 0;   // measured: spreading large seeds over the team duplicates growth of neighbouring seeds; no net gain
         if (getenv("LSDB_STEAL")) b->steal = atoi(getenv("LSDB_STEAL")) & 0xff;
         if (getenv("LSDB_SUPER_SHIFT")) b->steal |= ((atoi(getenv("LSDB_SUPER_SHIFT")) & 3) + 1) << 8;   // chunks per claim = 1 << n (default: per map)
@@ -361,7 +362,7 @@ extern "C" int lsdb_batch_run(lsdb_batch* b) {
     CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
     CK(ctx, cudaEventRecord(b->ev[0], s));
     const int nStencil = lsdb_launch_stencil(s, b->nTiles, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state, b->banBits, b->nzBits, b->gaussDbg, 0,
-                        b->cells, b->totalN * 4, b->imgCounter + 8);   // the seed-list plane is free until the ordering stage: scratch for the deferred pixels
+                        b->cells, b->totalN * 4, b->imgCounter + 8, b->stencilMode);   // the seed-list plane is free until the ordering stage: scratch for the deferred pixels
     CK(ctx, cudaEventRecord(b->ev[1], s));
     lsdb_launch_order(s, b->n, b->nBands, b->imgsD, b->dyn, b->kcD, b->mag, b->nzBits, b->bandOf, b->bandsOfImg, b->orderTabs, b->bins, b->cells);
     CK(ctx, cudaEventRecord(b->ev[2], s));
@@ -394,7 +395,7 @@ extern "C" int lsdb_batch_run_stencil_rows(lsdb_batch* b, int tileRow0, int tile
     CK(ctx, cudaMemsetAsync(b->imgCounter, 0, 64, s));
     CK(ctx, cudaEventRecord(b->ev[0], s));
     const int nStencil = lsdb_launch_stencil(s, (tileRow1 - tileRow0) * im.tilesX, b->imgsD, b->tileImg, b->dyn, b->kcD, b->src, b->mag, b->deg, b->cosm, b->sinm, b->state,
-                        b->banBits, b->nzBits, b->gaussDbg, tileRow0 * im.tilesX, b->cells, b->totalN * 4, b->imgCounter + 8);
+                        b->banBits, b->nzBits, b->gaussDbg, tileRow0 * im.tilesX, b->cells, b->totalN * 4, b->imgCounter + 8, b->stencilMode);
     CK(ctx, cudaEventRecord(b->ev[1], s));
     CK(ctx, cudaGetLastError());
     b->ran = false; b->downloaded = false; b->launches = nStencil;

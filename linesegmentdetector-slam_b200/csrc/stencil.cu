@@ -376,18 +376,26 @@ __global__ void __launch_bounds__(NT, 4) lsdb_stencil_kernel(const LsdbImg* __re
     }
 }
 
+int lsdb_stencil_mode(void) {
+    // LSDB_STENCIL=1: this file's kernel (the first cut); anything else: stencil2.cu.  LSDB_STENCIL_G: tiles per CTA of stencil2.cu
+    // (1, 2 or 4; default 1).  LSDB_STENCIL_DEFER=0 keeps the deferred pixels of stencil2.cu inside their tiles.
+    const char* e = getenv("LSDB_STENCIL");
+    const int version = e && e[0] == '1' ? 1 : 2;
+    e = getenv("LSDB_STENCIL_G");
+    int g = e ? atoi(e) : 1;
+    if (g != 2 && g != 4) g = 1;
+    e = getenv("LSDB_STENCIL_DEFER");
+    const int defer = !(e && e[0] == '0');
+    return version | (g << 2) | (defer << 5);
+}
+
 int lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
                          unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase,
-                         void* deferBuf, size_t deferBytes, int* deferCount) {
-    // LSDB_STENCIL=1: this file's kernel (the first cut); anything else: stencil2.cu.  LSDB_STENCIL_DEFER=0 keeps the deferred
-    // pixels of stencil2.cu inside their tiles.
-    static const int version = [] { const char* e = getenv("LSDB_STENCIL"); return e && e[0] == '1' ? 1 : 2; }();
-    static const bool defer = [] { const char* e = getenv("LSDB_STENCIL_DEFER"); return !(e && e[0] == '0'); }();
-    if (version == 2) {
+                         void* deferBuf, size_t deferBytes, int* deferCount, int mode) {
+    if ((mode & 3) != 1)
         return lsdb_launch_stencil_v2(s, nTiles, imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase,
-                                      defer ? deferBuf : nullptr, deferBytes, deferCount);
-    }
+                                      (mode >> 5) & 1 ? deferBuf : nullptr, deferBytes, deferCount, (mode >> 2) & 7);
     cudaFuncSetAttribute(lsdb_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StencilSmem));   // per device, cheap
     if (nTiles > 0)
         lsdb_stencil_kernel<<<nTiles, NT, sizeof(StencilSmem), s>>>(imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase);

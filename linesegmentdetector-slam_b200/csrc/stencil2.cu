@@ -557,11 +557,10 @@ static void st2_launch(cudaStream_t s, int nTiles, const LsdbImg* imgs, const in
 int lsdb_launch_stencil_v2(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                            const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
                            unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase,
-                           void* deferBuf, size_t deferBytes, int* deferCount) {
+                           void* deferBuf, size_t deferBytes, int* deferCount, int groups) {
     if (nTiles <= 0) return 0;
-    // tiles per CTA (LSDB_STENCIL_G = 1, 2 or 4).  Measured on 64 maps of 4096^2: 3.66 / 4.14 / 4.87 ms — groups in step share
-    // their instruction fetches but wait on each other's barriers, and the waiting costs more: one tile per CTA is the default.
-    static const int groups = [] { const char* e = getenv("LSDB_STENCIL_G"); const int g = e ? atoi(e) : 1; return g == 2 || g == 4 ? g : 1; }();
+    // groups = tiles per CTA (LSDB_STENCIL_G = 1, 2 or 4).  Measured on 64 maps of 4096^2: 3.66 / 4.14 / 4.87 ms — groups in step
+    // share their instruction fetches but wait on each other's barriers, and the waiting costs more: one tile per CTA is the default.
     const long long cap = deferBuf && deferCount ? (long long)(deferBytes / sizeof(LsdbDeferRec)) : 0;
     LsdbDeferRec* recs = cap > 0 ? (LsdbDeferRec*)deferBuf : nullptr;
     if (groups == 1) st2_launch<1>(s, nTiles, imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase, recs, cap, deferCount);

@@ -251,6 +251,33 @@ def test_result_is_independent_of_team_shape(lsdb, ctx, gold, env):
     b.close()
 
 
+@pytest.mark.parametrize("env", [dict(LSDB_STENCIL="1"), dict(LSDB_STENCIL_DEFER="0"), dict(LSDB_STENCIL_G="2"), dict(LSDB_STENCIL_G="4", LSDB_STENCIL_DEFER="0")])
+def test_result_is_independent_of_the_stencil_cut(lsdb, ctx, gold, env):
+    """The stencil stage's first cut (stencil.cu, LSDB_STENCIL=1) stays in the library as the fallback of the second
+    (stencil2.cu: work lists, phase-1-only angle math, failed rounding tests deferred to a second kernel); the second
+    also runs with the deferred pixels kept in their tiles and with 2 / 4 tiles per CTA.  Same planes, seed lists and
+    segments as the oracle from every one of them — borders with reflected taps, a ragged 33rd column and row 0 / column 0
+    walls included."""
+    maps = [gold["mapValue/map"], synth.occupancy_grid(1057, 771, seed=91), synth.occupancy_grid(400, 1300, seed=92, border_walls=True),
+            synth.occupancy_grid(97, 45, seed=12), synth.occupancy_grid(2048, 2048, seed=93)]
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        b = lsdb.Batch(ctx, [(m.shape[1], m.shape[0]) for m in maps])
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    b.upload(maps); b.run()
+    got = b.download(want_rects=True)
+    assert b.launches() == (5 if env.get("LSDB_STENCIL") == "1" or env.get("LSDB_STENCIL_DEFER") == "0" else 6)
+    for i, m in enumerate(maps):
+        _compare_with_oracle(lsdb, b, i, m, got, check_planes=True)
+    b.close()
+
+
 @pytest.mark.parametrize("warps", [1, 4, 16])
 def test_team_size_set_through_the_abi(lsdb, warps):
     """lsdb_set_team_warps: the caller's team size (several small batches in flight want 4 where one alone gets 8) — same result."""

@@ -78,6 +78,36 @@ def test_atan2_atan(L):
     assert math.isnan(L.t_atan2(float("nan"), 1.0))
 
 
+def test_phase_one_entry_points_equal_the_full_functions(L):
+    """lsdm_atan2_try / lsdm_sincos_try (what the stencil stage runs per pixel; a failed rounding test sends the pixel to a
+    second kernel that calls the full functions): wherever they report success the bits are those of lsdm_atan2 / lsdm_sin /
+    lsdm_cos, they fail on a fraction of a percent of the arguments only, and never succeed on zero / infinite / NaN operands.
+    Exact quotients (|y| == |x| and friends: lsdm_div_pos returns the zero remainder without dividing) against mpmath."""
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(8)
+    n = 400000
+    y = rng.normal(size=n) * 10.0 ** rng.uniform(-6, 3, n); x = rng.normal(size=n) * 10.0 ** rng.uniform(-6, 3, n)
+    y[:50000] = x[:50000] * rng.choice([1.0, -1.0, 0.5, 2.0, 0.25, 64.0, 1.0 / 64], 50000)        # exact ratios
+    o = np.empty(n); ok = np.empty(n, np.uint8); ref = np.empty(n)
+    k = L.v_atan2_try(P(y), P(x), P(o), P(ok), n); L.v_atan2(P(y), P(x), P(ref), n)
+    m = ok.astype(bool)
+    assert np.array_equal(o[m].view(np.int64), ref[m].view(np.int64)) and k > 0.995 * n
+    for i in range(0, 50000, 97):
+        assert ref[i] == _cr(mp.atan2(mp.mpf(float(y[i])), mp.mpf(float(x[i])))), (y[i], x[i])
+    sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0]); yy, xx = (np.ascontiguousarray(v.ravel()) for v in np.meshgrid(sp, sp))
+    o2 = np.empty(len(yy)); ok2 = np.empty(len(yy), np.uint8)
+    L.v_atan2_try(P(yy), P(xx), P(o2), P(ok2), len(yy))
+    assert not ok2[(yy == 0) | (xx == 0) | ~np.isfinite(yy) | ~np.isfinite(xx)].any() and ok2[(yy == 1) & (xx == 1)].all()
+    a = np.concatenate([rng.uniform(-np.pi, np.pi, n), 10.0 ** rng.uniform(-12, -1, 20000), [0.0, -0.0, np.pi, -np.pi, np.pi / 2, 2.0 ** -28]])
+    s_ = np.empty(len(a)); c_ = np.empty(len(a)); ok3 = np.empty(len(a), np.uint8); rs = np.empty(len(a)); rc = np.empty(len(a))
+    k = L.v_sincos_try(P(a), P(s_), P(c_), P(ok3), len(a)); L.v_sin(P(a), P(rs), len(a)); L.v_cos(P(a), P(rc), len(a))
+    m = ok3.astype(bool)
+    assert np.array_equal(s_[m].view(np.int64), rs[m].view(np.int64)) and np.array_equal(c_[m].view(np.int64), rc[m].view(np.int64))
+    assert k > 0.99 * len(a)
+    bad = np.array([np.inf, -np.inf, np.nan]); L.v_sincos_try(P(bad), P(s_), P(c_), P(ok3), 3)
+    assert not ok3[:3].any()
+
+
 def test_exp_log_family(L):
     rng = np.random.default_rng(4)
     _check(L.t_exp, mp.exp, np.concatenate([rng.uniform(-745, 709, 800), rng.uniform(-1, 1, 500),
