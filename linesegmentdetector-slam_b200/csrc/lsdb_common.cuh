@@ -81,7 +81,8 @@ __device__ __forceinline__ int lsdb_x86_d2i(double v) {
 
 // launchers (defined in the .cu files, called from api.cu); the stencil launchers return the number of kernels they launched.
 // mode (lsdb_stencil_mode(): LSDB_STENCIL / LSDB_STENCIL_G / LSDB_STENCIL_DEFER read when the batch is created): bits 0-1 the cut
-// (1: stencil.cu, 2: stencil2.cu), bits 2-4 tiles per CTA of stencil2.cu (1, 2, 4), bit 5 deferred pixels into a second kernel.
+// (1: stencil.cu, 2: stencil2.cu), bits 2-4 tiles per CTA of stencil2.cu (1, 2, 4), bit 5 deferred pixels into a second kernel, bits 8.. a cap
+// on the records of the deferred list (0: what the scratch plane holds).
 int lsdb_stencil_mode(void);
 int lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,

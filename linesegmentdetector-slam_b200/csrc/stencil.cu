@@ -384,15 +384,19 @@ int lsdb_stencil_mode(void) {
     e = getenv("LSDB_STENCIL_G");
     int g = e ? atoi(e) : 1;
     if (g != 2 && g != 4) g = 1;
-    e = getenv("LSDB_STENCIL_DEFER");
-    const int defer = !(e && e[0] == '0');
-    return version | (g << 2) | (defer << 5);
+    e = getenv("LSDB_STENCIL_DEFER");   // 0: off; n >= 2: on, the list capped at n records (exercises the overflow path); else: on
+    const int defer = !(e && e[0] == '0' && e[1] == 0);
+    int cap = e ? atoi(e) : 0;
+    if (cap < 2 || cap > (1 << 20)) cap = 0;
+    return version | (g << 2) | (defer << 5) | (cap << 8);
 }
 
 int lsdb_launch_stencil(cudaStream_t s, int nTiles, const LsdbImg* imgs, const int* tileImg, LsdbImgDyn* dyn,
                          const LsdbLsdConst* kc, const uint8_t* src, double* mag, double* deg, double* cosm, double* sinm,
                          unsigned int* state, unsigned int* banBits, unsigned int* nzBits, double* gaussOut, int tileBase,
                          void* deferBuf, size_t deferBytes, int* deferCount, int mode) {
+    const size_t capBytes = (size_t)(mode >> 8) * 24;   // 24 = bytes per deferred record
+    if (capBytes && capBytes < deferBytes) deferBytes = capBytes;
     if ((mode & 3) != 1)
         return lsdb_launch_stencil_v2(s, nTiles, imgs, tileImg, dyn, kc, src, mag, deg, cosm, sinm, state, banBits, nzBits, gaussOut, tileBase,
                                       (mode >> 5) & 1 ? deferBuf : nullptr, deferBytes, deferCount, (mode >> 2) & 7);

@@ -33,6 +33,7 @@
 #define SLOW_CAP 256            // deferred pixels a tile can hold
 
 struct LsdbDeferRec { unsigned long long p; double gx, gy; };   // pixel (index into the planes), gradX, gradY
+static_assert(sizeof(LsdbDeferRec) == 24, "stencil.cu caps the list in records of 24 bytes");
 
 struct __align__(16) Stencil2Smem {
     union {

@@ -251,11 +251,13 @@ def test_result_is_independent_of_team_shape(lsdb, ctx, gold, env):
     b.close()
 
 
-@pytest.mark.parametrize("env", [dict(LSDB_STENCIL="1"), dict(LSDB_STENCIL_DEFER="0"), dict(LSDB_STENCIL_G="2"), dict(LSDB_STENCIL_G="4", LSDB_STENCIL_DEFER="0")])
+@pytest.mark.parametrize("env", [dict(LSDB_STENCIL="1"), dict(LSDB_STENCIL_DEFER="0"), dict(LSDB_STENCIL_G="2"), dict(LSDB_STENCIL_G="4", LSDB_STENCIL_DEFER="0"),
+                                 dict(LSDB_STENCIL_DEFER="5")])
 def test_result_is_independent_of_the_stencil_cut(lsdb, ctx, gold, env):
     """The stencil stage's first cut (stencil.cu, LSDB_STENCIL=1) stays in the library as the fallback of the second
     (stencil2.cu: work lists, phase-1-only angle math, failed rounding tests deferred to a second kernel); the second
-    also runs with the deferred pixels kept in their tiles and with 2 / 4 tiles per CTA.  Same planes, seed lists and
+    also runs with the deferred pixels kept in their tiles, with a deferred list of five records (most tiles' reservations
+    then do not fit: the part inside the list becomes no-ops, the tile evaluates its own) and with 2 / 4 tiles per CTA.  Same planes, seed lists and
     segments as the oracle from every one of them — borders with reflected taps, a ragged 33rd column and row 0 / column 0
     walls included."""
     maps = [gold["mapValue/map"], synth.occupancy_grid(1057, 771, seed=91), synth.occupancy_grid(400, 1300, seed=92, border_walls=True),
