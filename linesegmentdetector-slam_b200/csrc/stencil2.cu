@@ -60,8 +60,7 @@ struct __align__(16) Stencil2Smem {
     unsigned char neRows[LSDB_SRC_MAX];                      // source rows of the window that hold a non-zero pixel
     int qn, qb, qt;
     int geo[6];
-    int nNe, anySrc, nX, nY, nSlow;
-    long long slowBase;
+    int nNe, nX, nY, nSlow;
 };
 static_assert(sizeof(((Stencil2Smem*)0)->u.out) <= sizeof(((Stencil2Smem*)0)->u.aux), "output tiles + queueB must fit the storage of aux");
 static_assert(sizeof(Stencil2Smem) <= 56 * 1024, "four CTAs per SM");
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(NT * G, 4 / G) lsdb_stencil2_kernel(const Lsdb
         S.geo[0] = a0; S.geo[1] = a1; S.geo[2] = b0; S.geo[3] = b1;
         S.geo[4] = (xcA_ - h >= 0 && xcB_ + h < im.cols) ? 1 : 0;   // taps are consecutive source pixels (no reflection at an
         S.geo[5] = (ycA_ - h >= 0 && ycB_ + h < im.rows) ? 1 : 0;   // image border) in x / in y
-        S.qn = 0; S.qb = 0; S.qt = 0; S.nNe = 0; S.anySrc = 0; S.nX = 0; S.nY = 0; S.nSlow = 0; S.slowBase = -1;
+        S.qn = 0; S.qb = 0; S.qt = 0; S.nNe = 0; S.nX = 0; S.nY = 0; S.nSlow = 0;
     }
     __syncthreads();
     const int sx0 = S.geo[0], sx1 = S.geo[1], sy0 = S.geo[2], sy1 = S.geo[3];
@@ -240,7 +239,6 @@ __global__ void __launch_bounds__(NT * G, 4 / G) lsdb_stencil2_kernel(const Lsdb
     // ---- the source window as one bit per pixel, the remap 1->255, 255->0 for y>=1, x>=1 (:135-142) applied
     const uint8_t* win = src + im.srcOff + ax0;   // window column 0 of source row 0
     {
-        unsigned int any = 0;
         // element o of the window = (row o / nVec, vector o % nVec); nVec <= 10 and o < 1360: the quotient by a multiply
         const unsigned int inv = (65536u + (unsigned int)nVec - 1u) / (unsigned int)nVec;
         const int nEl = nRows * nVec;
@@ -257,10 +255,7 @@ __global__ void __launch_bounds__(NT * G, 4 / G) lsdb_stencil2_kernel(const Lsdb
                 }
             }
             const unsigned int nz = st2_nz4(w[0]) | (st2_nz4(w[1]) << 4) | (st2_nz4(w[2]) << 8) | (st2_nz4(w[3]) << 12);
-            if (nz) {
-                atomicOr(&S.rowBits[r * ROW_WORDS + (v >> 1)], nz << ((v & 1) * 16));
-                any = 1;
-            }
+            if (nz) atomicOr(&S.rowBits[r * ROW_WORDS + (v >> 1)], nz << ((v & 1) * 16));
         };
         // two loads in flight per thread before the first is looked at
         for (int o = tid; o < nEl; o += 2 * NT) {
@@ -273,7 +268,6 @@ __global__ void __launch_bounds__(NT * G, 4 / G) lsdb_stencil2_kernel(const Lsdb
             flag(q, r, v);
             flag(q2, r2, v2);
         }
-        (void)any;
     }
     __syncthreads();
 
